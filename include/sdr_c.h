@@ -1,0 +1,196 @@
+/*
+ * sdr_c.h -- C ABI of the B200-native stereo depth engine (libsdr_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of Amar-Aliaga/Stereo_Depth_Ruler:
+ * rectify -> StereoSGBM-compatible disparity (CV_16S, 4 fractional bits) -> reproject
+ * with Q -> coloured VoxelGrid cloud. The reference has no FFI layer of its own; its
+ * "operator API" is three C++ classes plus the OpenCV / PCL free functions they call.
+ * Every entry point below names the reference interface it replaces (file:line in
+ * the reference tree). include/sdr/stereo_vision.hpp is the C++ facade with the
+ * reference's class and method names over this ABI; INTEGRATION.md shows the binding
+ * a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only; every call returns an sdr_status; the
+ * library never throws across the boundary; there is NO CPU fallback -- without a
+ * CUDA device sdr_create fails with SDR_ECUDA and nothing else can be called.
+ * A handle is thread-compatible, not thread-safe: one ctx <-> one device <-> one stream.
+ */
+#ifndef SDR_C_H
+#define SDR_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SDR_API __attribute__((visibility("default")))
+#else
+#define SDR_API
+#endif
+
+typedef enum sdr_status {
+    SDR_OK = 0,
+    SDR_EINVAL = 1,          /* bad argument (cv::Exception on bad args in the reference's OpenCV calls) */
+    SDR_ESIZE = 2,           /* image size / type mismatch (stereo_rectifier.cpp:27-29 only warns) */
+    SDR_ECUDA = 3,           /* CUDA runtime failure or no device */
+    SDR_ENOMEM = 4,
+    SDR_EIO = 5,             /* file could not be read / parsed (stereo_configuration.cpp:6-8,16-19,37-41) */
+    SDR_EVOXEL_OVERFLOW = 6  /* non-fatal: PCL's int32 voxel-index guard tripped, cloud passed through */
+} sdr_status;
+
+typedef enum sdr_mem { SDR_MEM_HOST = 0, SDR_MEM_PINNED = 1, SDR_MEM_DEVICE = 2 } sdr_mem;
+
+/* Layout-compatible with the fields of cv::Mat the reference relies on
+ * {data, rows, cols, step, type}; rows may be non-contiguous (the SBS ROI views of
+ * stereo_displayer.cpp:155-156). */
+typedef struct sdr_image {
+    void* data;
+    int rows, cols, channels, elem_size; /* elem_size: bytes per channel element (1 = u8, 2 = s16, 4 = f32) */
+    size_t step_bytes;
+    int mem; /* sdr_mem */
+} sdr_image;
+
+/* StereoConfiguration (stereo_vision/include/stereo_configuration.hpp:6-16), row-major fp64. */
+typedef struct sdr_calibration {
+    int image_width, image_height;
+    double K_left[9], dist_left[5], K_right[9], dist_right[5];
+    double R[9], T[3], E[9], F[9];
+    double R1[9], R2[9], P1[12], P2[12], Q[16];
+    uint32_t present; /* bit i set when field i (order above, K_left = bit 0) was found in the file */
+} sdr_calibration;
+
+/* Same order and meaning as cv::StereoSGBM::create(...) at stereo_disparity.cpp:5-6 /
+ * pcd_write.cpp:102-108. */
+typedef enum sdr_sgbm_mode { SDR_MODE_SGBM = 0, SDR_MODE_HH = 1, SDR_MODE_SGBM_3WAY = 2 } sdr_sgbm_mode;
+typedef struct sdr_sgbm_params {
+    int minDisparity, numDisparities, blockSize, P1, P2, disp12MaxDiff;
+    int preFilterCap, uniquenessRatio, speckleWindowSize, speckleRange, mode;
+} sdr_sgbm_params;
+
+typedef struct sdr_ctx sdr_ctx;
+typedef struct sdr_rectifier sdr_rectifier;
+typedef struct sdr_sgbm sdr_sgbm;
+typedef struct sdr_cloud sdr_cloud;
+typedef struct sdr_pipeline sdr_pipeline;
+
+/* ---- context ----------------------------------------------------------------- */
+SDR_API const char* sdr_version(void);
+SDR_API int sdr_device_count(void);
+SDR_API int sdr_create(int device, sdr_ctx** ctx);
+SDR_API void sdr_destroy(sdr_ctx* ctx);
+/* Run on a caller-owned CUDA stream (a cudaStream_t passed as void*); NULL restores the ctx's own stream. */
+SDR_API int sdr_set_stream(sdr_ctx* ctx, void* cuda_stream);
+SDR_API void* sdr_get_stream(sdr_ctx* ctx);
+SDR_API int sdr_synchronize(sdr_ctx* ctx);
+SDR_API const char* sdr_last_error(sdr_ctx* ctx);
+/* Number of this library's kernels launched through ctx since creation. */
+SDR_API uint64_t sdr_kernel_launches(sdr_ctx* ctx);
+
+/* ---- calibration: StereoConfiguration::loadFromFile / saveToFile / isValid
+ *      (stereo_configuration.cpp:4-46, :49-74, :77-80). OpenCV-dialect YAML 1.0. ---- */
+SDR_API int sdr_load_calibration_yaml(const char* path, sdr_calibration* out);
+SDR_API int sdr_save_calibration_yaml(const char* path, const sdr_calibration* in);
+SDR_API int sdr_calibration_is_valid(const sdr_calibration* c);
+
+/* ---- rectification: StereoRectifier ctor + rectify (stereo_rectifier.cpp:6-14, :17-41) ---- */
+SDR_API int sdr_rectifier_create(sdr_ctx* ctx, const sdr_calibration* calib, sdr_rectifier** out);
+SDR_API void sdr_rectifier_destroy(sdr_rectifier* r);
+/* eye 0 = left, 1 = right. map1: int16[H][W][2], map2: uint16[H][W] (host), exactly what
+ * cv::initUndistortRectifyMap(..., CV_16SC2, map1, map2) returns. */
+SDR_API int sdr_rectifier_get_maps(sdr_rectifier* r, int eye, int16_t* map1, uint16_t* map2);
+/* left_src/right_src: u8 BGR (3 ch) or gray (1 ch); *_dst same type; *_gray optional (NULL) u8 1-ch
+ * outputs = cvtColor(dst, BGR2GRAY) fused into the same kernel (stereo_disparity.cpp:19-20). */
+SDR_API int sdr_rectify(sdr_rectifier* r, const sdr_image* left_src, const sdr_image* right_src,
+                        sdr_image* left_dst, sdr_image* right_dst, sdr_image* left_gray, sdr_image* right_gray);
+/* cv::remap(src, dst, map1, map2, INTER_LINEAR) with caller-supplied CV_16SC2 maps (host pointers). */
+SDR_API int sdr_remap_with_maps(sdr_ctx* ctx, const sdr_image* src, const int16_t* map1, const uint16_t* map2,
+                                sdr_image* dst);
+/* cv::cvtColor(BGR2GRAY) (stereo_disparity.cpp:19-20, pcd_write.cpp:88-89). */
+SDR_API int sdr_bgr2gray(sdr_ctx* ctx, const sdr_image* bgr, sdr_image* gray);
+
+/* ---- disparity: cv::StereoSGBM::create + compute (stereo_disparity.cpp:5-6,27; pcd_write.cpp:102-111) ---- */
+SDR_API int sdr_sgbm_create(sdr_ctx* ctx, const sdr_sgbm_params* params, sdr_sgbm** out);
+SDR_API void sdr_sgbm_destroy(sdr_sgbm* m);
+/* left/right: u8 1-ch, same size. disp: int16 1-ch (CV_16S, disparity * 16; invalid = (minD-1)*16).
+ * Includes the medianBlur(3) and filterSpeckles that StereoSGBM::compute applies internally. */
+SDR_API int sdr_sgbm_compute(sdr_sgbm* m, const sdr_image* left, const sdr_image* right, sdr_image* disp);
+/* n independent pairs of one size in one submission (frame-parallel batch; frames share no state). */
+SDR_API int sdr_sgbm_compute_batch(sdr_sgbm* m, int n, const sdr_image* lefts, const sdr_image* rights,
+                                   sdr_image* disps);
+/* Per-kernel device times (ms) of the last compute, measured with CUDA events on the ctx stream.
+ * Enable first; names[i] point to static strings. Returns the number of stages written (<= cap). */
+SDR_API int sdr_sgbm_set_profiling(sdr_sgbm* m, int enabled);
+SDR_API int sdr_sgbm_stage_times(sdr_sgbm* m, int cap, const char** names, float* ms);
+/* Test hook: copy an internal buffer of the last single-frame compute to host.
+ * what: 0 = C volume int16 [rowsC][W1][D] (without the +P2 bias), 1 = S volume int16 [H][W1][D],
+ * 2 = raw matcher output int16 [H][W] (before median / speckle). */
+SDR_API int sdr_sgbm_debug_read(sdr_sgbm* m, int what, void* host_dst, size_t bytes);
+
+/* cv::medianBlur(disp, 3) on CV_16S and cv::filterSpeckles, as StereoSGBM::compute chains them. */
+SDR_API int sdr_median3_16s(sdr_ctx* ctx, const sdr_image* src, sdr_image* dst);
+SDR_API int sdr_filter_speckles(sdr_ctx* ctx, sdr_image* img, int new_val, int max_size, int max_diff);
+
+/* ---- depth: convertTo(CV_32F, 1/16) + cv::reprojectImageTo3D
+ *      (stereo_disparity.cpp:34,76-80; pcd_write.cpp:112,116) ---- */
+/* disp: int16 (CV_16S, divided by 16 internally, i.e. convertTo + reproject fused) or f32 (used as is).
+ * Q: 16 doubles row-major. points: f32 3-ch. */
+SDR_API int sdr_reproject_to_3d(sdr_ctx* ctx, const sdr_image* disp, const double* Q, int handle_missing,
+                                sdr_image* points);
+
+/* ---- cloud: convertCVMatToPCL + pcl::VoxelGrid<PointXYZRGB> (pcd_write.cpp:17-51, :123-130) ---- */
+typedef struct sdr_voxel_options {
+    float leaf[3];
+    int drop_invalid;  /* 0: literal reference semantics (every finite point, incl. the Z=10000 fill of
+                          handleMissingValues); 1: drop points whose disparity is invalid (<= (minD-1)) first */
+    float z_max;       /* > 0: also drop points with z > z_max (or z <= 0); 0 = off */
+    int min_disparity; /* used by drop_invalid */
+} sdr_voxel_options;
+
+typedef struct sdr_cloud_view {
+    int64_t n;          /* number of output points */
+    const float* xyz;   /* DEVICE pointer, f32[n][3] */
+    const uint8_t* rgb; /* DEVICE pointer, u8[n][3] (r,g,b) */
+    const uint32_t* idx;/* DEVICE pointer, voxel linear index per output point (ascending); NULL on passthrough */
+    const uint32_t* cnt;/* DEVICE pointer, points per voxel; NULL on passthrough */
+    int32_t min_b[3], div_b[3];
+    int passthrough;    /* 1 when the int32 guard tripped (status SDR_EVOXEL_OVERFLOW): cloud = finite input points */
+} sdr_cloud_view;
+
+SDR_API int sdr_cloud_create(sdr_ctx* ctx, sdr_cloud** out);
+SDR_API void sdr_cloud_destroy(sdr_cloud* c);
+/* points: f32 3-ch [H][W]; bgr: u8 3-ch (or NULL: colours 0); disp16: optional int16 disparity for
+ * drop_invalid (may be NULL when drop_invalid == 0). */
+SDR_API int sdr_voxelgrid(sdr_cloud* c, const sdr_image* points, const sdr_image* bgr, const sdr_image* disp16,
+                          const sdr_voxel_options* opt, sdr_cloud_view* view);
+/* Fused reprojectImageTo3D + voxelisation straight from the CV_16S disparity (no W*H*3 float image in HBM). */
+SDR_API int sdr_depth_cloud(sdr_cloud* c, const sdr_image* disp16, const sdr_image* bgr, const double* Q,
+                            int handle_missing, const sdr_voxel_options* opt, sdr_cloud_view* view);
+/* Copy the last cloud to host buffers (any may be NULL). */
+SDR_API int sdr_cloud_download(sdr_cloud* c, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt);
+
+/* ---- whole path per frame (stereo_displayer.cpp:155-162 + pcd_write.cpp:82-130) ---- */
+typedef struct sdr_pipeline_options {
+    sdr_sgbm_params sgbm;
+    sdr_voxel_options voxel;
+    int handle_missing; /* reprojectImageTo3D(..., handleMissingValues) */
+    int batch;          /* frames per submission (>= 1) */
+    int want_points;    /* also materialise the W*H*3 float image (computeDepth) */
+} sdr_pipeline_options;
+
+SDR_API int sdr_pipeline_create(sdr_ctx* ctx, const sdr_calibration* calib, const sdr_pipeline_options* opt,
+                                sdr_pipeline** out);
+SDR_API void sdr_pipeline_destroy(sdr_pipeline* p);
+/* sbs: n side-by-side BGR frames (u8 3-ch, cols = 2*image_width). Outputs (each optional / NULL):
+ * disp[n] int16 1-ch, points[n] f32 3-ch, left_rect[n] u8 3-ch. views[n] receives the clouds
+ * (valid until the next run). */
+SDR_API int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sdr_image* disp, sdr_image* points,
+                             sdr_image* left_rect, sdr_cloud_view* views);
+SDR_API int sdr_pipeline_stage_times(sdr_pipeline* p, int cap, const char** names, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDR_C_H */

@@ -83,21 +83,21 @@ def bgr2gray(bgr):
 
 
 def sgbm_match(left, right, params, want_volumes=False):
-    """Raw matcher output (before median/speckle). Optionally the C (+P2) and S volumes."""
+    """Raw matcher output (before median/speckle). Optionally the C (+P2), final S and pre-WTA S volumes."""
     left = np.ascontiguousarray(left); right = np.ascontiguousarray(right)
     H, W = left.shape
     disp = np.empty((H, W), np.int16)
-    Cv = Sv = None
+    Cv = Sv = Sp = None
     if want_volumes:
         D = params.numDisparities
         minX1 = max(params.minDisparity + D, 0); maxX1 = W + min(params.minDisparity, 0)
         W1 = max(maxX1 - minX1, 0)
-        Cv = np.zeros((H, W1, D), np.int16); Sv = np.zeros((H, W1, D), np.int16)
+        Cv = np.zeros((H, W1, D), np.int16); Sv = np.zeros((H, W1, D), np.int16); Sp = np.zeros((H, W1, D), np.int16)
     rc = lib().orc_sgbm_match(_p(left), C.c_size_t(W), _p(right), C.c_size_t(W), W, H, C.byref(params),
-                              _p(disp), _p(Cv), _p(Sv))
+                              _p(disp), _p(Cv), _p(Sv), _p(Sp))
     if rc:
         raise ValueError("orc_sgbm_match rc=%d" % rc)
-    return (disp, Cv, Sv) if want_volumes else disp
+    return (disp, Cv, Sv, Sp) if want_volumes else disp
 
 
 def sgbm_compute(left, right, params):

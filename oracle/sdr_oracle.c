@@ -313,7 +313,7 @@ static inline int path_update(const int16_t* C, const int16_t* prev, int minPrev
 /* ------------------------------------------------------------------------- */
 static int sgbm_full(const uint8_t* left, size_t lstep, const uint8_t* right, size_t rstep, int W, int H,
                      const orc_sgbm_params* p, int16_t* disp, size_t dstep_elems,
-                     int16_t* Cvol_out, int16_t* Svol_out) {
+                     int16_t* Cvol_out, int16_t* Svol_out, int16_t* Spre_out) {
     const int minD = p->minDisparity, D = p->numDisparities;
     const int uq = p->uniquenessRatio >= 0 ? p->uniquenessRatio : 10;
     const int d12 = p->disp12MaxDiff > 0 ? p->disp12MaxDiff : 1;
@@ -385,6 +385,7 @@ static int sgbm_full(const uint8_t* left, size_t lstep, const uint8_t* right, si
                 for (int d = 0; d < D; d++) Sp[d] = sat16(Sp[d] + L0[d] + L1[d] + L2[d] + L3[d]);
             }
             if (pass == npasses) {
+                if (Spre_out) memcpy(Spre_out + row * y, S, row * sizeof(int16_t)); /* S before the R->L path / WTA */
                 if (npasses == 1) {
                     /* 5th path, right-to-left on the same row, right border zero */
                     int16_t* prev = L4; int16_t* curL = L4 + D;
@@ -562,20 +563,21 @@ static int check_params(const orc_sgbm_params* p, int W, int H) {
     return 0;
 }
 
-/* raw matcher output (no median, no speckle); optional C / S volume dumps for MODE_SGBM / MODE_HH */
+/* raw matcher output (no median, no speckle); optional C / final S / pre-WTA S volume dumps (MODE_SGBM / MODE_HH) */
 ORC_API int orc_sgbm_match(const uint8_t* left, size_t lstep, const uint8_t* right, size_t rstep, int W, int H,
-                           const orc_sgbm_params* p, int16_t* disp, int16_t* Cvol_out, int16_t* Svol_out) {
+                           const orc_sgbm_params* p, int16_t* disp, int16_t* Cvol_out, int16_t* Svol_out,
+                           int16_t* Spre_out) {
     int rc = check_params(p, W, H);
     if (rc) return rc;
     if (p->mode == ORC_MODE_SGBM_3WAY) return sgbm_3way(left, lstep, right, rstep, W, H, p, disp, (size_t)W);
-    return sgbm_full(left, lstep, right, rstep, W, H, p, disp, (size_t)W, Cvol_out, Svol_out);
+    return sgbm_full(left, lstep, right, rstep, W, H, p, disp, (size_t)W, Cvol_out, Svol_out, Spre_out);
 }
 
 ORC_API int orc_sgbm_compute(const uint8_t* left, size_t lstep, const uint8_t* right, size_t rstep, int W, int H,
                              const orc_sgbm_params* p, int16_t* disp) {
     int16_t* raw = (int16_t*)malloc((size_t)W * H * sizeof(int16_t));
     if (!raw) return -1;
-    int rc = orc_sgbm_match(left, lstep, right, rstep, W, H, p, raw, NULL, NULL);
+    int rc = orc_sgbm_match(left, lstep, right, rstep, W, H, p, raw, NULL, NULL, NULL);
     if (rc) { free(raw); return rc; }
     orc_median3_16s(raw, (size_t)W, W, H, disp, (size_t)W);
     free(raw);

@@ -1,0 +1,271 @@
+"""ctypes binding of the C ABI in include/sdr_c.h (libsdr_b200.so).
+
+There is no CPU fallback: if the CUDA library is missing or no B200 is visible every
+compute entry point raises. Images may be numpy arrays (host memory) or torch CUDA tensors
+(device memory, used in place).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsdr_b200.so")
+
+SDR_OK, SDR_EINVAL, SDR_ESIZE, SDR_ECUDA, SDR_ENOMEM, SDR_EIO, SDR_EVOXEL_OVERFLOW = range(7)
+MEM_HOST, MEM_PINNED, MEM_DEVICE = 0, 1, 2
+MODE_SGBM, MODE_HH, MODE_SGBM_3WAY = 0, 1, 2
+
+_STATUS = {0: "SDR_OK", 1: "SDR_EINVAL", 2: "SDR_ESIZE", 3: "SDR_ECUDA", 4: "SDR_ENOMEM", 5: "SDR_EIO",
+           6: "SDR_EVOXEL_OVERFLOW"}
+
+
+class SdrError(RuntimeError):
+    def __init__(self, status, msg=""):
+        self.status = status
+        super().__init__("%s: %s" % (_STATUS.get(status, status), msg))
+
+
+class Image(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int), ("channels", C.c_int),
+                ("elem_size", C.c_int), ("step_bytes", C.c_size_t), ("mem", C.c_int)]
+
+
+class Calibration(C.Structure):
+    _fields_ = [("image_width", C.c_int), ("image_height", C.c_int),
+                ("K_left", C.c_double * 9), ("dist_left", C.c_double * 5),
+                ("K_right", C.c_double * 9), ("dist_right", C.c_double * 5),
+                ("R", C.c_double * 9), ("T", C.c_double * 3), ("E", C.c_double * 9), ("F", C.c_double * 9),
+                ("R1", C.c_double * 9), ("R2", C.c_double * 9), ("P1", C.c_double * 12), ("P2", C.c_double * 12),
+                ("Q", C.c_double * 16), ("present", C.c_uint32)]
+
+    def mat(self, name):
+        shape = {"K_left": (3, 3), "K_right": (3, 3), "dist_left": (1, 5), "dist_right": (1, 5), "R": (3, 3),
+                 "T": (3, 1), "E": (3, 3), "F": (3, 3), "R1": (3, 3), "R2": (3, 3), "P1": (3, 4), "P2": (3, 4),
+                 "Q": (4, 4)}[name]
+        return np.array(getattr(self, name), np.float64).reshape(shape)
+
+
+class SgbmParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "minDisparity", "numDisparities", "blockSize", "P1", "P2", "disp12MaxDiff",
+        "preFilterCap", "uniquenessRatio", "speckleWindowSize", "speckleRange", "mode")]
+
+
+class VoxelOptions(C.Structure):
+    _fields_ = [("leaf", C.c_float * 3), ("drop_invalid", C.c_int), ("z_max", C.c_float), ("min_disparity", C.c_int)]
+
+
+class CloudView(C.Structure):
+    _fields_ = [("n", C.c_int64), ("xyz", C.c_void_p), ("rgb", C.c_void_p), ("idx", C.c_void_p), ("cnt", C.c_void_p),
+                ("min_b", C.c_int32 * 3), ("div_b", C.c_int32 * 3), ("passthrough", C.c_int)]
+
+
+class PipelineOptions(C.Structure):
+    _fields_ = [("sgbm", SgbmParams), ("voxel", VoxelOptions), ("handle_missing", C.c_int), ("batch", C.c_int),
+                ("want_points", C.c_int)]
+
+
+# every symbol include/sdr_c.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "sdr_version", "sdr_device_count", "sdr_create", "sdr_destroy", "sdr_set_stream", "sdr_get_stream",
+    "sdr_synchronize", "sdr_last_error", "sdr_kernel_launches",
+    "sdr_load_calibration_yaml", "sdr_save_calibration_yaml", "sdr_calibration_is_valid",
+    "sdr_rectifier_create", "sdr_rectifier_destroy", "sdr_rectifier_get_maps", "sdr_rectify",
+    "sdr_remap_with_maps", "sdr_bgr2gray",
+    "sdr_sgbm_create", "sdr_sgbm_destroy", "sdr_sgbm_compute", "sdr_sgbm_compute_batch",
+    "sdr_sgbm_set_profiling", "sdr_sgbm_stage_times", "sdr_sgbm_debug_read",
+    "sdr_median3_16s", "sdr_filter_speckles", "sdr_reproject_to_3d",
+    "sdr_cloud_create", "sdr_cloud_destroy", "sdr_voxelgrid", "sdr_depth_cloud", "sdr_cloud_download",
+    "sdr_pipeline_create", "sdr_pipeline_destroy", "sdr_pipeline_run", "sdr_pipeline_stage_times",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads libsdr_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SdrError(SDR_ECUDA, "%s is missing: run `python -m stereo_depth_ruler_b200.build` "
+                                      "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.sdr_version.restype = C.c_char_p
+        L.sdr_last_error.restype = C.c_char_p
+        L.sdr_last_error.argtypes = [C.c_void_p]
+        L.sdr_get_stream.restype = C.c_void_p
+        L.sdr_get_stream.argtypes = [C.c_void_p]
+        L.sdr_kernel_launches.restype = C.c_uint64
+        L.sdr_kernel_launches.argtypes = [C.c_void_p]
+        L.sdr_destroy.argtypes = [C.c_void_p]
+        L.sdr_destroy.restype = None
+        for n in ("sdr_rectifier_destroy", "sdr_sgbm_destroy", "sdr_cloud_destroy", "sdr_pipeline_destroy"):
+            if hasattr(L, n):
+                getattr(L, n).argtypes = [C.c_void_p]
+                getattr(L, n).restype = None
+        _lib = L
+    return _lib
+
+
+def make_params(minDisparity=0, numDisparities=128, blockSize=5, P1=600, P2=2400, disp12MaxDiff=1,
+                preFilterCap=63, uniquenessRatio=12, speckleWindowSize=200, speckleRange=2, mode=MODE_SGBM):
+    """Same positional order as cv::StereoSGBM::create (stereo_disparity.cpp:5-6)."""
+    return SgbmParams(minDisparity, numDisparities, blockSize, P1, P2, disp12MaxDiff, preFilterCap,
+                      uniquenessRatio, speckleWindowSize, speckleRange, mode)
+
+
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+_NP_ELEM = {np.dtype(np.uint8): 1, np.dtype(np.int16): 2, np.dtype(np.uint16): 2, np.dtype(np.float32): 4}
+
+
+def as_image(a, channels=None):
+    """numpy array / torch tensor [H][W] or [H][W][C] -> (Image, keepalive)."""
+    if isinstance(a, Image):
+        return a, a
+    if _is_torch(a):
+        assert a.is_cuda, "torch tensors must live on the GPU (host data: pass numpy)"
+        es = a.element_size()
+        shape, strides = tuple(a.shape), tuple(s * es for s in a.stride())
+        ptr, mem = a.data_ptr(), MEM_DEVICE
+    else:
+        assert isinstance(a, np.ndarray) and a.dtype in _NP_ELEM, "unsupported array %r" % (type(a),)
+        es = a.dtype.itemsize
+        shape, strides = a.shape, a.strides
+        ptr, mem = a.ctypes.data, MEM_HOST
+    if len(shape) == 2:
+        H, W = shape
+        ch = 1
+        assert strides[1] == es
+    else:
+        H, W, ch = shape
+        assert strides[2] == es and strides[1] == es * ch, "pixels must be packed"
+    if channels is not None:
+        assert ch == channels, "expected %d channels, got %d" % (channels, ch)
+    return Image(ptr, H, W, ch, es, strides[0], mem), a
+
+
+class Context:
+    """One device, one stream (sdr_create / sdr_destroy)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().sdr_create(int(device), C.byref(self._h))
+        if rc != SDR_OK:
+            raise SdrError(rc, "sdr_create(device=%d) failed: no usable sm_100 CUDA device (no CPU fallback)" % device)
+        self.device = device
+
+    def check(self, rc, ok=(SDR_OK,)):
+        if rc not in ok:
+            raise SdrError(rc, (lib().sdr_last_error(self._h) or b"").decode())
+        return rc
+
+    def set_stream(self, cuda_stream_ptr):
+        self.check(lib().sdr_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self.check(lib().sdr_synchronize(self._h))
+
+    @property
+    def kernel_launches(self):
+        return int(lib().sdr_kernel_launches(self._h))
+
+    def close(self):
+        if self._h:
+            lib().sdr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def load_calibration(path):
+    c = Calibration()
+    rc = lib().sdr_load_calibration_yaml(str(path).encode(), C.byref(c))
+    if rc != SDR_OK:
+        raise SdrError(rc, "could not load calibration %s" % path)
+    return c
+
+
+def save_calibration(path, calib):
+    rc = lib().sdr_save_calibration_yaml(str(path).encode(), C.byref(calib))
+    if rc != SDR_OK:
+        raise SdrError(rc, "could not save calibration %s" % path)
+
+
+class Sgbm:
+    """cv::StereoSGBM stand-in (sdr_sgbm_*)."""
+
+    def __init__(self, ctx, params):
+        self.ctx = ctx
+        self.params = params
+        self._h = C.c_void_p()
+        ctx.check(lib().sdr_sgbm_create(ctx._h, C.byref(params), C.byref(self._h)))
+
+    def compute(self, left, right, out=None):
+        li, k1 = as_image(left, 1)
+        ri, k2 = as_image(right, 1)
+        if out is None:
+            if _is_torch(left):
+                import torch
+                out = torch.empty(tuple(left.shape), dtype=torch.int16, device=left.device)
+            else:
+                out = np.empty(left.shape, np.int16)
+        oi, k3 = as_image(out, 1)
+        self.ctx.check(lib().sdr_sgbm_compute(self._h, C.byref(li), C.byref(ri), C.byref(oi)))
+        return out
+
+    def compute_batch(self, lefts, rights, outs):
+        """lefts/rights/outs: [B][H][W] arrays (numpy or torch cuda)."""
+        n = len(lefts)
+        L = (Image * n)(*[as_image(lefts[i], 1)[0] for i in range(n)])
+        R = (Image * n)(*[as_image(rights[i], 1)[0] for i in range(n)])
+        O = (Image * n)(*[as_image(outs[i], 1)[0] for i in range(n)])
+        self.ctx.check(lib().sdr_sgbm_compute_batch(self._h, n, L, R, O))
+        return outs
+
+    def set_profiling(self, on=True):
+        lib().sdr_sgbm_set_profiling(self._h, int(on))
+
+    def stage_times(self):
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        n = lib().sdr_sgbm_stage_times(self._h, 64, names, ms)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
+    def debug_read(self, what, shape):
+        out = np.empty(shape, np.int16)
+        self.ctx.check(lib().sdr_sgbm_debug_read(self._h, int(what), out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes)))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().sdr_sgbm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def median3_16s(ctx, src):
+    out = np.empty_like(src)
+    si, _ = as_image(src, 1)
+    oi, _ = as_image(out, 1)
+    ctx.check(lib().sdr_median3_16s(ctx._h, C.byref(si), C.byref(oi)))
+    return out
+
+
+def filter_speckles(ctx, img, new_val, max_size, max_diff):
+    out = np.ascontiguousarray(img, np.int16).copy()
+    ii, _ = as_image(out, 1)
+    ctx.check(lib().sdr_filter_speckles(ctx._h, C.byref(ii), int(new_val), int(max_size), int(max_diff)))
+    return out

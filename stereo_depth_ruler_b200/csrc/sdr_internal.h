@@ -1,0 +1,94 @@
+// Internal declarations shared by the translation units of libsdr_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "sdr_c.h"
+
+struct sdr_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+};
+
+#define SDR_FAIL(ctx, code, ...) (sdr_set_error((ctx), __VA_ARGS__), (int)(code))
+void sdr_set_error(sdr_ctx* ctx, const char* fmt, ...);
+
+#define SDR_CUDA(ctx, expr)                                                                          \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return SDR_FAIL(ctx, SDR_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                            __FILE__, __LINE__);                                                     \
+    } while (0)
+
+// Checks the launch and counts it.
+#define SDR_LAUNCHED(ctx)                                                                            \
+    do {                                                                                             \
+        (ctx)->launches++;                                                                           \
+        cudaError_t _e = cudaGetLastError();                                                         \
+        if (_e != cudaSuccess)                                                                       \
+            return SDR_FAIL(ctx, SDR_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                            __FILE__, __LINE__);                                                     \
+    } while (0)
+
+// Growable device buffer owned by a handle (allocated at first use, reused across frames).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(sdr_ctx* ctx, size_t bytes);
+    void release();
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(sdr_ctx* ctx, size_t bytes);
+    void release();
+};
+
+// A device-side 2-D view. pitch in bytes.
+struct DevView {
+    uint8_t* p = nullptr;
+    size_t pitch = 0;
+};
+
+int sdr_check_image(sdr_ctx* ctx, const sdr_image* im, int channels, int elem_size, const char* what);
+// Input: returns a device view of `im` (copying host memory into `scratch` on the ctx stream when needed).
+int sdr_stage_in(sdr_ctx* ctx, const sdr_image* im, DevBuf& scratch, DevView* out);
+// Output: device view to write into; for host images it points into `scratch` and sdr_stage_out copies back.
+int sdr_stage_out_begin(sdr_ctx* ctx, const sdr_image* im, DevBuf& scratch, DevView* out);
+int sdr_stage_out_end(sdr_ctx* ctx, const sdr_image* im, const DevView& v);
+
+static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// ---- kernels exposed across translation units (host launchers) ----
+int sdr_launch_median3(sdr_ctx* ctx, const int16_t* src, size_t spitch, int16_t* dst, size_t dpitch, int W, int H,
+                       int batch, size_t sframe, size_t dframe);
+
+struct SpeckleScratch {
+    DevBuf parent, count;
+};
+int sdr_launch_speckle(sdr_ctx* ctx, int16_t* img, size_t pitch, int W, int H, int batch, size_t frame_bytes,
+                       int new_val, int max_size, int max_diff, SpeckleScratch& s);
+
+struct StageTimer {
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char*> names;
+    bool enabled = false;
+    size_t n = 0;
+    void begin(cudaStream_t s);
+    void mark(cudaStream_t s, const char* name);
+    int collect(int cap, const char** out_names, float* ms);
+    void release();
+};

@@ -1,0 +1,835 @@
+// Semi-global block matching for sm_100a, bit-exact with cv::StereoSGBM::compute
+// (the call at stereo_vision/src/stereo_disparity.cpp:27 and point_cloud/src/pcd_write.cpp:111
+// of the reference). Stages:
+//   k_prefilter   Sobel-x clip + raw channel, Birchfield-Tomasi half-sample intervals
+//   k_cost        BT pixel cost -> (2*SH2+1)x(2*SW2+1) box sum -> C volume [rows][W1][D] int16
+//   k_path_v      vertical / diagonal path aggregation (chains wrap around the row so every
+//                 chain is H steps long), S (+)= L
+//   k_path_h      horizontal paths; the last one keeps S in registers and runs WTA,
+//                 uniqueness and the sub-pixel parabola
+//   k_lrcheck     right-view disparity by keyed atomicMin (cost, then largest x) + LR check
+// All cost arithmetic is packed int16x2 on the DPX/video integer units (VIADD.16x2,
+// VIMNMX.S16x2, VIMNMX3, VIADDMNMX[.RELU]); a chain owns D disparities spread over G lanes.
+#include "sdr_internal.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace {
+
+struct Seg {
+    int src_start, src_end, dst_start, crow0;
+};
+
+struct Geom {
+    int W, H, D, minD, W1, minX1, maxX1;
+    int nseg, crows;
+    Seg seg[4];
+    int SW2, SH2, P1, P2, ftzero, uq, d12, three_way;
+    int Wp;  // padded width of the right-image byte planes
+};
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+__device__ __forceinline__ uint32_t dup_lo(uint32_t a) { return __byte_perm(a, a, 0x1010); }
+__device__ __forceinline__ uint32_t dup_hi(uint32_t a) { return __byte_perm(a, a, 0x3232); }
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+
+// ------------------------------------------------------------------------------------------
+// Prefilter. LEFT: one int4 per pixel = packed int16 {-u, u-255, -u1, u0-255} for the Sobel
+// channel (.x,.y) and the raw channel (.z,.w). RIGHT: byte planes (v, lo, 255-hi) x 2 channels
+// stored reversed (index W-1-x, so that disparity runs forward in memory) in 4 copies shifted by
+// 0..3 bytes so that any run of 4 disparities is one aligned 32-bit load.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefilt_px(const uint8_t* img, size_t pitch, int W, int H, int x, int y, int ft,
+                                           int& s, int& r) {
+    if (x <= 0 || x >= W - 1) {
+        s = ft;
+        r = ft;
+        return;
+    }
+    const uint8_t* r0 = img + (size_t)y * pitch;
+    const uint8_t* rn = img + (size_t)max(y - 1, 0) * pitch;
+    const uint8_t* rs = img + (size_t)min(y + 1, H - 1) * pitch;
+    int v = 2 * ((int)r0[x + 1] - (int)r0[x - 1]) + (int)rn[x + 1] - (int)rn[x - 1] + (int)rs[x + 1] - (int)rs[x - 1];
+    s = min(max(v, -ft), ft) + ft;
+    r = r0[x];
+}
+
+__global__ void __launch_bounds__(128) k_prefilter(Geom g, const uint8_t* left, size_t lpitch, size_t lframe,
+                                                   const uint8_t* right, size_t rpitch, size_t rframe, int4* PL,
+                                                   uint8_t* PR) {
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    const int y = blockIdx.y;
+    const int b = blockIdx.z >> 1, eye = blockIdx.z & 1;
+    if (x >= g.W) return;
+    const uint8_t* img = eye ? right + (size_t)b * rframe : left + (size_t)b * lframe;
+    const size_t pitch = eye ? rpitch : lpitch;
+    int s[3], r[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        int xx = x + i - 1;
+        if (xx >= 0 && xx < g.W)
+            prefilt_px(img, pitch, g.W, g.H, xx, y, g.ftzero, s[i], r[i]);
+        else {
+            s[i] = 0;  // never used: the x > 0 / x < W-1 guards below skip missing neighbours
+            r[i] = 0;
+        }
+    }
+    int lo[2], hi[2], v[2];
+    v[0] = s[1];
+    v[1] = r[1];
+    {
+        int vl = x > 0 ? (s[1] + s[0]) / 2 : s[1];
+        int vr = x < g.W - 1 ? (s[1] + s[2]) / 2 : s[1];
+        lo[0] = min(min(vl, vr), s[1]);
+        hi[0] = max(max(vl, vr), s[1]);
+        vl = x > 0 ? (r[1] + r[0]) / 2 : r[1];
+        vr = x < g.W - 1 ? (r[1] + r[2]) / 2 : r[1];
+        lo[1] = min(min(vl, vr), r[1]);
+        hi[1] = max(max(vl, vr), r[1]);
+    }
+    if (eye == 0) {
+        int4 o;
+        o.x = (int)pack16(-v[0], v[0] - 255);
+        o.y = (int)pack16(-hi[0], lo[0] - 255);
+        o.z = (int)pack16(-v[1], v[1] - 255);
+        o.w = (int)pack16(-hi[1], lo[1] - 255);
+        PL[((size_t)b * g.H + y) * g.W + x] = o;
+    } else {
+        uint8_t* row = PR + ((size_t)b * g.H + y) * 24 * g.Wp;
+        const int j = g.W - 1 - x;
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
+            const uint8_t val[3] = {(uint8_t)v[ch], (uint8_t)lo[ch], (uint8_t)(255 - hi[ch])};
+#pragma unroll
+            for (int pl = 0; pl < 3; pl++)
+#pragma unroll
+                for (int sft = 0; sft < 4; sft++) {
+                    int i = j - sft;
+                    if (i >= 0) row[((ch * 3 + pl) * 4 + sft) * g.Wp + i] = val[pl];
+                }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Cost volume. One CTA = TX columns (cost space) x RB rows of one segment. Per image row the
+// CTA evaluates the BT cost for TX+2*SW2 columns x D disparities into a shared-memory ring of
+// 2*SH2+1 rows (u8), sums the ring vertically into Vs (u16), then horizontally into C.
+// ------------------------------------------------------------------------------------------
+constexpr int COST_TX = 32;
+constexpr int COST_RB = 32;
+constexpr int COST_THREADS = 256;
+
+__device__ __forceinline__ void bt_item(const Geom& g, const int4* __restrict__ PLrow, const uint8_t* __restrict__ PRrow,
+                                        int ximg, int q, uint32_t& out0, uint32_t& out1) {
+    const int4 k = __ldg(PLrow + ximg);
+    const int j0 = (g.W - 1 - ximg) + g.minD + 8 * q;
+    const int a = j0 & 3, off = j0 - a;
+    uint32_t acc[4];
+#pragma unroll
+    for (int ch = 0; ch < 2; ch++) {
+        const uint32_t kx = ch ? (uint32_t)k.z : (uint32_t)k.x, ky = ch ? (uint32_t)k.w : (uint32_t)k.y;
+        const uint32_t negU = dup_lo(kx), Um = dup_hi(kx), negU1 = dup_lo(ky), U0m = dup_hi(ky);
+        const uint8_t* pv = PRrow + ((ch * 3 + 0) * 4 + a) * g.Wp + off;
+        const uint8_t* pl = PRrow + ((ch * 3 + 1) * 4 + a) * g.Wp + off;
+        const uint8_t* ph = PRrow + ((ch * 3 + 2) * 4 + a) * g.Wp + off;
+        const uint32_t wv[2] = {__ldg((const uint32_t*)pv), __ldg((const uint32_t*)pv + 1)};
+        const uint32_t wl[2] = {__ldg((const uint32_t*)pl), __ldg((const uint32_t*)pl + 1)};
+        const uint32_t wh[2] = {__ldg((const uint32_t*)ph), __ldg((const uint32_t*)ph + 1)};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t sel = (i & 1) ? 0x4342u : 0x4140u;
+            const uint32_t V = prmt(wv[i >> 1], 0, sel), V0 = prmt(wl[i >> 1], 0, sel), CV1 = prmt(wh[i >> 1], 0, sel);
+            const uint32_t a_ = __vadd2(Um, CV1);                      // u - v1
+            const uint32_t c0 = __viaddmax_s16x2_relu(V0, negU, a_);   // max(v0 - u, u - v1, 0)
+            const uint32_t b_ = __vadd2(U0m, V ^ 0x00FF00FFu);         // u0 - v
+            const uint32_t c1 = __viaddmax_s16x2_relu(V, negU1, b_);   // max(v - u1, u0 - v, 0)
+            const uint32_t c = __vmins2(c0, c1);
+            if (ch == 0)
+                acc[i] = c;
+            else
+                acc[i] = __vadd2(acc[i], (c >> 2) & 0x3FFF3FFFu);
+        }
+    }
+    out0 = prmt(acc[0], acc[1], 0x6420);
+    out1 = prmt(acc[2], acc[3], 0x6420);
+}
+
+__global__ void __launch_bounds__(COST_THREADS) k_cost(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ PR,
+                                                       int16_t* __restrict__ C) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int D = g.D, DQ = D >> 3;
+    const int TXH = COST_TX + 2 * g.SW2, n = 2 * g.SH2 + 1;
+    uint8_t* ring = smem;                                        // [n][TXH][D] u8
+    uint16_t* Vs = (uint16_t*)(smem + (size_t)n * TXH * D);      // [TXH][D] u16
+    const int b = blockIdx.z;
+    // locate (segment, band)
+    int band = blockIdx.y, si = 0;
+    for (; si < g.nseg; si++) {
+        int nb = (g.seg[si].src_end - g.seg[si].src_start + COST_RB - 1) / COST_RB;
+        if (band < nb) break;
+        band -= nb;
+    }
+    if (si >= g.nseg) return;
+    const Seg sg = g.seg[si];
+    const int ya = sg.src_start + band * COST_RB, yb = min(ya + COST_RB, sg.src_end);
+    const int ymin = sg.src_start, ymax = g.H - 1;
+    const int x0 = blockIdx.x * COST_TX;
+    const int tid = threadIdx.x;
+    int r = max(ya - g.SH2, ymin);
+    for (int y = ya; y < yb; y++) {
+        const int need = min(y + g.SH2, ymax);
+        for (; r <= need; r++) {
+            const int4* PLrow = PL + ((size_t)b * g.H + r) * g.W;
+            const uint8_t* PRrow = PR + ((size_t)b * g.H + r) * 24 * g.Wp;
+            uint8_t* slot = ring + (size_t)(r % n) * TXH * D;
+            for (int it = tid; it < TXH * DQ; it += COST_THREADS) {
+                const int xh = it / DQ, q = it - xh * DQ;
+                const int xc = min(max(x0 - g.SW2 + xh, 0), g.W1 - 1);
+                uint32_t o0, o1;
+                bt_item(g, PLrow, PRrow, xc + g.minX1, q, o0, o1);
+                *(uint2*)(slot + (size_t)xh * D + 8 * q) = make_uint2(o0, o1);
+            }
+        }
+        __syncthreads();
+        for (int it = tid; it < TXH * DQ; it += COST_THREADS) {
+            const int xh = it / DQ, q = it - xh * DQ;
+            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            for (int kk = y - g.SH2; kk <= y + g.SH2; kk++) {
+                const int rr = min(max(kk, ymin), ymax);
+                const uint2 w = *(const uint2*)(ring + ((size_t)(rr % n) * TXH + xh) * D + 8 * q);
+                a0 = __vadd2(a0, prmt(w.x, 0, 0x4140));
+                a1 = __vadd2(a1, prmt(w.x, 0, 0x4342));
+                a2 = __vadd2(a2, prmt(w.y, 0, 0x4140));
+                a3 = __vadd2(a3, prmt(w.y, 0, 0x4342));
+            }
+            *(uint4*)(Vs + (size_t)xh * D + 8 * q) = make_uint4(a0, a1, a2, a3);
+        }
+        __syncthreads();
+        int16_t* Crow = C + ((size_t)b * g.crows + sg.crow0 + (y - sg.src_start)) * g.W1 * D;
+        for (int it = tid; it < COST_TX * DQ; it += COST_THREADS) {
+            const int xl = it / DQ, q = it - xl * DQ;
+            const int x = x0 + xl;
+            if (x >= g.W1) continue;
+            uint4 acc = make_uint4(0, 0, 0, 0);
+            for (int j = 0; j <= 2 * g.SW2; j++) {
+                const uint4 w = *(const uint4*)(Vs + (size_t)(xl + j) * D + 8 * q);
+                acc.x = __vadd2(acc.x, w.x);
+                acc.y = __vadd2(acc.y, w.y);
+                acc.z = __vadd2(acc.z, w.z);
+                acc.w = __vadd2(acc.w, w.w);
+            }
+            *(uint4*)(Crow + (size_t)x * D + 8 * q) = acc;
+        }
+        // the next iteration's first __syncthreads orders Vs/ring reuse
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Path aggregation. A chain's D costs live in G lanes x NP packed registers (D = 2*G*NP).
+// State P is the previous L normalised by its minimum, so
+//   L[d] = C[d] + min(P[d], min(P[d-1], P[d+1]) + P1, P2)        (== OpenCV's Lr)
+// ------------------------------------------------------------------------------------------
+template <int NP>
+__device__ __forceinline__ void load_regs(const int16_t* p, uint32_t (&r)[NP]) {
+    if constexpr (NP % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < NP / 4; i++) {
+            uint4 v = *((const uint4*)p + i);
+            r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        }
+    } else if constexpr (NP % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < NP / 2; i++) {
+            uint2 v = *((const uint2*)p + i);
+            r[2 * i] = v.x; r[2 * i + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) r[i] = *((const uint32_t*)p + i);
+    }
+}
+template <int NP>
+__device__ __forceinline__ void store_regs(int16_t* p, const uint32_t (&r)[NP]) {
+    if constexpr (NP % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < NP / 4; i++) *((uint4*)p + i) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+    } else if constexpr (NP % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < NP / 2; i++) *((uint2*)p + i) = make_uint2(r[2 * i], r[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) *((uint32_t*)p + i) = r[i];
+    }
+}
+
+template <int NP, int G>
+__device__ __forceinline__ void sgm_step(uint32_t (&P)[NP], const uint32_t (&c)[NP], uint32_t (&L)[NP], uint32_t P1x2,
+                                         uint32_t P2x2, uint32_t PADx2, int lg) {
+    uint32_t up = __shfl_up_sync(0xffffffffu, P[NP - 1], 1, G);
+    uint32_t dn = __shfl_down_sync(0xffffffffu, P[0], 1, G);
+    if (lg == 0) up = PADx2;
+    if (lg == G - 1) dn = PADx2;
+    uint32_t T[NP + 1];
+    T[0] = prmt(up, P[0], 0x5432);
+#pragma unroll
+    for (int k = 1; k < NP; k++) T[k] = prmt(P[k - 1], P[k], 0x5432);
+    T[NP] = prmt(P[NP - 1], dn, 0x5432);
+    uint32_t m = 0x7FFF7FFFu;
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+        uint32_t t = __vmins2(T[k], T[k + 1]);
+        t = __viaddmin_s16x2(t, P1x2, P[k]);
+        t = __vmins2(t, P2x2);
+        L[k] = __vadd2(c[k], t);
+        m = __vmins2(m, L[k]);
+    }
+    m = __vmins2(m, prmt(m, m, 0x1032));
+#pragma unroll
+    for (int o = G / 2; o >= 1; o >>= 1) m = __vmins2(m, __shfl_xor_sync(0xffffffffu, m, o, G));
+    const uint32_t negm = __vadd2(~m, 0x00010001u);
+#pragma unroll
+    for (int k = 0; k < NP; k++) P[k] = __vadd2(L[k], negm);
+}
+
+// vertical (dirx = 0) and diagonal (dirx = +-1) chains, top-down (diry = +1) or bottom-up (-1).
+// Chain c visits x = (c + dirx*step) mod W1; on wrap-around it restarts from the zero border.
+template <int NP, int G>
+__global__ void __launch_bounds__(128) k_path_v(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int dirx,
+                                                int diry, int accumulate) {
+    constexpr int CPB = 128 / G;
+    const int lane = threadIdx.x & 31, lg = lane & (G - 1);
+    const int chain = blockIdx.x * CPB + threadIdx.x / G;
+    const bool active = chain < g.W1;
+    const Seg sg = g.seg[blockIdx.y];
+    const int b = blockIdx.z;
+    const int D = g.D;
+    const uint32_t P1x2 = pack16(g.P1, g.P1), P2x2 = pack16(g.P2, g.P2);
+    const int pad = 32767 - g.P1;
+    const uint32_t PADx2 = pack16(pad, pad);
+    int x = min(chain, g.W1 - 1);
+    const int nrows = sg.src_end - sg.src_start;
+    int y = diry > 0 ? sg.src_start : sg.src_end - 1;
+    uint32_t P[NP], c[NP], s[NP], L[NP], cn[NP], sn[NP];
+#pragma unroll
+    for (int k = 0; k < NP; k++) { P[k] = 0; sn[k] = 0; }
+    const size_t lane_off = (size_t)lg * 2 * NP;
+    const int16_t* Cb = C + ((size_t)b * g.crows + sg.crow0) * g.W1 * D + lane_off;
+    int16_t* Sb = S + (size_t)b * g.H * g.W1 * D + lane_off;
+    load_regs<NP>(Cb + ((size_t)(y - sg.src_start) * g.W1 + x) * D, cn);
+    if (accumulate && y >= sg.dst_start) load_regs<NP>(Sb + ((size_t)y * g.W1 + x) * D, sn);
+    for (int step = 0; step < nrows; step++) {
+#pragma unroll
+        for (int k = 0; k < NP; k++) { c[k] = cn[k]; s[k] = sn[k]; }
+        // next position
+        int xn = x + dirx, yn = y + diry;
+        bool wrap = false;
+        if (xn >= g.W1) { xn = 0; wrap = true; }
+        if (xn < 0) { xn = g.W1 - 1; wrap = true; }
+        if (step + 1 < nrows) {
+            load_regs<NP>(Cb + ((size_t)(yn - sg.src_start) * g.W1 + xn) * D, cn);
+            if (accumulate && yn >= sg.dst_start) load_regs<NP>(Sb + ((size_t)yn * g.W1 + xn) * D, sn);
+        }
+        sgm_step<NP, G>(P, c, L, P1x2, P2x2, PADx2, lg);
+        if (active && y >= sg.dst_start) {
+            if (accumulate) {
+#pragma unroll
+                for (int k = 0; k < NP; k++) L[k] = __vminu2(__vadd2(s[k], L[k]), 0x7FFF7FFFu);
+            }
+            store_regs<NP>(Sb + ((size_t)y * g.W1 + x) * D, L);
+        }
+        if (wrap) {
+#pragma unroll
+            for (int k = 0; k < NP; k++) P[k] = 0;
+        }
+        x = xn;
+        y = yn;
+    }
+}
+
+// WTA + uniqueness + sub-pixel for one pixel whose final S is in registers (all lanes of the group
+// take part; results are uniform across the group).
+template <int NP, int G>
+__device__ __forceinline__ void wta_pixel(const uint32_t (&Sr)[NP], int lg, const Geom& g, int16_t* sm, int& disp_out,
+                                          uint32_t& wta_out) {
+    uint32_t key = 0xFFFFFFFFu;
+    const int d0 = lg * 2 * NP;
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+        const uint32_t klo = ((Sr[k] & 0xFFFFu) << 8) | (uint32_t)(d0 + 2 * k);
+        const uint32_t khi = ((Sr[k] >> 16) << 8) | (uint32_t)(d0 + 2 * k + 1);
+        key = min(key, min(klo, khi));
+    }
+#pragma unroll
+    for (int o = G / 2; o >= 1; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o, G));
+    const int minS = (int)(key >> 8), best = (int)(key & 0xFFu);
+    // S[d] < thr  <=>  the uniqueness predicate of the mode
+    const int q = 100 - g.uq;
+    int thr = g.three_way ? (g.uq > 0 ? (100 * minS) / q + 1 : 0) : (minS * 100 + q - 1) / q;
+    thr = min(thr, 0x8000);
+    const uint32_t cst = 0x80008000u - pack16(thr, thr);  // per half: 0x8000 - thr, no borrow
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+        const uint32_t t = Sr[k] + cst;  // bit15 / bit31 set <=> S >= thr
+        cnt += (~t >> 15) & 0x00010001u;
+    }
+    int nlt = (int)((cnt & 0xFFFFu) + (cnt >> 16));
+#pragma unroll
+    for (int o = G / 2; o >= 1; o >>= 1) nlt += __shfl_xor_sync(0xffffffffu, nlt, o, G);
+    // neighbours of the minimum through shared memory
+    store_regs<NP>(sm + d0, Sr);
+    __syncwarp();
+    const int Sm = best > 0 ? sm[best - 1] : 0, Sp = best < g.D - 1 ? sm[best + 1] : 0;
+    __syncwarp();
+    int nexcl = (minS < thr) + (best > 0 && Sm < thr) + (best < g.D - 1 && Sp < thr);
+    if (nlt > nexcl) {
+        disp_out = (g.minD - 1) * 16;
+        wta_out = 0xFFFFFFFFu;
+        return;
+    }
+    int d = best * 16;
+    if (best > 0 && best < g.D - 1) {
+        const int denom2 = max(Sm + Sp - 2 * minS, 1);
+        d += ((Sm - Sp) * 16 + denom2) / (denom2 * 2);
+    }
+    disp_out = d + g.minD * 16;
+    wta_out = ((uint32_t)minS << 16) | (uint32_t)best;
+}
+
+// Horizontal chains: one group per output row. dir = +1 (L->R) accumulates into S;
+// dir = -1 (R->L) with WTA = true finishes S in registers and emits the raw disparity.
+template <int NP, int G, bool WTA>
+__global__ void __launch_bounds__(128) k_path_h(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int dir,
+                                                int accumulate, int16_t* __restrict__ dispraw, uint32_t* __restrict__ wta) {
+    constexpr int CPB = 128 / G;
+    __shared__ __align__(16) int16_t smS[WTA ? CPB * 2 * NP * G : 8];
+    const int lane = threadIdx.x & 31, lg = lane & (G - 1);
+    const int row = blockIdx.x * CPB + threadIdx.x / G;
+    const bool active = row < g.H;
+    const int y = min(row, g.H - 1);
+    const int b = blockIdx.z;
+    const int D = g.D;
+    int si = 0;
+    for (int i = 0; i < g.nseg; i++)
+        if (y >= g.seg[i].dst_start && y < g.seg[i].src_end) si = i;
+    const Seg sg = g.seg[si];
+    const uint32_t P1x2 = pack16(g.P1, g.P1), P2x2 = pack16(g.P2, g.P2);
+    const int pad = 32767 - g.P1;
+    const uint32_t PADx2 = pack16(pad, pad);
+    uint32_t P[NP], c[NP], s[NP], L[NP], cn[NP], sn[NP];
+#pragma unroll
+    for (int k = 0; k < NP; k++) { P[k] = 0; sn[k] = 0; }
+    const size_t lane_off = (size_t)lg * 2 * NP;
+    const int16_t* Cb = C + (((size_t)b * g.crows + sg.crow0 + (y - sg.src_start)) * g.W1) * D + lane_off;
+    int16_t* Sb = S + (((size_t)b * g.H + y) * g.W1) * D + lane_off;
+    int x = dir > 0 ? 0 : g.W1 - 1;
+    load_regs<NP>(Cb + (size_t)x * D, cn);
+    if (accumulate) load_regs<NP>(Sb + (size_t)x * D, sn);
+    int16_t* sm = smS + (threadIdx.x / G) * 2 * NP * G;
+    for (int step = 0; step < g.W1; step++) {
+#pragma unroll
+        for (int k = 0; k < NP; k++) { c[k] = cn[k]; s[k] = sn[k]; }
+        const int xn = x + dir;
+        if (step + 1 < g.W1) {
+            load_regs<NP>(Cb + (size_t)xn * D, cn);
+            if (accumulate) load_regs<NP>(Sb + (size_t)xn * D, sn);
+        }
+        sgm_step<NP, G>(P, c, L, P1x2, P2x2, PADx2, lg);
+        if (accumulate) {
+#pragma unroll
+            for (int k = 0; k < NP; k++) L[k] = __vminu2(__vadd2(s[k], L[k]), 0x7FFF7FFFu);
+        }
+        if constexpr (WTA) {
+            int dv;
+            uint32_t wv;
+            wta_pixel<NP, G>(L, lg, g, sm, dv, wv);
+            if (active && lg == 0) {
+                dispraw[((size_t)b * g.H + y) * g.W + x + g.minX1] = (int16_t)dv;
+                wta[((size_t)b * g.H + y) * g.W1 + x] = wv;
+            }
+        } else {
+            if (active) store_regs<NP>(Sb + (size_t)x * D, L);
+        }
+        x = xn;
+    }
+}
+
+// Right-view disparity + left-right check for one row. disp2 is reduced
+// with atomicMin on (cost << 16 | 0xFFFF - x): smallest cost wins, ties go to the largest x,
+// which is what OpenCV's descending-x "disp2cost[x2] > minS" scan produces.
+__global__ void __launch_bounds__(256) k_lrcheck(Geom g, const int16_t* __restrict__ dispraw, const uint32_t* __restrict__ wta,
+                                                 int16_t* __restrict__ out, size_t opitch, size_t oframe) {
+    extern __shared__ uint32_t keys[];
+    const int y = blockIdx.x, b = blockIdx.z;
+    const int INV = (g.minD - 1) * 16;
+    for (int x = threadIdx.x; x < g.W; x += blockDim.x) keys[x] = 0xFFFFFFFFu;
+    __syncthreads();
+    const uint32_t* wr = wta + ((size_t)b * g.H + y) * g.W1;
+    for (int x = threadIdx.x; x < g.W1; x += blockDim.x) {
+        const uint32_t w = wr[x];
+        if (w != 0xFFFFFFFFu) {
+            const int best = (int)(w & 0xFFFFu), minS = (int)(w >> 16);
+            const int x2 = x + g.minX1 - best - g.minD;
+            if (x2 >= 0 && x2 < g.W) atomicMin(&keys[x2], ((uint32_t)minS << 16) | (uint32_t)(0xFFFF - x));
+        }
+    }
+    __syncthreads();
+    const int16_t* dr = dispraw + ((size_t)b * g.H + y) * g.W;
+    int16_t* orow = (int16_t*)((uint8_t*)out + (size_t)b * oframe + (size_t)y * opitch);
+    for (int x = threadIdx.x; x < g.W; x += blockDim.x) {
+        int d1 = INV;
+        if (x >= g.minX1 && x < g.maxX1) {
+            d1 = dr[x];
+            if (d1 != INV) {
+                const int _d = d1 >> 4, d_ = (d1 + 15) >> 4;
+                const int _x = x - _d, x_ = x - d_;
+                bool bad0 = false, bad1 = false;
+                if (_x >= 0 && _x < g.W) {
+                    const uint32_t k = keys[_x];
+                    const int v = k == 0xFFFFFFFFu ? INV : (0xFFFF - (int)(k & 0xFFFFu)) + g.minX1 - _x;
+                    bad0 = v >= g.minD && abs(v - _d) > g.d12;
+                }
+                if (x_ >= 0 && x_ < g.W) {
+                    const uint32_t k = keys[x_];
+                    const int v = k == 0xFFFFFFFFu ? INV : (0xFFFF - (int)(k & 0xFFFFu)) + g.minX1 - x_;
+                    bad1 = v >= g.minD && abs(v - d_) > g.d12;
+                }
+                if (bad0 && bad1) d1 = INV;
+            }
+        }
+        orow[x] = (int16_t)d1;
+    }
+}
+
+__global__ void k_fill16(int16_t* out, size_t opitch, size_t oframe, int W, int H, int val) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x < W) ((int16_t*)((uint8_t*)out + (size_t)b * oframe + (size_t)y * opitch))[x] = (int16_t)val;
+}
+
+// ---- dispatch over (NP, G): D = 2*G*NP ----------------------------------------------------
+struct PathCfg {
+    int NP, G;
+};
+// D multiple of 16 up to 256. Prefer G = 8 (four chains per warp, three shuffle steps per
+// reduction); D = 16*k -> NP = k.
+inline PathCfg path_cfg(int D) { return PathCfg{D / 16, 8}; }
+
+template <int NP>
+int launch_path_v(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int16_t* S, int dirx, int diry, int acc) {
+    constexpr int G = 8;
+    dim3 grid(div_up(g.W1, 128 / G), g.nseg, batch);
+    k_path_v<NP, G><<<grid, 128, 0, ctx->stream>>>(g, C, S, dirx, diry, acc);
+    SDR_LAUNCHED(ctx);
+    return SDR_OK;
+}
+template <int NP>
+int launch_path_h(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int16_t* S, int dir, int acc, bool wta_on,
+                  int16_t* dispraw, uint32_t* wta) {
+    constexpr int G = 8;
+    dim3 grid(div_up(g.H, 128 / G), 1, batch);
+    if (wta_on)
+        k_path_h<NP, G, true><<<grid, 128, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
+    else
+        k_path_h<NP, G, false><<<grid, 128, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
+    SDR_LAUNCHED(ctx);
+    return SDR_OK;
+}
+
+#define NP_SWITCH(np, CALL)                                                              \
+    switch (np) {                                                                        \
+        case 1: { constexpr int NPc = 1; CALL; } break;                                  \
+        case 2: { constexpr int NPc = 2; CALL; } break;                                  \
+        case 3: { constexpr int NPc = 3; CALL; } break;                                  \
+        case 4: { constexpr int NPc = 4; CALL; } break;                                  \
+        case 5: { constexpr int NPc = 5; CALL; } break;                                  \
+        case 6: { constexpr int NPc = 6; CALL; } break;                                  \
+        case 7: { constexpr int NPc = 7; CALL; } break;                                  \
+        case 8: { constexpr int NPc = 8; CALL; } break;                                  \
+        case 9: { constexpr int NPc = 9; CALL; } break;                                  \
+        case 10: { constexpr int NPc = 10; CALL; } break;                                \
+        case 11: { constexpr int NPc = 11; CALL; } break;                                \
+        case 12: { constexpr int NPc = 12; CALL; } break;                                \
+        case 13: { constexpr int NPc = 13; CALL; } break;                                \
+        case 14: { constexpr int NPc = 14; CALL; } break;                                \
+        case 15: { constexpr int NPc = 15; CALL; } break;                                \
+        case 16: { constexpr int NPc = 16; CALL; } break;                                \
+        default: rc = SDR_EINVAL;                                                        \
+    }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+struct sdr_sgbm {
+    sdr_ctx* ctx = nullptr;
+    sdr_sgbm_params p{};
+    DevBuf inL, inR, PL, PR, C, S, dispraw, wta, matched, out;
+    SpeckleScratch speckle;
+    StageTimer timer;
+    Geom g{};
+    int last_batch = 0;
+};
+
+static int validate_params(sdr_ctx* ctx, const sdr_sgbm_params* p) {
+    if (p->numDisparities <= 0 || p->numDisparities % 16 != 0)
+        return SDR_FAIL(ctx, SDR_EINVAL, "numDisparities must be a positive multiple of 16 (got %d)", p->numDisparities);
+    if (p->numDisparities > 256)
+        return SDR_FAIL(ctx, SDR_EINVAL, "numDisparities > 256 is not supported (got %d)", p->numDisparities);
+    if (p->blockSize > 0 && p->blockSize % 2 == 0)
+        return SDR_FAIL(ctx, SDR_EINVAL, "blockSize must be odd (got %d)", p->blockSize);
+    if (p->blockSize > 11) return SDR_FAIL(ctx, SDR_EINVAL, "blockSize > 11 is not supported (got %d)", p->blockSize);
+    if (p->mode != SDR_MODE_SGBM && p->mode != SDR_MODE_HH && p->mode != SDR_MODE_SGBM_3WAY)
+        return SDR_FAIL(ctx, SDR_EINVAL, "unsupported mode %d (MODE_SGBM=0, MODE_HH=1, MODE_SGBM_3WAY=2)", p->mode);
+    if (p->preFilterCap > 95) return SDR_FAIL(ctx, SDR_EINVAL, "preFilterCap > 95 is not supported (got %d)", p->preFilterCap);
+    if (p->uniquenessRatio >= 100) return SDR_FAIL(ctx, SDR_EINVAL, "uniquenessRatio must be < 100");
+    const int P1 = p->P1 > 0 ? p->P1 : 2;
+    const int P2 = std::max(p->P2 > 0 ? p->P2 : 5, P1 + 1);
+    const int bs = p->blockSize > 0 ? p->blockSize : 5;
+    const int ft = std::max(p->preFilterCap, 15) | 1;
+    if ((2 * ft + 63) * bs * bs + P2 + P1 > 32767)
+        return SDR_FAIL(ctx, SDR_EINVAL, "P1/P2/blockSize/preFilterCap combination overflows CV_16S path costs");
+    return SDR_OK;
+}
+
+extern "C" int sdr_sgbm_create(sdr_ctx* ctx, const sdr_sgbm_params* params, sdr_sgbm** out) {
+    if (!ctx || !params || !out) return SDR_EINVAL;
+    int rc = validate_params(ctx, params);
+    if (rc) return rc;
+    sdr_sgbm* m = new sdr_sgbm();
+    m->ctx = ctx;
+    m->p = *params;
+    *out = m;
+    return SDR_OK;
+}
+
+extern "C" void sdr_sgbm_destroy(sdr_sgbm* m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    for (DevBuf* b : {&m->inL, &m->inR, &m->PL, &m->PR, &m->C, &m->S, &m->dispraw, &m->wta, &m->matched, &m->out,
+                      &m->speckle.parent, &m->speckle.count})
+        b->release();
+    m->timer.release();
+    delete m;
+}
+
+static void make_geom(const sdr_sgbm_params& p, int W, int H, Geom& g) {
+    g.W = W; g.H = H; g.D = p.numDisparities; g.minD = p.minDisparity;
+    const int maxD = g.minD + g.D;
+    g.minX1 = std::max(maxD, 0);
+    g.maxX1 = W + std::min(g.minD, 0);
+    g.W1 = g.maxX1 - g.minX1;
+    g.uq = p.uniquenessRatio >= 0 ? p.uniquenessRatio : 10;
+    g.d12 = p.disp12MaxDiff > 0 ? p.disp12MaxDiff : 1;
+    g.P1 = p.P1 > 0 ? p.P1 : 2;
+    g.P2 = std::max(p.P2 > 0 ? p.P2 : 5, g.P1 + 1);
+    g.ftzero = std::max(p.preFilterCap, 15) | 1;
+    g.three_way = p.mode == SDR_MODE_SGBM_3WAY;
+    g.Wp = ((W + 3) & ~3) + 8;
+    if (g.three_way) {
+        g.SW2 = g.SH2 = p.blockSize > 0 ? p.blockSize / 2 : 1;
+        const int nstripes = 4;
+        const int stripe_sz = (H + nstripes - 1) / nstripes;
+        // same double expression as OpenCV: 0.1*stripe_sz is not exact, e.g. 0.1*180 > 18
+        const int overlap = (p.blockSize / 2 + 1) + (int)std::ceil(0.1 * stripe_sz);
+        g.nseg = 0;
+        int crow = 0;
+        for (int s = 0; s < nstripes; s++) {
+            Seg sg;
+            sg.src_start = s == 0 ? 0 : std::max(std::min(s * stripe_sz - overlap, H), 0);
+            sg.dst_start = s * stripe_sz;
+            sg.src_end = std::min((s + 1) * stripe_sz, H);
+            if (sg.dst_start >= sg.src_end) continue;  // empty stripe (tiny images)
+            sg.crow0 = crow;
+            crow += sg.src_end - sg.src_start;
+            g.seg[g.nseg++] = sg;
+        }
+        g.crows = crow;
+    } else {
+        g.SW2 = g.SH2 = (p.blockSize > 0 ? p.blockSize : 5) / 2;
+        g.nseg = 1;
+        g.seg[0] = Seg{0, H, 0, 0};
+        g.crows = H;
+    }
+}
+
+static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, size_t lframe, const uint8_t* R, size_t rpitch,
+                    size_t rframe, int W, int H, int16_t* out, size_t opitch, size_t oframe) {
+    sdr_ctx* ctx = m->ctx;
+    Geom& g = m->g;
+    make_geom(m->p, W, H, g);
+    m->last_batch = batch;
+    cudaStream_t st = ctx->stream;
+    m->timer.begin(st);
+    const int INV = (g.minD - 1) * 16;
+    int rc = SDR_OK;
+    // raw matcher output goes to m->matched, median to m->out (or directly to `out`)
+    const size_t img16 = (size_t)W * H * sizeof(int16_t);
+    if ((rc = m->matched.reserve(ctx, img16 * batch))) return rc;
+    if (g.W1 <= 0) {
+        k_fill16<<<dim3(div_up(W, 256), H, batch), 256, 0, st>>>(m->matched.as<int16_t>(), (size_t)W * 2, img16, W, H, INV);
+        SDR_LAUNCHED(ctx);
+    } else {
+        const size_t vol = (size_t)g.W1 * g.D * sizeof(int16_t);
+        if ((rc = m->PL.reserve(ctx, (size_t)batch * H * W * sizeof(int4)))) return rc;
+        if ((rc = m->PR.reserve(ctx, (size_t)batch * H * 24 * g.Wp))) return rc;
+        if ((rc = m->C.reserve(ctx, vol * g.crows * batch))) return rc;
+        if ((rc = m->S.reserve(ctx, vol * H * batch))) return rc;
+        if ((rc = m->dispraw.reserve(ctx, img16 * batch))) return rc;
+        if ((rc = m->wta.reserve(ctx, (size_t)batch * H * g.W1 * sizeof(uint32_t)))) return rc;
+        k_prefilter<<<dim3(div_up(W, 128), H, batch * 2), 128, 0, st>>>(g, L, lpitch, lframe, R, rpitch, rframe,
+                                                                         m->PL.as<int4>(), m->PR.as<uint8_t>());
+        SDR_LAUNCHED(ctx);
+        m->timer.mark(st, "prefilter");
+        {
+            const int TXH = COST_TX + 2 * g.SW2, n = 2 * g.SH2 + 1;
+            const size_t smem = (size_t)n * TXH * g.D + (size_t)TXH * g.D * 2;
+            if (smem > ctx->smem_optin) return SDR_FAIL(ctx, SDR_EINVAL, "cost kernel needs %zu B shared memory", smem);
+            SDR_CUDA(ctx, cudaFuncSetAttribute(k_cost, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int bands = 0;
+            for (int i = 0; i < g.nseg; i++) bands += div_up(g.seg[i].src_end - g.seg[i].src_start, COST_RB);
+            k_cost<<<dim3(div_up(g.W1, COST_TX), bands, batch), COST_THREADS, smem, st>>>(g, m->PL.as<int4>(), m->PR.as<uint8_t>(),
+                                                                                        m->C.as<int16_t>());
+            SDR_LAUNCHED(ctx);
+            m->timer.mark(st, "cost");
+        }
+        const int16_t* C = m->C.as<int16_t>();
+        int16_t* S = m->S.as<int16_t>();
+        const int np = path_cfg(g.D).NP;
+        // direction list: {dirx, diry}; the first one initialises S
+        if (m->p.mode == SDR_MODE_SGBM_3WAY) {
+            NP_SWITCH(np, rc = launch_path_v<NPc>(ctx, g, batch, C, S, 0, +1, 0));
+            if (rc) return rc;
+            m->timer.mark(st, "path_v");
+        } else {
+            const int dirs[6][2] = {{0, +1}, {+1, +1}, {-1, +1}, {0, -1}, {+1, -1}, {-1, -1}};
+            const int nd = m->p.mode == SDR_MODE_HH ? 6 : 3;
+            for (int i = 0; i < nd; i++) {
+                NP_SWITCH(np, rc = launch_path_v<NPc>(ctx, g, batch, C, S, dirs[i][0], dirs[i][1], i > 0));
+                if (rc) return rc;
+                m->timer.mark(st, i == 0 ? "path_v0" : i == 1 ? "path_v1" : i == 2 ? "path_v2" : i == 3 ? "path_v3" : i == 4 ? "path_v4" : "path_v5");
+            }
+        }
+        NP_SWITCH(np, rc = launch_path_h<NPc>(ctx, g, batch, C, S, +1, 1, false, nullptr, nullptr));
+        if (rc) return rc;
+        m->timer.mark(st, "path_h_fwd");
+        NP_SWITCH(np, rc = launch_path_h<NPc>(ctx, g, batch, C, S, -1, 1, true, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>()));
+        if (rc) return rc;
+        m->timer.mark(st, "path_h_bwd_wta");
+        k_lrcheck<<<dim3(H, 1, batch), 256, (size_t)W * sizeof(uint32_t), st>>>(g, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>(),
+                                                                                  m->matched.as<int16_t>(), (size_t)W * 2, img16);
+        SDR_LAUNCHED(ctx);
+        m->timer.mark(st, "lrcheck");
+    }
+    if ((rc = sdr_launch_median3(ctx, m->matched.as<int16_t>(), (size_t)W * 2, out, opitch, W, H, batch, img16, oframe))) return rc;
+    m->timer.mark(st, "median3");
+    if (m->p.speckleWindowSize > 0) {
+        if ((rc = sdr_launch_speckle(ctx, out, opitch, W, H, batch, oframe, INV, m->p.speckleWindowSize, 16 * m->p.speckleRange,
+                                     m->speckle)))
+            return rc;
+        m->timer.mark(st, "speckle");
+    }
+    return SDR_OK;
+}
+
+extern "C" int sdr_sgbm_compute_batch(sdr_sgbm* m, int n, const sdr_image* lefts, const sdr_image* rights, sdr_image* disps) {
+    if (!m || n <= 0 || !lefts || !rights || !disps) return SDR_EINVAL;
+    sdr_ctx* ctx = m->ctx;
+    SDR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int W = lefts[0].cols, H = lefts[0].rows;
+    int rc;
+    for (int i = 0; i < n; i++) {
+        if ((rc = sdr_check_image(ctx, &lefts[i], 1, 1, "left"))) return rc;
+        if ((rc = sdr_check_image(ctx, &rights[i], 1, 1, "right"))) return rc;
+        if ((rc = sdr_check_image(ctx, &disps[i], 1, 2, "disp"))) return rc;
+        if (lefts[i].cols != W || lefts[i].rows != H || rights[i].cols != W || rights[i].rows != H || disps[i].cols != W ||
+            disps[i].rows != H)
+            return SDR_FAIL(ctx, SDR_ESIZE, "left/right/disp sizes differ (pair %d)", i);
+    }
+    // Fast path: device-resident frames laid out at a constant stride are used in place.
+    auto strided = [&](const sdr_image* a, size_t& frame) {
+        if (a[0].mem != SDR_MEM_DEVICE) return false;
+        frame = n > 1 ? (size_t)((const uint8_t*)a[1].data - (const uint8_t*)a[0].data) : 0;
+        for (int i = 0; i < n; i++) {
+            if (a[i].mem != SDR_MEM_DEVICE || a[i].step_bytes != a[0].step_bytes) return false;
+            if ((const uint8_t*)a[i].data != (const uint8_t*)a[0].data + (size_t)i * frame) return false;
+        }
+        return true;
+    };
+    const uint8_t *L, *R;
+    size_t lp, lf, rp, rf;
+    if (strided(lefts, lf)) {
+        L = (const uint8_t*)lefts[0].data; lp = lefts[0].step_bytes;
+    } else {
+        if ((rc = m->inL.reserve(ctx, (size_t)n * W * H))) return rc;
+        for (int i = 0; i < n; i++)
+            SDR_CUDA(ctx, cudaMemcpy2DAsync(m->inL.as<uint8_t>() + (size_t)i * W * H, W, lefts[i].data, lefts[i].step_bytes, W, H,
+                                            cudaMemcpyDefault, ctx->stream));
+        L = m->inL.as<uint8_t>(); lp = W; lf = (size_t)W * H;
+    }
+    if (strided(rights, rf)) {
+        R = (const uint8_t*)rights[0].data; rp = rights[0].step_bytes;
+    } else {
+        if ((rc = m->inR.reserve(ctx, (size_t)n * W * H))) return rc;
+        for (int i = 0; i < n; i++)
+            SDR_CUDA(ctx, cudaMemcpy2DAsync(m->inR.as<uint8_t>() + (size_t)i * W * H, W, rights[i].data, rights[i].step_bytes, W, H,
+                                            cudaMemcpyDefault, ctx->stream));
+        R = m->inR.as<uint8_t>(); rp = W; rf = (size_t)W * H;
+    }
+    size_t of;
+    const bool out_direct = strided(disps, of);
+    int16_t* O;
+    size_t op;
+    if (out_direct) {
+        O = (int16_t*)disps[0].data; op = disps[0].step_bytes;
+    } else {
+        if ((rc = m->out.reserve(ctx, (size_t)n * W * H * 2))) return rc;
+        O = m->out.as<int16_t>(); op = (size_t)W * 2; of = (size_t)W * H * 2;
+    }
+    if ((rc = sgbm_run(m, n, L, lp, lf, R, rp, rf, W, H, O, op, of))) return rc;
+    if (!out_direct) {
+        bool any_host = false;
+        for (int i = 0; i < n; i++) {
+            SDR_CUDA(ctx, cudaMemcpy2DAsync(disps[i].data, disps[i].step_bytes, (const uint8_t*)O + (size_t)i * of, op, (size_t)W * 2, H,
+                                            cudaMemcpyDefault, ctx->stream));
+            any_host |= disps[i].mem != SDR_MEM_DEVICE;
+        }
+        if (any_host) SDR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SDR_OK;
+}
+
+extern "C" int sdr_sgbm_compute(sdr_sgbm* m, const sdr_image* left, const sdr_image* right, sdr_image* disp) {
+    return sdr_sgbm_compute_batch(m, 1, left, right, disp);
+}
+
+extern "C" int sdr_sgbm_set_profiling(sdr_sgbm* m, int enabled) {
+    if (!m) return SDR_EINVAL;
+    m->timer.enabled = enabled != 0;
+    return SDR_OK;
+}
+
+extern "C" int sdr_sgbm_stage_times(sdr_sgbm* m, int cap, const char** names, float* ms) {
+    if (!m) return 0;
+    cudaSetDevice(m->ctx->device);
+    return m->timer.collect(cap, names, ms);
+}
+
+extern "C" int sdr_sgbm_debug_read(sdr_sgbm* m, int what, void* host_dst, size_t bytes) {
+    if (!m || !host_dst) return SDR_EINVAL;
+    sdr_ctx* ctx = m->ctx;
+    SDR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const Geom& g = m->g;
+    const void* src = nullptr;
+    size_t have = 0;
+    if (what == 0) { src = m->C.p; have = (size_t)g.crows * g.W1 * g.D * 2; }
+    else if (what == 1) { src = m->S.p; have = (size_t)g.H * g.W1 * g.D * 2; }
+    else if (what == 2) { src = m->matched.p; have = (size_t)g.H * g.W * 2; }
+    else return SDR_FAIL(ctx, SDR_EINVAL, "debug_read: unknown buffer %d", what);
+    if (!src || bytes > have) return SDR_FAIL(ctx, SDR_ESIZE, "debug_read: %zu bytes requested, %zu available", bytes, have);
+    SDR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SDR_CUDA(ctx, cudaMemcpy(host_dst, src, bytes, cudaMemcpyDeviceToHost));
+    return SDR_OK;
+}
