@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the stereo hot path (BASELINE.json metric: SGBM frames/s and Mpix*disp/s at 1280x720x128).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+Workload (config.workload = BASELINE.json configs[1]): the full pipeline per frame -- remap rectification of both
+halves of a 2560x720 SBS frame, StereoSGBM-compatible MODE_SGBM (D=128, reference parameter tuple) with LR check,
+median and speckle filter, reprojectImageTo3D and the 5 mm VoxelGrid -- on synthetic textured frames.
+A step = one pass over a batch of B frames per GPU. `value` is measured with the frames resident in HBM;
+`e2e` goes through the same C-ABI call with pinned HOST buffers (H2D of the frames and D2H of the disparity maps
+and clouds inside the timed region). `--impl reference` times the reference's CPU arithmetic (cv2 + C VoxelGrid
+restatement) on all host cores for the same metric.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, D = 1280, 720, 128
+SGBM_ARGS = (0, D, 5, 8 * 3 * 5 * 5, 32 * 3 * 5 * 5, 1, 63, 12, 200, 2, 0)   # pcd_write.cpp:102-108 with D=128, MODE_SGBM
+LEAF_MM, Z_MAX_MM = 5.0, 5000.0
+CALIB = os.path.join(ROOT, "tests", "golden", "zed2_calibration.yaml")
+MPIX_DISP_PER_FRAME = W * H * D / 1e6
+METRIC = "sgbm_full_pipeline_frames_per_s_1280x720x128"
+
+
+def make_frames(n, base=4):
+    """n distinct SBS frames from `base` synthetic textured pairs: rolling the rows of a rectified pair gives
+    another valid pair (disparity is horizontal), so the pool is cheap to build yet every frame differs."""
+    from stereo_depth_ruler_b200 import synth
+    pool = []
+    for s in range(min(base, n)):
+        l, r = synth.stereo_pair(W, H, D, s)
+        pool.append(np.concatenate([synth.colorize(l, s), synth.colorize(r, s + 1)], axis=1))
+    frames = []
+    for i in range(n):
+        f = pool[i % len(pool)]
+        k = (i // len(pool)) * 37
+        frames.append(np.ascontiguousarray(np.roll(f, k, axis=0)) if k else f)
+    return frames
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for t, line in self.rows:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9 or not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(p[1])); smax = float(p[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:     # timed region shorter than the sampling period: take every sample we have
+            for t, line in self.rows:
+                p = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(p[1])); smax = float(p[2])
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """The reference's CPU arithmetic on all host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.cpu_pipeline import CpuPipeline
+    cores = os.cpu_count() or 1
+    cpu = CpuPipeline(CALIB, SGBM_ARGS, LEAF_MM, Z_MAX_MM, cores=cores)
+    frames = make_frames(cores)                       # a step = one frame per core (bounded sample of the workload)
+    cpu.prepare(frames)
+    for _ in range(max(0, args.warmup - 1)):
+        cpu.run()
+    total = 0.0
+    for _ in range(args.steps):
+        dt, _ = cpu.run()
+        total += dt
+    fps = args.steps * len(frames) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "s16", "data": "synthetic",
+        "mpix_disp_per_s": fps * MPIX_DISP_PER_FRAME,
+        "config": {"workload": "configs[1]: full pipeline per frame at 1280x720x128 (remap + MODE_SGBM + LR + median + speckle + "
+                               "reproject + 5 mm VoxelGrid)", "frames_per_step": len(frames), "sgbm": list(SGBM_ARGS),
+                   "leaf_mm": LEAF_MM, "z_max_mm": Z_MAX_MM},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": cpu.kind,
+                         "sample": "%d steps x %d frames; %s" % (args.steps, len(frames), cpu.describe())},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    cpu.close()
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from stereo_depth_ruler_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+
+    # ---- CPU baseline first (rank 0, N=1 only), before this process touches CUDA ----
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.cpu_pipeline import CpuPipeline
+        cores = os.cpu_count() or 1
+        cpu = CpuPipeline(CALIB, SGBM_ARGS, LEAF_MM, Z_MAX_MM, cores=cores)
+        cframes = make_frames(cores)
+        cpu.prepare(cframes)
+        reps, total = 0, 0.0
+        while total < 8.0 and reps < 8:               # bounded: about 10-20 s of CPU work in all
+            dt, _ = cpu.run()
+            total += dt
+            reps += 1
+        cpu_baseline = {"value": reps * len(cframes) / total, "unit": "frames/s", "cores": cores, "kind": cpu.kind,
+                        "sample": "%d passes x %d frames of the same workload; %s" % (reps, len(cframes), cpu.describe())}
+        cpu.close()
+
+    ctx = capi.Context(local)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    calib = capi.load_calibration(CALIB)
+    params = capi.make_params(*SGBM_ARGS)
+    vox = capi.voxel_options(LEAF_MM, drop_invalid=True, z_max=Z_MAX_MM)
+    pipe = capi.Pipeline(ctx, calib, params, vox, handle_missing=True, batch=B)
+
+    # frame pool larger than L2 (126 MB): POOL x 5.5 MB resident in HBM, a different batch every step
+    n_pool = max(args.pool, 2 * B)
+    frames_np = make_frames(n_pool)
+    # frame i of the stream goes to rank i mod N: each rank builds the frames it owns (weak scaling: B per rank per step)
+    mine = [frames_np[(rank + j * world) % n_pool] for j in range(n_pool)]
+    dev_pool = torch.from_numpy(np.stack(mine)).cuda()                       # [P][H][2W][3] u8
+    host_pool = torch.from_numpy(np.stack(mine)).pin_memory()
+    host_np = host_pool.numpy()
+    disp_host = torch.empty((B, H, W), dtype=torch.int16).pin_memory()
+    disp_np = disp_host.numpy()
+
+    def batch_dev(step):
+        s = (step * B) % (n_pool - B + 1)
+        return [dev_pool[s + i] for i in range(B)]
+
+    def batch_host(step):
+        s = (step * B) % (n_pool - B + 1)
+        return [host_np[s + i] for i in range(B)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        with torch.cuda.stream(stream):
+            for s in range(warmup):
+                fn(s)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = ctx.kernel_launches
+            t0 = time.perf_counter()
+            e0.record(stream)
+            for s in range(steps):
+                fn(warmup + s)
+            e1.record(stream)
+            barrier()
+            t1 = time.perf_counter()
+        ms = e0.elapsed_time(e1)
+        launches = ctx.kernel_launches - l0
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, t0, t1
+
+    # ---- value: frames resident in HBM ----
+    def step_dev(s):
+        pipe.run(batch_dev(s))
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches, t0, t1 = timed(step_dev, args.steps, args.warmup)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    fps = world * B * args.steps / (ms / 1e3)
+
+    # ---- per-kernel times of one step (CUDA events on the launching stream, inside the library) ----
+    sg = capi.Sgbm(ctx, params)
+    sg.set_profiling(True)
+    gl = torch.empty((B, H, W), dtype=torch.uint8, device="cuda")
+    gr = torch.empty((B, H, W), dtype=torch.uint8, device="cuda")
+    do = torch.empty((B, H, W), dtype=torch.int16, device="cuda")
+    rect = capi.Rectifier(ctx, calib)
+    with torch.cuda.stream(stream):
+        for i in range(B):
+            f = batch_dev(0)[i]
+            _, _, a, b = rect.rectify(f[:, :W], f[:, W:], want_gray=True)
+            gl[i].copy_(a); gr[i].copy_(b)
+        acc = {}
+        reps = 3
+        for rep in range(reps + 1):
+            sg.compute_batch(gl, gr, do)
+            ctx.synchronize()
+            if rep == 0:
+                continue                                  # warm-up (allocations)
+            for name, t in sg.stage_times():
+                acc[name] = acc.get(name, 0.0) + t / reps
+    sg.close(); rect.close()
+    W1 = W - D
+    vol = W1 * H * D * 2                                   # bytes of one int16 volume per frame
+    img = W * H
+    # algorithmic bytes per frame of each SGBM kernel (DESIGN.md "Kernels"): distinct bytes it must read + write
+    algo = {"prefilter": 2 * img + (16 + 24) * img, "cost": (16 + 24) * img + vol, "path_v0": 2 * vol, "path_v1": 3 * vol,
+            "path_v2": 3 * vol, "path_h_fwd": 3 * vol, "path_h_bwd_wta": 2 * vol + 6 * img, "lrcheck": 8 * img,
+            "median3": 4 * img, "speckle": 24 * img}
+    dom = max(acc, key=acc.get)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = algo.get(dom, 2 * vol) * B / (acc[dom] * 1e-3) / 1e9
+    sgbm_ms = sum(acc.values())
+    core_bytes = (2 * vol + 4 * img) * B                   # compulsory 3.69 MB + one int16 volume round trip per frame
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
+                "algorithmic_bytes_per_launch": algo.get(dom, 2 * vol) * B, "kernel_ms": acc[dom],
+                "kernel_share_of_sgbm": acc[dom] / sgbm_ms,
+                "sgbm_core": {"achieved": core_bytes / (sgbm_ms * 1e-3) / 1e9, "frac": core_bytes / (sgbm_ms * 1e-3) / 1e9 / peak,
+                              "ms_per_batch": sgbm_ms, "algorithmic_bytes": core_bytes},
+                "stage_ms_per_batch": {k: round(v, 4) for k, v in acc.items()}}
+
+    # ---- e2e: pinned host frames in, disparity maps + clouds out, through the same C-ABI call ----
+    disp_imgs = [disp_np[i] for i in range(B)]
+    cloud_bytes = [0]
+
+    def step_host(s):
+        pipe.run(batch_host(s), disp=disp_imgs)
+        nb = 0
+        for i in range(B):
+            c = pipe.cloud_to_host(i)
+            nb += c["xyz"].nbytes + c["rgb"].nbytes + (c["idx"].nbytes + c["cnt"].nbytes if "idx" in c else 0)
+        cloud_bytes[0] = nb
+
+    ms_e, _, _, _ = timed(step_host, args.steps, args.warmup)
+    fps_e = world * B * args.steps / (ms_e / 1e3)
+    h2d = B * H * 2 * W * 3
+    d2h = B * H * W * 2 + cloud_bytes[0]
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s16",
+            "data": "synthetic", "mpix_disp_per_s": fps * MPIX_DISP_PER_FRAME,
+            "config": {"workload": "configs[1]: full pipeline per frame at 1280x720x128 (remap + MODE_SGBM + LR + median + speckle + "
+                                   "reproject + 5 mm VoxelGrid)", "frames_per_step_per_gpu": B, "frame_pool": n_pool,
+                       "l2": "inputs larger than L2 (frame pool %d MB, a different batch each step; volumes %d MB per step)" % (
+                           n_pool * H * 2 * W * 3 >> 20, 2 * vol * B >> 20),
+                       "sgbm": list(SGBM_ARGS), "leaf_mm": LEAF_MM, "z_max_mm": Z_MAX_MM, "sharding": "frame i -> rank i mod N, no collective"},
+            "e2e": {"value": fps_e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    pipe.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8, help="frames per step per GPU")
+    ap.add_argument("--pool", type=int, default=32, help="distinct frames resident per GPU (pool > L2)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

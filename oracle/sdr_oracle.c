@@ -560,6 +560,11 @@ static int check_params(const orc_sgbm_params* p, int W, int H) {
     if (p->numDisparities <= 0 || p->numDisparities % 16) return -2;
     if (p->mode != ORC_MODE_SGBM && p->mode != ORC_MODE_HH && p->mode != ORC_MODE_SGBM_3WAY) return -2;
     if (p->blockSize > 0 && p->blockSize % 2 == 0) return -2;
+    /* cv2 raises for these in MODE_SGBM / MODE_HH (CV_Assert in computeDisparitySGBM, "input images are too small ...
+     * non-deterministic SGBM results"); the 3-way path only fails on W1 <= 0 but is non-deterministic in the same
+     * regime, so the oracle (and the CUDA path) refuse it in every mode. */
+    if ((W + imin(p->minDisparity, 0)) - imax(p->minDisparity + p->numDisparities, 0) <= 0) return -2;
+    if (W - (p->minDisparity + p->numDisparities) <= (p->blockSize > 0 ? p->blockSize : 5) / 2) return -2;
     return 0;
 }
 
@@ -646,7 +651,9 @@ ORC_API long orc_voxelgrid(const float* points, const uint8_t* bgr, const uint8_
     int64_t dx = (int64_t)((mx[0] - mn[0]) * inv[0]) + 1;
     int64_t dy = (int64_t)((mx[1] - mn[1]) * inv[1]) + 1;
     int64_t dz = (int64_t)((mx[2] - mn[2]) * inv[2]) + 1;
-    if (dx * dy * dz > (int64_t)INT32_MAX) return -3;
+    /* PCL multiplies in int64; for absurd boxes (the reference's literal leaf 0.005 on a mm cloud) the
+     * product wraps. Two's-complement wrap (what an x86 PCL build does) is made explicit here. */
+    if ((int64_t)((uint64_t)dx * (uint64_t)dy * (uint64_t)dz) > (int64_t)INT32_MAX) return -3;
     int minb[3], maxb[3], divb[3];
     for (int c = 0; c < 3; c++) {
         minb[c] = (int)floorf(mn[c] * inv[c]);
@@ -654,7 +661,7 @@ ORC_API long orc_voxelgrid(const float* points, const uint8_t* bgr, const uint8_
         divb[c] = maxb[c] - minb[c] + 1;
     }
     if (out_minb_divb) for (int c = 0; c < 3; c++) { out_minb_divb[c] = minb[c]; out_minb_divb[3 + c] = divb[c]; }
-    const int mul[3] = {1, divb[0], divb[0] * divb[1]};
+    const int mul[3] = {1, divb[0], (int)((uint32_t)divb[0] * (uint32_t)divb[1])};
     vox_key* keys = (vox_key*)malloc((size_t)nvalid * sizeof(vox_key));
     if (!keys) return -1;
     long k = 0;
@@ -665,7 +672,7 @@ ORC_API long orc_voxelgrid(const float* points, const uint8_t* bgr, const uint8_
         int ijk0 = (int)(floorf(p[0] * inv[0]) - (float)minb[0]);
         int ijk1 = (int)(floorf(p[1] * inv[1]) - (float)minb[1]);
         int ijk2 = (int)(floorf(p[2] * inv[2]) - (float)minb[2]);
-        keys[k].idx = (uint32_t)(ijk0 * mul[0] + ijk1 * mul[1] + ijk2 * mul[2]);
+        keys[k].idx = (uint32_t)ijk0 * (uint32_t)mul[0] + (uint32_t)ijk1 * (uint32_t)mul[1] + (uint32_t)ijk2 * (uint32_t)mul[2];
         keys[k].pt = (uint32_t)i;
         k++;
     }

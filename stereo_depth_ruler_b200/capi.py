@@ -78,6 +78,7 @@ SYMBOLS = [
     "sdr_median3_16s", "sdr_filter_speckles", "sdr_reproject_to_3d",
     "sdr_cloud_create", "sdr_cloud_destroy", "sdr_voxelgrid", "sdr_depth_cloud", "sdr_cloud_download",
     "sdr_pipeline_create", "sdr_pipeline_destroy", "sdr_pipeline_run", "sdr_pipeline_stage_times",
+    "sdr_pipeline_cloud_download",
 ]
 
 _lib = None
@@ -269,3 +270,191 @@ def filter_speckles(ctx, img, new_val, max_size, max_diff):
     ii, _ = as_image(out, 1)
     ctx.check(lib().sdr_filter_speckles(ctx._h, C.byref(ii), int(new_val), int(max_size), int(max_diff)))
     return out
+
+
+def _empty_like_kind(ref, shape, np_dtype, torch_dtype_name):
+    if _is_torch(ref):
+        import torch
+        return torch.empty(shape, dtype=getattr(torch, torch_dtype_name), device=ref.device)
+    return np.empty(shape, np_dtype)
+
+
+class Rectifier:
+    """StereoRectifier stand-in (sdr_rectifier_*): fused initUndistortRectifyMap + remap (+ BGR2GRAY)."""
+
+    def __init__(self, ctx, calib):
+        self.ctx = ctx
+        self.calib = calib
+        self.size = (calib.image_width, calib.image_height)
+        self._h = C.c_void_p()
+        ctx.check(lib().sdr_rectifier_create(ctx._h, C.byref(calib), C.byref(self._h)))
+
+    def maps(self, eye):
+        W, H = self.size
+        m1 = np.empty((H, W, 2), np.int16)
+        m2 = np.empty((H, W), np.uint16)
+        self.ctx.check(lib().sdr_rectifier_get_maps(self._h, int(eye), m1.ctypes.data_as(C.c_void_p), m2.ctypes.data_as(C.c_void_p)))
+        return m1, m2
+
+    def rectify(self, left_src, right_src, want_gray=False):
+        W, H = self.size
+        ch = 1 if len(left_src.shape) == 2 else left_src.shape[2]
+        shp = (H, W) if ch == 1 else (H, W, ch)
+        ld = _empty_like_kind(left_src, shp, np.uint8, "uint8")
+        rd = _empty_like_kind(left_src, shp, np.uint8, "uint8")
+        li, _ = as_image(left_src); ri, _ = as_image(right_src)
+        ldi, _ = as_image(ld); rdi, _ = as_image(rd)
+        if want_gray:
+            lg = _empty_like_kind(left_src, (H, W), np.uint8, "uint8")
+            rg = _empty_like_kind(left_src, (H, W), np.uint8, "uint8")
+            lgi, _ = as_image(lg); rgi, _ = as_image(rg)
+            self.ctx.check(lib().sdr_rectify(self._h, C.byref(li), C.byref(ri), C.byref(ldi), C.byref(rdi), C.byref(lgi), C.byref(rgi)))
+            return ld, rd, lg, rg
+        self.ctx.check(lib().sdr_rectify(self._h, C.byref(li), C.byref(ri), C.byref(ldi), C.byref(rdi), None, None))
+        return ld, rd
+
+    def close(self):
+        if self._h:
+            lib().sdr_rectifier_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def remap_with_maps(ctx, src, map1, map2):
+    H, W = map2.shape
+    ch = 1 if src.ndim == 2 else src.shape[2]
+    dst = np.empty((H, W) if ch == 1 else (H, W, ch), np.uint8)
+    si, _ = as_image(src); di, _ = as_image(dst)
+    m1 = np.ascontiguousarray(map1, np.int16); m2 = np.ascontiguousarray(map2, np.uint16)
+    ctx.check(lib().sdr_remap_with_maps(ctx._h, C.byref(si), m1.ctypes.data_as(C.c_void_p), m2.ctypes.data_as(C.c_void_p), C.byref(di)))
+    return dst
+
+
+def bgr2gray(ctx, bgr):
+    out = _empty_like_kind(bgr, tuple(bgr.shape[:2]), np.uint8, "uint8")
+    si, _ = as_image(bgr, 3); di, _ = as_image(out, 1)
+    ctx.check(lib().sdr_bgr2gray(ctx._h, C.byref(si), C.byref(di)))
+    return out
+
+
+def reproject_to_3d(ctx, disp, Q, handle_missing=False):
+    """disp: int16 (CV_16S, /16 fused) or float32. Returns float32 [H][W][3]."""
+    out = _empty_like_kind(disp, tuple(disp.shape) + (3,), np.float32, "float32")
+    di, _ = as_image(disp, 1); oi, _ = as_image(out, 3)
+    q = (C.c_double * 16)(*np.asarray(Q, np.float64).ravel())
+    ctx.check(lib().sdr_reproject_to_3d(ctx._h, C.byref(di), q, int(bool(handle_missing)), C.byref(oi)))
+    return out
+
+
+def voxel_options(leaf, drop_invalid=False, z_max=0.0, min_disparity=0):
+    leaf = (leaf,) * 3 if np.isscalar(leaf) else tuple(leaf)
+    return VoxelOptions((C.c_float * 3)(*leaf), int(bool(drop_invalid)), float(z_max), int(min_disparity))
+
+
+class Cloud:
+    """convertCVMatToPCL + pcl::VoxelGrid stand-in (sdr_cloud_*)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        ctx.check(lib().sdr_cloud_create(ctx._h, C.byref(self._h)))
+        self.view = CloudView()
+
+    def _download(self):
+        v = self.view
+        n = int(v.n)
+        xyz = np.empty((n, 3), np.float32); rgb = np.empty((n, 3), np.uint8)
+        idx = np.empty(n, np.uint32); cnt = np.empty(n, np.uint32)
+        self.ctx.check(lib().sdr_cloud_download(self._h, xyz.ctypes.data_as(C.c_void_p), rgb.ctypes.data_as(C.c_void_p),
+                                                idx.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)))
+        res = dict(xyz=xyz, rgb=rgb, passthrough=bool(v.passthrough), minb=np.array(v.min_b[:]), divb=np.array(v.div_b[:]))
+        if not v.passthrough:
+            res.update(idx=idx, cnt=cnt)
+        return res
+
+    def voxelgrid(self, points, bgr, opt, disp16=None, download=True):
+        pi, _ = as_image(points, 3)
+        bi = as_image(bgr, 3)[0] if bgr is not None else None
+        di = as_image(disp16, 1)[0] if disp16 is not None else None
+        rc = lib().sdr_voxelgrid(self._h, C.byref(pi), C.byref(bi) if bi else None, C.byref(di) if di else None,
+                                 C.byref(opt), C.byref(self.view))
+        self.ctx.check(rc, ok=(SDR_OK, SDR_EVOXEL_OVERFLOW))
+        return self._download() if download else self.view
+
+    def depth_cloud(self, disp16, bgr, Q, opt, handle_missing=False, download=True):
+        di, _ = as_image(disp16, 1)
+        bi = as_image(bgr, 3)[0] if bgr is not None else None
+        q = (C.c_double * 16)(*np.asarray(Q, np.float64).ravel())
+        rc = lib().sdr_depth_cloud(self._h, C.byref(di), C.byref(bi) if bi else None, q, int(bool(handle_missing)),
+                                   C.byref(opt), C.byref(self.view))
+        self.ctx.check(rc, ok=(SDR_OK, SDR_EVOXEL_OVERFLOW))
+        return self._download() if download else self.view
+
+    def close(self):
+        if self._h:
+            lib().sdr_cloud_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Pipeline:
+    """SBS frame -> rectify -> SGBM -> reproject -> VoxelGrid, device resident (sdr_pipeline_*)."""
+
+    def __init__(self, ctx, calib, sgbm_params, voxel_opt, handle_missing=False, batch=1, want_points=False):
+        self.ctx = ctx
+        self.calib = calib
+        self.batch = batch
+        self.opt = PipelineOptions(sgbm_params, voxel_opt, int(bool(handle_missing)), int(batch), int(bool(want_points)))
+        self._h = C.c_void_p()
+        ctx.check(lib().sdr_pipeline_create(ctx._h, C.byref(calib), C.byref(self.opt), C.byref(self._h)))
+        self.views = (CloudView * batch)()
+
+    def run(self, sbs_frames, disp=None, points=None, left_rect=None, clouds=True):
+        n = len(sbs_frames)
+        S = (Image * n)(*[as_image(f, 3)[0] for f in sbs_frames])
+        D = (Image * n)(*[as_image(d, 1)[0] for d in disp]) if disp is not None else None
+        Pn = (Image * n)(*[as_image(p, 3)[0] for p in points]) if points is not None else None
+        Lr = (Image * n)(*[as_image(p, 3)[0] for p in left_rect]) if left_rect is not None else None
+        rc = lib().sdr_pipeline_run(self._h, n, S, D, Pn, Lr, self.views if clouds else None)
+        self.ctx.check(rc, ok=(SDR_OK, SDR_EVOXEL_OVERFLOW))
+        return rc
+
+    def cloud_to_host(self, i):
+        """Copies cloud i of the last run to numpy (device -> host)."""
+        v = self.views[i]
+        n = int(v.n)
+        xyz = np.empty((n, 3), np.float32); rgb = np.empty((n, 3), np.uint8)
+        idx = np.empty(n, np.uint32); cnt = np.empty(n, np.uint32)
+        self.ctx.check(lib().sdr_pipeline_cloud_download(self._h, int(i), xyz.ctypes.data_as(C.c_void_p), rgb.ctypes.data_as(C.c_void_p),
+                                                         idx.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)))
+        out = dict(xyz=xyz, rgb=rgb, passthrough=bool(v.passthrough), minb=np.array(v.min_b[:]), divb=np.array(v.div_b[:]))
+        if not v.passthrough:
+            out.update(idx=idx, cnt=cnt)
+        return out
+
+    def stage_times(self):
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        n = lib().sdr_pipeline_stage_times(self._h, 64, names, ms)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
+    def close(self):
+        if self._h:
+            lib().sdr_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

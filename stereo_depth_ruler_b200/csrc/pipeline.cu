@@ -1,0 +1,165 @@
+// Whole hot path per frame, device-resident end to end: the loop body of
+// StereoDisplayer::show_disparity_overlay (stereo_vision/src/stereo_displayer.cpp:155-162:
+// split the SBS frame, rectify, disparity, depth) composed with save_and_display_pointcloud
+// (point_cloud/src/pcd_write.cpp:82-130: gray, SGBM, /16, reproject, colourise, VoxelGrid).
+#include "sdr_internal.h"
+
+#include <cstring>
+
+struct sdr_pipeline {
+    sdr_ctx* ctx = nullptr;
+    sdr_calibration calib{};
+    sdr_pipeline_options opt{};
+    sdr_rectifier* rect = nullptr;
+    sdr_sgbm* sgbm = nullptr;
+    std::vector<sdr_cloud*> clouds;
+    DevBuf sbs, rectL, rectR, grayL, grayR, disp, points, minkey;
+    StageTimer timer;
+};
+
+extern "C" int sdr_pipeline_create(sdr_ctx* ctx, const sdr_calibration* calib, const sdr_pipeline_options* opt, sdr_pipeline** out) {
+    if (!ctx || !calib || !opt || !out) return SDR_EINVAL;
+    if (opt->batch < 1) return SDR_FAIL(ctx, SDR_EINVAL, "pipeline: batch must be >= 1");
+    sdr_pipeline* p = new sdr_pipeline();
+    p->ctx = ctx;
+    p->calib = *calib;
+    p->opt = *opt;
+    int rc = sdr_rectifier_create(ctx, calib, &p->rect);
+    if (rc == SDR_OK) rc = sdr_sgbm_create(ctx, &opt->sgbm, &p->sgbm);
+    for (int i = 0; rc == SDR_OK && i < opt->batch; i++) {
+        sdr_cloud* c = nullptr;
+        rc = sdr_cloud_create(ctx, &c);
+        if (rc == SDR_OK) p->clouds.push_back(c);
+    }
+    if (rc != SDR_OK) {
+        sdr_pipeline_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return SDR_OK;
+}
+
+extern "C" void sdr_pipeline_destroy(sdr_pipeline* p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    if (p->rect) sdr_rectifier_destroy(p->rect);
+    if (p->sgbm) sdr_sgbm_destroy(p->sgbm);
+    for (sdr_cloud* c : p->clouds) sdr_cloud_destroy(c);
+    for (DevBuf* b : {&p->sbs, &p->rectL, &p->rectR, &p->grayL, &p->grayR, &p->disp, &p->points, &p->minkey}) b->release();
+    p->timer.release();
+    delete p;
+}
+
+extern "C" int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sdr_image* disp, sdr_image* points, sdr_image* left_rect,
+                                sdr_cloud_view* views) {
+    if (!p || n <= 0 || !sbs) return SDR_EINVAL;
+    sdr_ctx* ctx = p->ctx;
+    SDR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n > p->opt.batch) return SDR_FAIL(ctx, SDR_EINVAL, "pipeline: %d frames submitted, batch is %d", n, p->opt.batch);
+    const int W = p->calib.image_width, H = p->calib.image_height;
+    cudaStream_t st = ctx->stream;
+    int rc;
+    for (int i = 0; i < n; i++) {
+        if ((rc = sdr_check_image(ctx, &sbs[i], 3, 1, "sbs"))) return rc;
+        if (sbs[i].cols != 2 * W || sbs[i].rows != H)
+            return SDR_FAIL(ctx, SDR_ESIZE, "pipeline: SBS frame must be %dx%d, got %dx%d", 2 * W, H, sbs[i].cols, sbs[i].rows);
+    }
+    p->timer.begin(st);
+    // 1. frames to the device (used in place when they are already there at a constant stride)
+    const size_t sbs_row = (size_t)2 * W * 3, sbs_frame_c = sbs_row * H;
+    const uint8_t* S0;
+    size_t sstep, sframe;
+    bool in_place = sbs[0].mem == SDR_MEM_DEVICE;
+    sframe = n > 1 ? (size_t)((const uint8_t*)sbs[1].data - (const uint8_t*)sbs[0].data) : 0;
+    for (int i = 0; i < n && in_place; i++)
+        in_place = sbs[i].mem == SDR_MEM_DEVICE && sbs[i].step_bytes == sbs[0].step_bytes &&
+                   (const uint8_t*)sbs[i].data == (const uint8_t*)sbs[0].data + (size_t)i * sframe;
+    if (in_place) {
+        S0 = (const uint8_t*)sbs[0].data; sstep = sbs[0].step_bytes;
+    } else {
+        if ((rc = p->sbs.reserve(ctx, sbs_frame_c * n))) return rc;
+        for (int i = 0; i < n; i++)
+            SDR_CUDA(ctx, cudaMemcpy2DAsync(p->sbs.as<uint8_t>() + (size_t)i * sbs_frame_c, sbs_row, sbs[i].data, sbs[i].step_bytes, sbs_row, H,
+                                            cudaMemcpyDefault, st));
+        S0 = p->sbs.as<uint8_t>(); sstep = sbs_row; sframe = sbs_frame_c;
+    }
+    p->timer.mark(st, "h2d");
+    // 2. rectify both eyes (+ gray) in one launch
+    const size_t bgr_frame = (size_t)W * H * 3, gray_frame = (size_t)W * H;
+    if ((rc = p->rectL.reserve(ctx, bgr_frame * n)) || (rc = p->rectR.reserve(ctx, bgr_frame * n)) ||
+        (rc = p->grayL.reserve(ctx, gray_frame * n)) || (rc = p->grayR.reserve(ctx, gray_frame * n)) ||
+        (rc = p->disp.reserve(ctx, gray_frame * 2 * n)) || (rc = p->minkey.reserve(ctx, 256 + 4 * (size_t)n)))
+        return rc;
+    {
+        const uint8_t* src[2] = {S0, S0 + (size_t)W * 3};
+        const size_t ss[2] = {sstep, sstep}, sf[2] = {sframe, sframe};
+        uint8_t* dst[2] = {p->rectL.as<uint8_t>(), p->rectR.as<uint8_t>()};
+        const size_t ds[2] = {(size_t)W * 3, (size_t)W * 3}, df[2] = {bgr_frame, bgr_frame};
+        uint8_t* gr[2] = {p->grayL.as<uint8_t>(), p->grayR.as<uint8_t>()};
+        const size_t gs[2] = {(size_t)W, (size_t)W}, gf[2] = {gray_frame, gray_frame};
+        if ((rc = sdr_launch_rectify(p->rect, n, 3, src, ss, sf, W, H, dst, ds, df, gr, gs, gf))) return rc;
+    }
+    p->timer.mark(st, "rectify");
+    // 3. disparity
+    if ((rc = sdr_sgbm_run_device(p->sgbm, n, p->grayL.as<uint8_t>(), W, gray_frame, p->grayR.as<uint8_t>(), W, gray_frame, W, H,
+                                  p->disp.as<int16_t>(), (size_t)W * 2, gray_frame * 2)))
+        return rc;
+    p->timer.mark(st, "sgbm");
+    // 4. depth image (optional) and clouds (reprojection fused into the voxel kernels)
+    const bool need_points = p->opt.want_points || points;
+    if (need_points) {
+        if ((rc = p->points.reserve(ctx, (size_t)W * H * 12 * n))) return rc;
+        if ((rc = sdr_launch_reproject(ctx, true, p->disp.as<uint8_t>(), (size_t)W * 2, gray_frame * 2, W, H, n, p->calib.Q, p->opt.handle_missing,
+                                       p->minkey.as<int>(), p->points.as<float>(), (size_t)W * 12, (size_t)W * H * 12)))
+            return rc;
+        p->timer.mark(st, "reproject");
+    }
+    if (views) {
+        for (int i = 0; i < n; i++) {
+            if ((rc = sdr_cloud_enqueue(p->clouds[i], nullptr, 0, p->disp.as<uint8_t>() + (size_t)i * gray_frame * 2, (size_t)W * 2,
+                                        p->rectL.as<uint8_t>() + (size_t)i * bgr_frame, (size_t)W * 3, W, H, p->calib.Q, p->opt.handle_missing,
+                                        &p->opt.voxel)))
+                return rc;
+        }
+        p->timer.mark(st, "voxelgrid");
+    }
+    // 5. outputs
+    for (int i = 0; i < n; i++) {
+        if (disp) {
+            if ((rc = sdr_check_image(ctx, &disp[i], 1, 2, "disp")) ) return rc;
+            SDR_CUDA(ctx, cudaMemcpy2DAsync(disp[i].data, disp[i].step_bytes, p->disp.as<uint8_t>() + (size_t)i * gray_frame * 2, (size_t)W * 2,
+                                            (size_t)W * 2, H, cudaMemcpyDefault, st));
+        }
+        if (points) {
+            if ((rc = sdr_check_image(ctx, &points[i], 3, 4, "points"))) return rc;
+            SDR_CUDA(ctx, cudaMemcpy2DAsync(points[i].data, points[i].step_bytes, p->points.as<uint8_t>() + (size_t)i * W * H * 12, (size_t)W * 12,
+                                            (size_t)W * 12, H, cudaMemcpyDefault, st));
+        }
+        if (left_rect) {
+            if ((rc = sdr_check_image(ctx, &left_rect[i], 3, 1, "left_rect"))) return rc;
+            SDR_CUDA(ctx, cudaMemcpy2DAsync(left_rect[i].data, left_rect[i].step_bytes, p->rectL.as<uint8_t>() + (size_t)i * bgr_frame, (size_t)W * 3,
+                                            (size_t)W * 3, H, cudaMemcpyDefault, st));
+        }
+    }
+    p->timer.mark(st, "d2h");
+    int status = SDR_OK;
+    if (views)
+        for (int i = 0; i < n; i++) {
+            rc = sdr_cloud_finish(p->clouds[i], &views[i]);
+            if (rc == SDR_EVOXEL_OVERFLOW) status = rc;
+            else if (rc) return rc;
+        }
+    SDR_CUDA(ctx, cudaStreamSynchronize(st));
+    return status;
+}
+
+extern "C" int sdr_pipeline_stage_times(sdr_pipeline* p, int cap, const char** names, float* ms) {
+    if (!p) return 0;
+    cudaSetDevice(p->ctx->device);
+    return p->timer.collect(cap, names, ms);
+}
+
+extern "C" int sdr_pipeline_cloud_download(sdr_pipeline* p, int i, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt) {
+    if (!p || i < 0 || i >= (int)p->clouds.size()) return SDR_EINVAL;
+    return sdr_cloud_download(p->clouds[i], xyz, rgb, idx, cnt);
+}

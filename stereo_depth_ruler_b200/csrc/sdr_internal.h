@@ -92,3 +92,16 @@ struct StageTimer {
     int collect(int cap, const char** out_names, float* ms);
     void release();
 };
+
+// ---- device-pointer entry points used by the per-frame pipeline ----
+int sdr_sgbm_run_device(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, size_t lframe, const uint8_t* R, size_t rpitch,
+                        size_t rframe, int W, int H, int16_t* out, size_t opitch, size_t oframe);
+int sdr_launch_rectify(sdr_rectifier* r, int batch, int channels, const uint8_t* const src[2], const size_t src_step[2],
+                       const size_t src_frame[2], int sw, int sh, uint8_t* const dst[2], const size_t dst_step[2],
+                       const size_t dst_frame[2], uint8_t* const gray[2], const size_t gray_step[2], const size_t gray_frame[2]);
+int sdr_launch_reproject(sdr_ctx* ctx, bool is16, const uint8_t* disp, size_t step, size_t frame, int W, int H, int batch,
+                         const double* Q, int handle_missing, int* min_key, float* out, size_t ostep, size_t oframe);
+int sdr_cloud_enqueue(sdr_cloud* c, const uint8_t* points, size_t pstep, const uint8_t* disp, size_t dstep, const uint8_t* bgr, size_t cstep,
+                      int W, int H, const double* Q, int handle_missing, const sdr_voxel_options* opt);
+int sdr_cloud_finish(sdr_cloud* c, sdr_cloud_view* view);
+StageTimer* sdr_sgbm_timer(sdr_sgbm* m);

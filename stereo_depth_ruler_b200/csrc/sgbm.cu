@@ -668,10 +668,17 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
     // raw matcher output goes to m->matched, median to m->out (or directly to `out`)
     const size_t img16 = (size_t)W * H * sizeof(int16_t);
     if ((rc = m->matched.reserve(ctx, img16 * batch))) return rc;
-    if (g.W1 <= 0) {
-        k_fill16<<<dim3(div_up(W, 256), H, batch), 256, 0, st>>>(m->matched.as<int16_t>(), (size_t)W * 2, img16, W, H, INV);
-        SDR_LAUNCHED(ctx);
-    } else {
+    // OpenCV refuses these inputs in MODE_SGBM / MODE_HH (CV_Assert in computeDisparitySGBM: "Your input images are too
+    // small for your window size and max disparity, and will result in non-deterministic SGBM results"). Its 3-way path
+    // lacks the assert (it only fails on W1 <= 0) but is in the same non-deterministic regime, so it is refused too.
+    {
+        const int sw2 = (m->p.blockSize > 0 ? m->p.blockSize : 5) / 2;
+        if (g.W1 <= 0 || W - (g.minD + g.D) <= sw2)
+            return SDR_FAIL(ctx, SDR_EINVAL,
+                            "input images are too small for the window size and max disparity: width - (minDisparity + "
+                            "numDisparities) = %d must be greater than %d", W - (g.minD + g.D), sw2);
+    }
+    {
         const size_t vol = (size_t)g.W1 * g.D * sizeof(int16_t);
         if ((rc = m->PL.reserve(ctx, (size_t)batch * H * W * sizeof(int4)))) return rc;
         if ((rc = m->PR.reserve(ctx, (size_t)batch * H * 24 * g.Wp))) return rc;
@@ -733,6 +740,12 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
     }
     return SDR_OK;
 }
+
+int sdr_sgbm_run_device(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, size_t lframe, const uint8_t* R, size_t rpitch,
+                        size_t rframe, int W, int H, int16_t* out, size_t opitch, size_t oframe) {
+    return sgbm_run(m, batch, L, lpitch, lframe, R, rpitch, rframe, W, H, out, opitch, oframe);
+}
+StageTimer* sdr_sgbm_timer(sdr_sgbm* m) { return &m->timer; }
 
 extern "C" int sdr_sgbm_compute_batch(sdr_sgbm* m, int n, const sdr_image* lefts, const sdr_image* rights, sdr_image* disps) {
     if (!m || n <= 0 || !lefts || !rights || !disps) return SDR_EINVAL;

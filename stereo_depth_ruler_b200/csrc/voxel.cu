@@ -1,0 +1,537 @@
+// convertCVMatToPCL + pcl::VoxelGrid<PointXYZRGB>::filter (point_cloud/src/pcd_write.cpp:17-51,
+// :123-130 of the reference; PCL 1.14 semantics restated in SURVEY.md Appendix A.8), optionally fused
+// with cv::reprojectImageTo3D so the W*H*3 float image never reaches HBM.
+//
+// PCL's algorithm is kept step for step so that the output is the same cloud in the same order:
+//   bbox of the finite points -> int32 index guard (passthrough when it trips) -> per point
+//   idx = i + j*dx + k*dx*dy -> sort by idx -> one output point per run of equal idx (fp32 sums in
+//   sorted order, colour means truncated). The sort is a stable LSD radix sort written here
+//   (4 x 8-bit passes: histogram, digit-major scan, ranked scatter).
+#include "sdr_internal.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+struct QMat {
+    double q[16];
+};
+
+struct VoxParams {  // lives on the device; written by k_vox_params
+    float inv[3];
+    int minb[3], divb[3], mul[3];
+    int overflow;
+    unsigned nvalid;
+    int bbox_key[6];  // min xyz, max xyz as ordered-int keys
+    unsigned nvox;
+    int min_disp_key;
+};
+
+struct Source {  // where a pixel's 3-D point comes from
+    const uint8_t* points;  // f32x3 image, or null
+    size_t pstep;
+    const uint8_t* disp;  // int16 image (required when points == null or drop_invalid)
+    size_t dstep;
+    const uint8_t* bgr;  // optional
+    size_t cstep;
+    int W, H;
+    QMat Q;
+    int handle_missing, from_disp;
+    int drop_invalid, min_valid16;  // drop when disp16 < min_valid16
+    float z_max;
+};
+
+__device__ __forceinline__ int fkey(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float kfloat(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
+
+// xyz of pixel i; returns false when the point does not enter the voxel grid.
+__device__ __forceinline__ bool fetch_point(const Source& s, const VoxParams* vp, int i, float& X, float& Y, float& Z) {
+    const int y = i / s.W, x = i - y * s.W;
+    int d16 = 0;
+    if (s.disp) d16 = ((const int16_t*)(s.disp + (size_t)y * s.dstep))[x];
+    if (s.from_disp) {
+        const float df = (float)d16 * 0.0625f;
+        const double d = (double)df, dx = (double)x, dy = (double)y;
+        double h[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            h[c] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(s.Q.q[c * 4], dx), __dmul_rn(s.Q.q[c * 4 + 1], dy)), __dmul_rn(s.Q.q[c * 4 + 2], d)),
+                             s.Q.q[c * 4 + 3]);
+        const double iw = __ddiv_rn(1.0, h[3]);
+        X = (float)__dmul_rn((double)(float)h[0], iw);
+        Y = (float)__dmul_rn((double)(float)h[1], iw);
+        Z = (float)__dmul_rn((double)(float)h[2], iw);
+        if (s.handle_missing && fabs(d - (double)kfloat(vp->min_disp_key)) <= 1.1920928955078125e-07) Z = 10000.f;
+    } else {
+        const float* p = (const float*)(s.points + (size_t)y * s.pstep) + (size_t)x * 3;
+        X = p[0]; Y = p[1]; Z = p[2];
+    }
+    if (!(isfinite(X) && isfinite(Y) && isfinite(Z))) return false;  // pcd_write.cpp:35 + PCL isXYZFinite
+    if (s.drop_invalid && d16 < s.min_valid16) return false;
+    if (s.z_max > 0.f && !(Z > 0.f && Z <= s.z_max)) return false;
+    return true;
+}
+
+__global__ void k_vox_reset(VoxParams* vp) {
+    vp->bbox_key[0] = vp->bbox_key[1] = vp->bbox_key[2] = 0x7FFFFFFF;
+    vp->bbox_key[3] = vp->bbox_key[4] = vp->bbox_key[5] = (int)0x80000000;
+    vp->nvalid = 0;
+    vp->nvox = 0;
+    vp->overflow = 0;
+    vp->min_disp_key = 0x7FFFFFFF;
+}
+
+__global__ void __launch_bounds__(256) k_vox_mindisp(Source s, VoxParams* vp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int key = 0x7FFFFFFF;
+    if (i < s.W * s.H) {
+        const int y = i / s.W, x = i - y * s.W;
+        key = fkey((float)((const int16_t*)(s.disp + (size_t)y * s.dstep))[x] * 0.0625f);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+    if ((threadIdx.x & 31) == 0 && key != 0x7FFFFFFF) atomicMin(&vp->min_disp_key, key);
+}
+
+__global__ void __launch_bounds__(256) k_vox_bbox(Source s, VoxParams* vp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int mn[3] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF}, mx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+    unsigned ok = 0;
+    if (i < s.W * s.H) {
+        float p[3];
+        if (fetch_point(s, vp, i, p[0], p[1], p[2])) {
+            ok = 1;
+#pragma unroll
+            for (int c = 0; c < 3; c++) mn[c] = mx[c] = fkey(p[c]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            mn[c] = min(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            mx[c] = max(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        }
+        ok += __shfl_xor_sync(0xffffffffu, ok, o);
+    }
+    if ((threadIdx.x & 31) == 0 && ok) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            atomicMin(&vp->bbox_key[c], mn[c]);
+            atomicMax(&vp->bbox_key[3 + c], mx[c]);
+        }
+        atomicAdd(&vp->nvalid, ok);
+    }
+}
+
+// PCL: inverse leaf, int64 guard, min_b / div_b / divb_mul (all fp32 as in voxel_grid.hpp)
+__global__ void k_vox_params(VoxParams* vp, float lx, float ly, float lz) {
+    const float leaf[3] = {lx, ly, lz};
+    if (vp->nvalid == 0) {
+        for (int c = 0; c < 3; c++) { vp->inv[c] = __fdiv_rn(1.0f, leaf[c]); vp->minb[c] = 0; vp->divb[c] = 1; vp->mul[c] = 1; }
+        return;
+    }
+    long long d[3];
+    for (int c = 0; c < 3; c++) {
+        const float inv = __fdiv_rn(1.0f, leaf[c]);
+        const float mn = kfloat(vp->bbox_key[c]), mx = kfloat(vp->bbox_key[3 + c]);
+        vp->inv[c] = inv;
+        d[c] = (long long)__fmul_rn(__fsub_rn(mx, mn), inv) + 1;
+        vp->minb[c] = (int)floorf(__fmul_rn(mn, inv));
+        const int maxb = (int)floorf(__fmul_rn(mx, inv));
+        vp->divb[c] = maxb - vp->minb[c] + 1;
+    }
+    // PCL multiplies in int64; for absurd boxes the product wraps (two's complement, as on x86)
+    const long long prod = (long long)((unsigned long long)d[0] * (unsigned long long)d[1] * (unsigned long long)d[2]);
+    vp->overflow = prod > 2147483647LL ? 1 : 0;
+    vp->mul[0] = 1;
+    vp->mul[1] = vp->divb[0];
+    vp->mul[2] = (int)((unsigned)vp->divb[0] * (unsigned)vp->divb[1]);
+}
+
+__global__ void __launch_bounds__(256) k_vox_keys(Source s, const VoxParams* vp, uint32_t* keys, uint32_t* vals, int npad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad) return;
+    uint32_t key = 0xFFFFFFFFu;
+    if (i < s.W * s.H && !vp->overflow) {
+        float p[3];
+        if (fetch_point(s, vp, i, p[0], p[1], p[2])) {
+            const int i0 = (int)__fsub_rn(floorf(__fmul_rn(p[0], vp->inv[0])), (float)vp->minb[0]);
+            const int i1 = (int)__fsub_rn(floorf(__fmul_rn(p[1], vp->inv[1])), (float)vp->minb[1]);
+            const int i2 = (int)__fsub_rn(floorf(__fmul_rn(p[2], vp->inv[2])), (float)vp->minb[2]);
+            key = (uint32_t)i0 * (uint32_t)vp->mul[0] + (uint32_t)i1 * (uint32_t)vp->mul[1] + (uint32_t)i2 * (uint32_t)vp->mul[2];
+        }
+    }
+    keys[i] = key;
+    vals[i] = (uint32_t)i;
+}
+
+// ---- stable LSD radix sort, 8-bit digits ---------------------------------------------------
+constexpr int RS_THREADS = 256, RS_ITEMS = 8, RS_TILE = RS_THREADS * RS_ITEMS;
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint32_t* __restrict__ keys, int n, int shift, uint32_t* __restrict__ hist,
+                                                        int nblocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; k++) {
+        const int i = base + k * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of m uint32 values by one block (digit-major histogram, or head flags)
+__global__ void __launch_bounds__(1024) k_scan_block(uint32_t* data, int m, uint32_t* total) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < m; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < m ? data[i] : 0;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warp_sums[threadIdx.x], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (threadIdx.x >= o) wi += t;
+            }
+            warp_sums[threadIdx.x] = wi - w;  // exclusive
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_sums[threadIdx.x >> 5] + incl - v;
+        if (i < m) data[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n,
+                                                           int shift, const uint32_t* __restrict__ hist, int nblocks,
+                                                           uint32_t* __restrict__ okeys, uint32_t* __restrict__ ovals) {
+    constexpr int NW = RS_THREADS / 32;
+    __shared__ uint32_t wcount[NW][256];
+    for (int i = threadIdx.x; i < NW * 256; i += RS_THREADS) (&wcount[0][0])[i] = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp w owns the contiguous sub-tile [w*256, (w+1)*256) of the block's tile: order = (block, warp, round, lane)
+    const int base = blockIdx.x * RS_TILE + warp * (RS_ITEMS * 32);
+    uint32_t k[RS_ITEMS], v[RS_ITEMS], rank[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const int i = base + r * 32 + lane;
+        const bool in = i < n;
+        k[r] = in ? keys[i] : 0xFFFFFFFFu;
+        v[r] = in ? vals[i] : 0;
+        const uint32_t d = (k[r] >> shift) & 255u;
+        const unsigned act = __ballot_sync(0xffffffffu, in);
+        rank[r] = 0;
+        if (in) {
+            const unsigned peers = __match_any_sync(act, d);
+            const uint32_t before = wcount[warp][d];
+            rank[r] = before + __popc(peers & ((1u << lane) - 1));
+            __syncwarp(act);
+            if (lane == __ffs(peers) - 1) wcount[warp][d] = before + __popc(peers);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit: exclusive prefix over warps + global base of this block
+    {
+        const int d = threadIdx.x;  // RS_THREADS == 256 digits
+        uint32_t run = hist[(size_t)d * nblocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            const uint32_t c = wcount[w][d];
+            wcount[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const int i = base + r * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (k[r] >> shift) & 255u;
+            const uint32_t pos = wcount[warp][d] + rank[r];
+            okeys[pos] = k[r];
+            ovals[pos] = v[r];
+        }
+    }
+}
+
+// ---- run detection and reduction -------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_vox_heads(const uint32_t* __restrict__ keys, int n, uint32_t* __restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = keys[i];
+    flags[i] = (k != 0xFFFFFFFFu && (i == 0 || keys[i - 1] != k)) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_vox_reduce(Source s, VoxParams* vp, const uint32_t* __restrict__ keys,
+                                                    const uint32_t* __restrict__ vals, const uint32_t* __restrict__ slot, int n,
+                                                    float* __restrict__ oxyz, uint8_t* __restrict__ orgb, uint32_t* __restrict__ oidx,
+                                                    uint32_t* __restrict__ ocnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t key = keys[i];
+    if (key == 0xFFFFFFFFu || (i > 0 && keys[i - 1] == key)) return;
+    float sx = 0.f, sy = 0.f, sz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
+    int cnt = 0;
+    for (int j = i; j < n && keys[j] == key; j++) {
+        const int pt = (int)vals[j];
+        float X, Y, Z;
+        fetch_point(s, vp, pt, X, Y, Z);
+        sx = __fadd_rn(sx, X); sy = __fadd_rn(sy, Y); sz = __fadd_rn(sz, Z);
+        if (s.bgr) {
+            const int y = pt / s.W, x = pt - y * s.W;
+            const uint8_t* c = s.bgr + (size_t)y * s.cstep + (size_t)x * 3;
+            sr = __fadd_rn(sr, (float)c[2]); sg = __fadd_rn(sg, (float)c[1]); sb = __fadd_rn(sb, (float)c[0]);
+        }
+        cnt++;
+    }
+    const uint32_t o = slot[i];
+    const float fc = (float)cnt;
+    oxyz[(size_t)o * 3] = __fdiv_rn(sx, fc);
+    oxyz[(size_t)o * 3 + 1] = __fdiv_rn(sy, fc);
+    oxyz[(size_t)o * 3 + 2] = __fdiv_rn(sz, fc);
+    orgb[(size_t)o * 3] = (uint8_t)(uint32_t)__fdiv_rn(sr, fc);
+    orgb[(size_t)o * 3 + 1] = (uint8_t)(uint32_t)__fdiv_rn(sg, fc);
+    orgb[(size_t)o * 3 + 2] = (uint8_t)(uint32_t)__fdiv_rn(sb, fc);
+    oidx[o] = key;
+    ocnt[o] = (uint32_t)cnt;
+}
+
+// PCL passthrough ("Leaf size is too small"): output = input cloud, organised, NaN where non-finite.
+__global__ void __launch_bounds__(256) k_vox_passthrough(Source s, const VoxParams* vp, float* __restrict__ oxyz, uint8_t* __restrict__ orgb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.W * s.H || !vp->overflow) return;
+    Source t = s;
+    t.drop_invalid = 0;
+    t.z_max = 0.f;
+    float X, Y, Z;
+    const bool fin = fetch_point(t, vp, i, X, Y, Z);
+    const float nan = __int_as_float(0x7FC00000);
+    oxyz[(size_t)i * 3] = fin ? X : nan;
+    oxyz[(size_t)i * 3 + 1] = fin ? Y : nan;
+    oxyz[(size_t)i * 3 + 2] = fin ? Z : nan;
+    uint8_t r = 0, g = 0, b = 0;
+    if (fin && s.bgr) {
+        const int y = i / s.W, x = i - y * s.W;
+        const uint8_t* c = s.bgr + (size_t)y * s.cstep + (size_t)x * 3;
+        r = c[2]; g = c[1]; b = c[0];
+    }
+    orgb[(size_t)i * 3] = r; orgb[(size_t)i * 3 + 1] = g; orgb[(size_t)i * 3 + 2] = b;
+}
+
+}  // namespace
+
+struct sdr_cloud {
+    sdr_ctx* ctx = nullptr;
+    DevBuf in_points, in_bgr, in_disp;
+    DevBuf keys[2], vals[2], hist, flags, params;
+    DevBuf oxyz, orgb, oidx, ocnt;
+    PinnedBuf host_params;
+    cudaEvent_t done = nullptr;
+    int64_t last_n = 0;
+    int last_passthrough = 0;
+    int W = 0, H = 0;
+};
+
+extern "C" int sdr_cloud_create(sdr_ctx* ctx, sdr_cloud** out) {
+    if (!ctx || !out) return SDR_EINVAL;
+    sdr_cloud* c = new sdr_cloud();
+    c->ctx = ctx;
+    *out = c;
+    return SDR_OK;
+}
+
+extern "C" void sdr_cloud_destroy(sdr_cloud* c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    for (DevBuf* b : {&c->in_points, &c->in_bgr, &c->in_disp, &c->keys[0], &c->keys[1], &c->vals[0], &c->vals[1], &c->hist, &c->flags,
+                      &c->params, &c->oxyz, &c->orgb, &c->oidx, &c->ocnt})
+        b->release();
+    c->host_params.release();
+    if (c->done) cudaEventDestroy(c->done);
+    delete c;
+}
+
+// Enqueues the whole voxelisation on the ctx stream; the result header lands in c->host_params.
+int sdr_cloud_enqueue(sdr_cloud* c, const uint8_t* points, size_t pstep, const uint8_t* disp, size_t dstep, const uint8_t* bgr, size_t cstep,
+                      int W, int H, const double* Q, int handle_missing, const sdr_voxel_options* opt) {
+    sdr_ctx* ctx = c->ctx;
+    cudaStream_t st = ctx->stream;
+    const int n = W * H;
+    const int nblocks = div_up(n, RS_TILE);
+    int rc;
+    for (int i = 0; i < 2; i++) {
+        if ((rc = c->keys[i].reserve(ctx, (size_t)n * 4))) return rc;
+        if ((rc = c->vals[i].reserve(ctx, (size_t)n * 4))) return rc;
+    }
+    if ((rc = c->hist.reserve(ctx, (size_t)256 * nblocks * 4))) return rc;
+    if ((rc = c->flags.reserve(ctx, (size_t)n * 4))) return rc;
+    if ((rc = c->params.reserve(ctx, sizeof(VoxParams)))) return rc;
+    if ((rc = c->oxyz.reserve(ctx, (size_t)n * 12))) return rc;
+    if ((rc = c->orgb.reserve(ctx, (size_t)n * 3))) return rc;
+    if ((rc = c->oidx.reserve(ctx, (size_t)n * 4))) return rc;
+    if ((rc = c->ocnt.reserve(ctx, (size_t)n * 4))) return rc;
+    if ((rc = c->host_params.reserve(ctx, sizeof(VoxParams)))) return rc;
+    c->W = W; c->H = H;
+    Source s{};
+    s.points = points; s.pstep = pstep; s.disp = disp; s.dstep = dstep; s.bgr = bgr; s.cstep = cstep; s.W = W; s.H = H;
+    s.from_disp = points == nullptr;
+    if (Q) memcpy(s.Q.q, Q, sizeof s.Q.q);
+    s.handle_missing = s.from_disp ? handle_missing : 0;
+    s.drop_invalid = opt->drop_invalid && disp != nullptr;
+    s.min_valid16 = opt->min_disparity * 16;
+    s.z_max = opt->z_max;
+    VoxParams* vp = c->params.as<VoxParams>();
+    const int g256 = div_up(n, 256);
+    k_vox_reset<<<1, 1, 0, st>>>(vp);
+    SDR_LAUNCHED(ctx);
+    if (s.from_disp && s.handle_missing) {
+        k_vox_mindisp<<<g256, 256, 0, st>>>(s, vp);
+        SDR_LAUNCHED(ctx);
+    }
+    k_vox_bbox<<<g256, 256, 0, st>>>(s, vp);
+    SDR_LAUNCHED(ctx);
+    k_vox_params<<<1, 1, 0, st>>>(vp, opt->leaf[0], opt->leaf[1], opt->leaf[2]);
+    SDR_LAUNCHED(ctx);
+    k_vox_keys<<<g256, 256, 0, st>>>(s, vp, c->keys[0].as<uint32_t>(), c->vals[0].as<uint32_t>(), n);
+    SDR_LAUNCHED(ctx);
+    int cur = 0;
+    for (int pass = 0; pass < 4; pass++) {
+        const int shift = pass * 8;
+        k_rs_hist<<<nblocks, RS_THREADS, 0, st>>>(c->keys[cur].as<uint32_t>(), n, shift, c->hist.as<uint32_t>(), nblocks);
+        SDR_LAUNCHED(ctx);
+        k_scan_block<<<1, 1024, 0, st>>>(c->hist.as<uint32_t>(), 256 * nblocks, nullptr);
+        SDR_LAUNCHED(ctx);
+        k_rs_scatter<<<nblocks, RS_THREADS, 0, st>>>(c->keys[cur].as<uint32_t>(), c->vals[cur].as<uint32_t>(), n, shift, c->hist.as<uint32_t>(),
+                                                     nblocks, c->keys[cur ^ 1].as<uint32_t>(), c->vals[cur ^ 1].as<uint32_t>());
+        SDR_LAUNCHED(ctx);
+        cur ^= 1;
+    }
+    k_vox_heads<<<g256, 256, 0, st>>>(c->keys[cur].as<uint32_t>(), n, c->flags.as<uint32_t>());
+    SDR_LAUNCHED(ctx);
+    k_scan_block<<<1, 1024, 0, st>>>(c->flags.as<uint32_t>(), n, &vp->nvox);
+    SDR_LAUNCHED(ctx);
+    k_vox_reduce<<<g256, 256, 0, st>>>(s, vp, c->keys[cur].as<uint32_t>(), c->vals[cur].as<uint32_t>(), c->flags.as<uint32_t>(), n,
+                                       c->oxyz.as<float>(), c->orgb.as<uint8_t>(), c->oidx.as<uint32_t>(), c->ocnt.as<uint32_t>());
+    SDR_LAUNCHED(ctx);
+    k_vox_passthrough<<<g256, 256, 0, st>>>(s, vp, c->oxyz.as<float>(), c->orgb.as<uint8_t>());
+    SDR_LAUNCHED(ctx);
+    SDR_CUDA(ctx, cudaMemcpyAsync(c->host_params.p, vp, sizeof(VoxParams), cudaMemcpyDeviceToHost, st));
+    if (!c->done) SDR_CUDA(ctx, cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
+    SDR_CUDA(ctx, cudaEventRecord(c->done, st));
+    return SDR_OK;
+}
+
+// Waits for the enqueued work and fills the view. Returns SDR_OK or SDR_EVOXEL_OVERFLOW.
+int sdr_cloud_finish(sdr_cloud* c, sdr_cloud_view* view) {
+    sdr_ctx* ctx = c->ctx;
+    SDR_CUDA(ctx, cudaEventSynchronize(c->done));
+    const VoxParams* hp = (const VoxParams*)c->host_params.p;
+    c->last_passthrough = hp->overflow;
+    c->last_n = hp->overflow ? (int64_t)c->W * c->H : (int64_t)hp->nvox;
+    if (view) {
+        view->n = c->last_n;
+        view->xyz = c->oxyz.as<float>();
+        view->rgb = c->orgb.as<uint8_t>();
+        view->idx = hp->overflow ? nullptr : c->oidx.as<uint32_t>();
+        view->cnt = hp->overflow ? nullptr : c->ocnt.as<uint32_t>();
+        for (int i = 0; i < 3; i++) { view->min_b[i] = hp->minb[i]; view->div_b[i] = hp->divb[i]; }
+        view->passthrough = hp->overflow;
+    }
+    if (hp->overflow) {
+        sdr_set_error(ctx, "[VoxelGrid] Leaf size is too small for the input dataset. Integer indices would overflow.");
+        return SDR_EVOXEL_OVERFLOW;
+    }
+    return SDR_OK;
+}
+
+static int check_opt(sdr_ctx* ctx, const sdr_voxel_options* opt) {
+    if (!opt || !(opt->leaf[0] > 0.f) || !(opt->leaf[1] > 0.f) || !(opt->leaf[2] > 0.f))
+        return SDR_FAIL(ctx, SDR_EINVAL, "voxel leaf sizes must be positive");
+    return SDR_OK;
+}
+
+extern "C" int sdr_voxelgrid(sdr_cloud* c, const sdr_image* points, const sdr_image* bgr, const sdr_image* disp16,
+                             const sdr_voxel_options* opt, sdr_cloud_view* view) {
+    if (!c || !points) return SDR_EINVAL;
+    sdr_ctx* ctx = c->ctx;
+    SDR_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = check_opt(ctx, opt))) return rc;
+    if ((rc = sdr_check_image(ctx, points, 3, 4, "points"))) return rc;
+    const int W = points->cols, H = points->rows;
+    DevView vp, vc{}, vd{};
+    if ((rc = sdr_stage_in(ctx, points, c->in_points, &vp))) return rc;
+    if (bgr) {
+        if ((rc = sdr_check_image(ctx, bgr, 3, 1, "bgr"))) return rc;
+        if (bgr->cols != W || bgr->rows != H) return SDR_FAIL(ctx, SDR_ESIZE, "voxelgrid: colour image size differs");  // pcd_write.cpp:25
+        if ((rc = sdr_stage_in(ctx, bgr, c->in_bgr, &vc))) return rc;
+    }
+    if (disp16) {
+        if ((rc = sdr_check_image(ctx, disp16, 1, 2, "disp16"))) return rc;
+        if (disp16->cols != W || disp16->rows != H) return SDR_FAIL(ctx, SDR_ESIZE, "voxelgrid: disparity size differs");
+        if ((rc = sdr_stage_in(ctx, disp16, c->in_disp, &vd))) return rc;
+    } else if (opt->drop_invalid) {
+        return SDR_FAIL(ctx, SDR_EINVAL, "voxelgrid: drop_invalid needs the CV_16S disparity");
+    }
+    if ((rc = sdr_cloud_enqueue(c, vp.p, vp.pitch, vd.p, vd.pitch, vc.p, vc.pitch, W, H, nullptr, 0, opt))) return rc;
+    return sdr_cloud_finish(c, view);
+}
+
+extern "C" int sdr_depth_cloud(sdr_cloud* c, const sdr_image* disp16, const sdr_image* bgr, const double* Q, int handle_missing,
+                               const sdr_voxel_options* opt, sdr_cloud_view* view) {
+    if (!c || !disp16 || !Q) return SDR_EINVAL;
+    sdr_ctx* ctx = c->ctx;
+    SDR_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = check_opt(ctx, opt))) return rc;
+    if ((rc = sdr_check_image(ctx, disp16, 1, 2, "disp16"))) return rc;
+    const int W = disp16->cols, H = disp16->rows;
+    DevView vc{}, vd;
+    if ((rc = sdr_stage_in(ctx, disp16, c->in_disp, &vd))) return rc;
+    if (bgr) {
+        if ((rc = sdr_check_image(ctx, bgr, 3, 1, "bgr"))) return rc;
+        if (bgr->cols != W || bgr->rows != H) return SDR_FAIL(ctx, SDR_ESIZE, "depth_cloud: colour image size differs");
+        if ((rc = sdr_stage_in(ctx, bgr, c->in_bgr, &vc))) return rc;
+    }
+    if ((rc = sdr_cloud_enqueue(c, nullptr, 0, vd.p, vd.pitch, vc.p, vc.pitch, W, H, Q, handle_missing, opt))) return rc;
+    return sdr_cloud_finish(c, view);
+}
+
+extern "C" int sdr_cloud_download(sdr_cloud* c, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt) {
+    if (!c) return SDR_EINVAL;
+    sdr_ctx* ctx = c->ctx;
+    SDR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)c->last_n;
+    if (xyz) SDR_CUDA(ctx, cudaMemcpyAsync(xyz, c->oxyz.p, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rgb) SDR_CUDA(ctx, cudaMemcpyAsync(rgb, c->orgb.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!c->last_passthrough) {
+        if (idx) SDR_CUDA(ctx, cudaMemcpyAsync(idx, c->oidx.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (cnt) SDR_CUDA(ctx, cudaMemcpyAsync(cnt, c->ocnt.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    SDR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SDR_OK;
+}

@@ -1,0 +1,150 @@
+"""GPU parity: the CUDA SGBM path (through the C ABI) against the C oracle and the cv2 golden vectors.
+Bit-exact CV_16S is the bar (integer work)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_golden_vectors(ctx, golden):
+    from stereo_depth_ruler_b200 import capi
+    for name in golden["sgbm_cases"]:
+        args = [int(v) for v in golden[name + "_args"]]
+        m = capi.Sgbm(ctx, capi.make_params(*args))
+        got = m.compute(golden[name + "_left"], golden[name + "_right"])
+        assert np.array_equal(got, golden[name + "_disp"]), name
+        m.close()
+
+
+SWEEP = []
+for mode in (0, 1, 2):
+    SWEEP += [
+        (96, 48, (0, 16, 1, 8, 32, 1, 0, 10, 0, 0, mode), "tex"),
+        (130, 40, (0, 32, 11, 2904, 11616, 1, 31, 1, 20, 1, mode), "tex"),
+        (100, 33, (0, 64, 5, 600, 2400, 2, 63, 30, 200, 2, mode), "noise"),
+        (90, 17, (4, 16, 3, 0, 0, 0, 15, -1, 10, 4, mode), "low"),
+        (67, 20, (0, 64, 5, 600, 2400, 1, 63, 12, 0, 0, mode), "tex"),
+        (333, 61, (0, 112, 7, 1176, 4704, 1, 63, 12, 100, 2, mode), "tex"),
+        (300, 37, (-16, 48, 5, 600, 2400, 1, 63, 12, 200, 2, mode), "tex"),
+        (420, 50, (0, 256, 5, 600, 2400, 1, 63, 12, 200, 2, mode), "tex"),
+        (131, 3, (0, 16, 5, 600, 2400, 1, 63, 12, 0, 0, mode), "noise"),   # fewer rows than the window
+        (50, 1, (0, 16, 3, 216, 864, 1, 63, 0, 0, 0, mode), "noise"),      # single row
+    ]
+
+
+@pytest.mark.parametrize("W,H,args,kind", SWEEP)
+def test_against_oracle(ctx, orc, W, H, args, kind):
+    from stereo_depth_ruler_b200 import capi, synth
+    if kind == "tex":
+        l, r = synth.stereo_pair(W, H, args[1], 3)
+    else:
+        l, r = synth.noise_pair(W, H, 5, 256 if kind == "noise" else 8)
+    ref = orc.sgbm_compute(l, r, orc.make_params(*args))
+    m = capi.Sgbm(ctx, capi.make_params(*args))
+    got = m.compute(l, r)
+    assert np.array_equal(ref, got)
+    # raw matcher output (before median / speckle) as well
+    assert np.array_equal(m.debug_read(2, (H, W)), orc.sgbm_match(l, r, orc.make_params(*args)))
+    m.close()
+
+
+def test_cost_and_aggregate_volumes(ctx, orc):
+    """Stage-level parity: C volume and the 4-path aggregate S of MODE_SGBM."""
+    from stereo_depth_ruler_b200 import capi, synth
+    W, H, D = 200, 60, 48
+    l, r = synth.stereo_pair(W, H, D, 9)
+    po = orc.make_params(0, D, 5, 600, 2400, 1, 63, 12, 0, 0, 0)
+    raw, Cv, Sv, Sp = orc.sgbm_match(l, r, po, want_volumes=True)
+    m = capi.Sgbm(ctx, capi.make_params(0, D, 5, 600, 2400, 1, 63, 12, 0, 0, 0))
+    m.compute(l, r)
+    W1 = W - D
+    assert np.array_equal(m.debug_read(0, (H, W1, D)).astype(np.int32) + 2400, Cv)
+    assert np.array_equal(m.debug_read(1, (H, W1, D)), Sp)
+    m.close()
+
+
+def test_headline_config_bit_exact_vs_cv2_golden(ctx, golden):
+    """1280x720x128 MODE_SGBM with the reference tuple: the map cv2 4.13.0 produced (sha256 + crop)."""
+    from stereo_depth_ruler_b200 import capi, synth
+    l, r = synth.stereo_pair(1280, 720, 128, 0)
+    assert sha(l) + sha(r) == str(golden["full_c1_inputs_sha"])
+    m = capi.Sgbm(ctx, capi.make_params())
+    got = m.compute(l, r)
+    assert np.array_equal(got[300:364, 600:728], golden["full_c1_crop"])
+    assert int((got >= 0).sum()) == int(golden["full_c1_valid"])
+    assert sha(got) == str(golden["full_c1_sha"])
+    # idempotence of the handle: a second call on the same handle gives the same bytes
+    assert sha(m.compute(l, r)) == str(golden["full_c1_sha"])
+    m.close()
+
+
+def test_reference_tuple_3way_full_size(ctx, golden):
+    """The reference's own parameter tuple (D=80, MODE_SGBM_3WAY) at 1280x720 vs the cv2 sha."""
+    from stereo_depth_ruler_b200 import capi, synth
+    l, r = synth.stereo_pair(1280, 720, 80, 1)
+    m = capi.Sgbm(ctx, capi.make_params(0, 80, 5, 600, 2400, 1, 63, 12, 200, 2, capi.MODE_SGBM_3WAY))
+    assert sha(m.compute(l, r)) == str(golden["full_3way_sha"])
+    m.close()
+
+
+def test_batch_equals_single_and_device_resident(ctx, orc):
+    """Frames share no state: a batch gives the per-frame results; torch CUDA tensors are used in place."""
+    import torch
+    from stereo_depth_ruler_b200 import capi, synth
+    W, H, D, B = 256, 64, 64, 5
+    pairs = [synth.stereo_pair(W, H, D, s) for s in range(B)]
+    args = (0, D, 5, 600, 2400, 1, 63, 12, 100, 2, 0)
+    m = capi.Sgbm(ctx, capi.make_params(*args))
+    L = torch.from_numpy(np.stack([p[0] for p in pairs])).cuda()
+    R = torch.from_numpy(np.stack([p[1] for p in pairs])).cuda()
+    O = torch.empty((B, H, W), dtype=torch.int16, device="cuda")
+    m.compute_batch(L, R, O)
+    ctx.synchronize()
+    out = O.cpu().numpy()
+    for i in range(B):
+        assert np.array_equal(out[i], orc.sgbm_compute(pairs[i][0], pairs[i][1], orc.make_params(*args))), i
+    # host batch path, ragged strides (row-padded inputs)
+    padL = np.zeros((H, W + 13), np.uint8); padL[:, :W] = pairs[0][0]
+    padR = np.zeros((H, W + 13), np.uint8); padR[:, :W] = pairs[0][1]
+    got = m.compute(padL[:, :W], padR[:, :W])
+    assert np.array_equal(got, out[0])
+    m.close()
+
+
+def test_error_behaviour(ctx):
+    from stereo_depth_ruler_b200 import capi, synth
+    for bad in (dict(numDisparities=100), dict(numDisparities=0), dict(blockSize=4), dict(mode=3), dict(numDisparities=512)):
+        with pytest.raises(capi.SdrError) as e:
+            capi.Sgbm(ctx, capi.make_params(**bad))
+        assert e.value.status == capi.SDR_EINVAL
+    m = capi.Sgbm(ctx, capi.make_params(numDisparities=64))
+    l, r = synth.noise_pair(66, 20, 1)
+    with pytest.raises(capi.SdrError) as e:      # cv2 raises for this input too
+        m.compute(l, r)
+    assert e.value.status == capi.SDR_EINVAL and "too small" in str(e.value)
+    with pytest.raises(capi.SdrError) as e:
+        m.compute(np.zeros((20, 100), np.uint8), np.zeros((21, 100), np.uint8))
+    assert e.value.status == capi.SDR_ESIZE
+    m.close()
+
+
+def test_post_filters_standalone(ctx, orc, golden):
+    from stereo_depth_ruler_b200 import capi
+    assert np.array_equal(capi.median3_16s(ctx, golden["median_in"]), golden["median_out"])
+    assert np.array_equal(capi.filter_speckles(ctx, golden["speckle_in"], -16, 200, 32), golden["speckle_out"])
+    rng = np.random.default_rng(5)
+    for size, diff, shape in ((200, 32, (300, 400)), (30, 16, (97, 131)), (5, 0, (64, 64)), (100000, 1000, (50, 70))):
+        y = (rng.integers(0, 30, size=shape) * 8).astype(np.int16)
+        y[rng.random(shape) < 0.25] = -16
+        assert np.array_equal(capi.filter_speckles(ctx, y, -16, size, diff), orc.filter_speckles(y, -16, size, diff))
+    x = rng.integers(-3000, 3000, size=(1, 9)).astype(np.int16)
+    assert np.array_equal(capi.median3_16s(ctx, x), orc.median3(x))
+    # speckle filtering is idempotent
+    y1 = capi.filter_speckles(ctx, y, -16, 50, 16)
+    assert np.array_equal(capi.filter_speckles(ctx, y1, -16, 50, 16), y1)
