@@ -272,6 +272,14 @@ def run_ours(args):
                               "ms_per_batch": sgbm_ms, "algorithmic_bytes": core_bytes},
                 "stage_ms_per_batch": {k: round(v, 4) for k, v in acc.items()}}
 
+    # ---- per-stage times of the whole pipeline (one extra profiled step) ----
+    pipe.set_profiling(True)
+    with torch.cuda.stream(stream):
+        pipe.run(batch_dev(1))
+        pipe_stages = {k: round(v, 4) for k, v in pipe.stage_times()}
+    pipe.set_profiling(False)
+    roofline["pipeline_stage_ms_per_batch"] = pipe_stages
+
     # ---- e2e: pinned host frames in, disparity maps + clouds out, through the same C-ABI call ----
     disp_imgs = [disp_np[i] for i in range(B)]
     cloud_bytes = [0]

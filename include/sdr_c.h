@@ -188,6 +188,8 @@ SDR_API void sdr_pipeline_destroy(sdr_pipeline* p);
  * (valid until the next run). */
 SDR_API int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sdr_image* disp, sdr_image* points,
                              sdr_image* left_rect, sdr_cloud_view* views);
+/* Per-stage device times (ms) of the last run (CUDA events on the ctx stream); enable first. */
+SDR_API int sdr_pipeline_set_profiling(sdr_pipeline* p, int enabled);
 SDR_API int sdr_pipeline_stage_times(sdr_pipeline* p, int cap, const char** names, float* ms);
 /* Copy cloud i of the last run to host buffers (any may be NULL); sized by views[i].n. */
 SDR_API int sdr_pipeline_cloud_download(sdr_pipeline* p, int i, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt);

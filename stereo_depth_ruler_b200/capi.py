@@ -78,7 +78,7 @@ SYMBOLS = [
     "sdr_median3_16s", "sdr_filter_speckles", "sdr_reproject_to_3d",
     "sdr_cloud_create", "sdr_cloud_destroy", "sdr_voxelgrid", "sdr_depth_cloud", "sdr_cloud_download",
     "sdr_pipeline_create", "sdr_pipeline_destroy", "sdr_pipeline_run", "sdr_pipeline_stage_times",
-    "sdr_pipeline_cloud_download",
+    "sdr_pipeline_cloud_download", "sdr_pipeline_set_profiling",
 ]
 
 _lib = None
@@ -441,6 +441,9 @@ class Pipeline:
         if not v.passthrough:
             out.update(idx=idx, cnt=cnt)
         return out
+
+    def set_profiling(self, on=True):
+        lib().sdr_pipeline_set_profiling(self._h, int(on))
 
     def stage_times(self):
         names = (C.c_char_p * 64)()

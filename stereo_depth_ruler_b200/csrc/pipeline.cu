@@ -153,6 +153,12 @@ extern "C" int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sd
     return status;
 }
 
+extern "C" int sdr_pipeline_set_profiling(sdr_pipeline* p, int enabled) {
+    if (!p) return SDR_EINVAL;
+    p->timer.enabled = enabled != 0;
+    return SDR_OK;
+}
+
 extern "C" int sdr_pipeline_stage_times(sdr_pipeline* p, int cap, const char** names, float* ms) {
     if (!p) return 0;
     cudaSetDevice(p->ctx->device);

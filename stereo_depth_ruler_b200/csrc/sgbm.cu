@@ -117,23 +117,21 @@ __global__ void __launch_bounds__(128) k_prefilter(Geom g, const uint8_t* left, 
 // CTA evaluates the BT cost for TX+2*SW2 columns x D disparities into a shared-memory ring of
 // 2*SH2+1 rows (u8), sums the ring vertically into Vs (u16), then horizontally into C.
 // ------------------------------------------------------------------------------------------
-constexpr int COST_TX = 32;
-constexpr int COST_RB = 32;
-constexpr int COST_THREADS = 256;
+constexpr int COST_TXH = 64;   // columns per CTA including the 2*SW2 halo
+constexpr int COST_RB = 90;    // output rows per CTA (2*SH2 warm-up rows are recomputed per band)
 
+// BT cost of 8 consecutive disparities at one pixel (both channels) -> two u8x4 words.
 __device__ __forceinline__ void bt_item(const Geom& g, const int4* __restrict__ PLrow, const uint8_t* __restrict__ PRrow,
-                                        int ximg, int q, uint32_t& out0, uint32_t& out1) {
+                                        int ximg, int proff, uint32_t& out0, uint32_t& out1) {
     const int4 k = __ldg(PLrow + ximg);
-    const int j0 = (g.W - 1 - ximg) + g.minD + 8 * q;
-    const int a = j0 & 3, off = j0 - a;
     uint32_t acc[4];
 #pragma unroll
     for (int ch = 0; ch < 2; ch++) {
         const uint32_t kx = ch ? (uint32_t)k.z : (uint32_t)k.x, ky = ch ? (uint32_t)k.w : (uint32_t)k.y;
         const uint32_t negU = dup_lo(kx), Um = dup_hi(kx), negU1 = dup_lo(ky), U0m = dup_hi(ky);
-        const uint8_t* pv = PRrow + ((ch * 3 + 0) * 4 + a) * g.Wp + off;
-        const uint8_t* pl = PRrow + ((ch * 3 + 1) * 4 + a) * g.Wp + off;
-        const uint8_t* ph = PRrow + ((ch * 3 + 2) * 4 + a) * g.Wp + off;
+        const uint8_t* pv = PRrow + (ch * 3 + 0) * 4 * g.Wp + proff;
+        const uint8_t* pl = PRrow + (ch * 3 + 1) * 4 * g.Wp + proff;
+        const uint8_t* ph = PRrow + (ch * 3 + 2) * 4 * g.Wp + proff;
         const uint32_t wv[2] = {__ldg((const uint32_t*)pv), __ldg((const uint32_t*)pv + 1)};
         const uint32_t wl[2] = {__ldg((const uint32_t*)pl), __ldg((const uint32_t*)pl + 1)};
         const uint32_t wh[2] = {__ldg((const uint32_t*)ph), __ldg((const uint32_t*)ph + 1)};
@@ -156,18 +154,22 @@ __device__ __forceinline__ void bt_item(const Geom& g, const int4* __restrict__ 
     out1 = prmt(acc[2], acc[3], 0x6420);
 }
 
-__global__ void __launch_bounds__(COST_THREADS) k_cost(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ PR,
-                                                       int16_t* __restrict__ C) {
+// blockDim.x is a multiple of DQ = D/8: thread = (q, xg); it owns ITEMS columns xh = xg + k*XG of the 64-column tile for
+// the whole band, keeps their running vertical sums in registers and their last 2*SH2+1 pixel-cost rows in a
+// thread-private shared-memory ring (no synchronisation needed for it). One __syncthreads per output row (Vs is
+// double-buffered) separates the vertical and the horizontal box sums.
+template <int ITEMS>
+__global__ void __launch_bounds__(256) k_cost(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ PR,
+                                              int16_t* __restrict__ C) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int D = g.D, DQ = D >> 3;
-    const int TXH = COST_TX + 2 * g.SW2, n = 2 * g.SH2 + 1;
-    uint8_t* ring = smem;                                        // [n][TXH][D] u8
-    uint16_t* Vs = (uint16_t*)(smem + (size_t)n * TXH * D);      // [TXH][D] u16
+    const int n = 2 * g.SH2 + 1, TX = COST_TXH - 2 * g.SW2;
+    uint8_t* ring = smem;                                              // [n][64][D] u8
+    uint16_t* Vs = (uint16_t*)(smem + (size_t)n * COST_TXH * D);       // [2][64][D] u16
     const int b = blockIdx.z;
-    // locate (segment, band)
     int band = blockIdx.y, si = 0;
     for (; si < g.nseg; si++) {
-        int nb = (g.seg[si].src_end - g.seg[si].src_start + COST_RB - 1) / COST_RB;
+        const int nb = (g.seg[si].src_end - g.seg[si].src_start + COST_RB - 1) / COST_RB;
         if (band < nb) break;
         band -= nb;
     }
@@ -175,54 +177,71 @@ __global__ void __launch_bounds__(COST_THREADS) k_cost(Geom g, const int4* __res
     const Seg sg = g.seg[si];
     const int ya = sg.src_start + band * COST_RB, yb = min(ya + COST_RB, sg.src_end);
     const int ymin = sg.src_start, ymax = g.H - 1;
-    const int x0 = blockIdx.x * COST_TX;
-    const int tid = threadIdx.x;
-    int r = max(ya - g.SH2, ymin);
-    for (int y = ya; y < yb; y++) {
-        const int need = min(y + g.SH2, ymax);
-        for (; r <= need; r++) {
-            const int4* PLrow = PL + ((size_t)b * g.H + r) * g.W;
-            const uint8_t* PRrow = PR + ((size_t)b * g.H + r) * 24 * g.Wp;
-            uint8_t* slot = ring + (size_t)(r % n) * TXH * D;
-            for (int it = tid; it < TXH * DQ; it += COST_THREADS) {
-                const int xh = it / DQ, q = it - xh * DQ;
-                const int xc = min(max(x0 - g.SW2 + xh, 0), g.W1 - 1);
-                uint32_t o0, o1;
-                bt_item(g, PLrow, PRrow, xc + g.minX1, q, o0, o1);
-                *(uint2*)(slot + (size_t)xh * D + 8 * q) = make_uint2(o0, o1);
+    const int x0 = blockIdx.x * TX;
+    const int q = threadIdx.x % DQ, xg = threadIdx.x / DQ, XG = blockDim.x / DQ;
+    int ximg[ITEMS], proff[ITEMS];
+    uint32_t V[ITEMS][4];
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        const int xh = xg + k * XG;
+        const int xc = min(max(x0 - g.SW2 + xh, 0), g.W1 - 1);
+        ximg[k] = xc + g.minX1;
+        const int j0 = (g.W - 1 - ximg[k]) + g.minD + 8 * q;
+        const int a = j0 & 3;
+        proff[k] = a * g.Wp + (j0 - a);
+        V[k][0] = V[k][1] = V[k][2] = V[k][3] = 0;
+        if (xh < COST_TXH)
+            for (int s = 0; s < n; s++) *(uint2*)(ring + ((size_t)s * COST_TXH + xh) * D + 8 * q) = make_uint2(0, 0);
+    }
+    int slot = 0;
+    for (int kv = ya - g.SH2; kv <= yb - 1 + g.SH2; kv++) {
+        const int rc = min(max(kv, ymin), ymax);
+        const int4* PLrow = PL + ((size_t)b * g.H + rc) * g.W;
+        const uint8_t* PRrow = PR + ((size_t)b * g.H + rc) * 24 * g.Wp;
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+            const int xh = xg + k * XG;
+            if (xh < COST_TXH) {
+                uint32_t n0, n1;
+                bt_item(g, PLrow, PRrow, ximg[k], proff[k], n0, n1);
+                uint2* rp = (uint2*)(ring + ((size_t)slot * COST_TXH + xh) * D + 8 * q);
+                const uint2 old = *rp;
+                *rp = make_uint2(n0, n1);
+                const uint32_t o0 = ~old.x, o1 = ~old.y;   // 255 - old per byte
+                // V += new - old  ==  V + new + (255 - old) - 255 per 16-bit half
+                V[k][0] = __vadd2(__vadd2(__vadd2(V[k][0], prmt(n0, 0, 0x4140)), prmt(o0, 0, 0x4140)), 0xFF01FF01u);
+                V[k][1] = __vadd2(__vadd2(__vadd2(V[k][1], prmt(n0, 0, 0x4342)), prmt(o0, 0, 0x4342)), 0xFF01FF01u);
+                V[k][2] = __vadd2(__vadd2(__vadd2(V[k][2], prmt(n1, 0, 0x4140)), prmt(o1, 0, 0x4140)), 0xFF01FF01u);
+                V[k][3] = __vadd2(__vadd2(__vadd2(V[k][3], prmt(n1, 0, 0x4342)), prmt(o1, 0, 0x4342)), 0xFF01FF01u);
             }
         }
-        __syncthreads();
-        for (int it = tid; it < TXH * DQ; it += COST_THREADS) {
-            const int xh = it / DQ, q = it - xh * DQ;
-            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-            for (int kk = y - g.SH2; kk <= y + g.SH2; kk++) {
-                const int rr = min(max(kk, ymin), ymax);
-                const uint2 w = *(const uint2*)(ring + ((size_t)(rr % n) * TXH + xh) * D + 8 * q);
-                a0 = __vadd2(a0, prmt(w.x, 0, 0x4140));
-                a1 = __vadd2(a1, prmt(w.x, 0, 0x4342));
-                a2 = __vadd2(a2, prmt(w.y, 0, 0x4140));
-                a3 = __vadd2(a3, prmt(w.y, 0, 0x4342));
+        slot = slot + 1 == n ? 0 : slot + 1;
+        const int y = kv - g.SH2;
+        if (y >= ya) {   // uniform across the CTA
+            uint16_t* Vb = Vs + (size_t)(y & 1) * COST_TXH * D;
+#pragma unroll
+            for (int k = 0; k < ITEMS; k++) {
+                const int xh = xg + k * XG;
+                if (xh < COST_TXH) *(uint4*)(Vb + (size_t)xh * D + 8 * q) = make_uint4(V[k][0], V[k][1], V[k][2], V[k][3]);
             }
-            *(uint4*)(Vs + (size_t)xh * D + 8 * q) = make_uint4(a0, a1, a2, a3);
-        }
-        __syncthreads();
-        int16_t* Crow = C + ((size_t)b * g.crows + sg.crow0 + (y - sg.src_start)) * g.W1 * D;
-        for (int it = tid; it < COST_TX * DQ; it += COST_THREADS) {
-            const int xl = it / DQ, q = it - xl * DQ;
-            const int x = x0 + xl;
-            if (x >= g.W1) continue;
-            uint4 acc = make_uint4(0, 0, 0, 0);
-            for (int j = 0; j <= 2 * g.SW2; j++) {
-                const uint4 w = *(const uint4*)(Vs + (size_t)(xl + j) * D + 8 * q);
-                acc.x = __vadd2(acc.x, w.x);
-                acc.y = __vadd2(acc.y, w.y);
-                acc.z = __vadd2(acc.z, w.z);
-                acc.w = __vadd2(acc.w, w.w);
+            __syncthreads();
+            int16_t* Crow = C + ((size_t)b * g.crows + sg.crow0 + (y - sg.src_start)) * g.W1 * D;
+#pragma unroll
+            for (int k = 0; k < ITEMS; k++) {
+                const int xl = xg + k * XG;
+                if (xl < TX && x0 + xl < g.W1) {
+                    uint4 acc = make_uint4(0, 0, 0, 0);
+                    for (int j = 0; j <= 2 * g.SW2; j++) {
+                        const uint4 w = *(const uint4*)(Vb + (size_t)(xl + j) * D + 8 * q);
+                        acc.x = __vadd2(acc.x, w.x);
+                        acc.y = __vadd2(acc.y, w.y);
+                        acc.z = __vadd2(acc.z, w.z);
+                        acc.w = __vadd2(acc.w, w.w);
+                    }
+                    *(uint4*)(Crow + (size_t)(x0 + xl) * D + 8 * q) = acc;
+                }
             }
-            *(uint4*)(Crow + (size_t)x * D + 8 * q) = acc;
         }
-        // the next iteration's first __syncthreads orders Vs/ring reuse
     }
 }
 
@@ -691,14 +710,24 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
         SDR_LAUNCHED(ctx);
         m->timer.mark(st, "prefilter");
         {
-            const int TXH = COST_TX + 2 * g.SW2, n = 2 * g.SH2 + 1;
-            const size_t smem = (size_t)n * TXH * g.D + (size_t)TXH * g.D * 2;
+            const int n = 2 * g.SH2 + 1, DQ = g.D / 8;
+            const int nthr = (256 / DQ) * DQ, XG = nthr / DQ;
+            const int items = div_up(COST_TXH, XG);
+            const size_t smem = (size_t)n * COST_TXH * g.D + (size_t)2 * COST_TXH * g.D * 2;
             if (smem > ctx->smem_optin) return SDR_FAIL(ctx, SDR_EINVAL, "cost kernel needs %zu B shared memory", smem);
-            SDR_CUDA(ctx, cudaFuncSetAttribute(k_cost, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int bands = 0;
             for (int i = 0; i < g.nseg; i++) bands += div_up(g.seg[i].src_end - g.seg[i].src_start, COST_RB);
-            k_cost<<<dim3(div_up(g.W1, COST_TX), bands, batch), COST_THREADS, smem, st>>>(g, m->PL.as<int4>(), m->PR.as<uint8_t>(),
-                                                                                        m->C.as<int16_t>());
+            const dim3 grid(div_up(g.W1, COST_TXH - 2 * g.SW2), bands, batch);
+#define COST_LAUNCH(IT)                                                                                               \
+    case IT:                                                                                                          \
+        SDR_CUDA(ctx, cudaFuncSetAttribute(k_cost<IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        k_cost<IT><<<grid, nthr, smem, st>>>(g, m->PL.as<int4>(), m->PR.as<uint8_t>(), m->C.as<int16_t>());          \
+        break;
+            switch (items) {
+                COST_LAUNCH(1) COST_LAUNCH(2) COST_LAUNCH(3) COST_LAUNCH(4) COST_LAUNCH(5) COST_LAUNCH(6) COST_LAUNCH(7) COST_LAUNCH(8)
+                default: return SDR_FAIL(ctx, SDR_EINVAL, "cost kernel: unsupported tiling (items=%d)", items);
+            }
+#undef COST_LAUNCH
             SDR_LAUNCHED(ctx);
             m->timer.mark(st, "cost");
         }

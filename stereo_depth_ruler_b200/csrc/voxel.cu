@@ -94,7 +94,13 @@ __global__ void __launch_bounds__(256) k_vox_mindisp(Source s, VoxParams* vp) {
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
-    if ((threadIdx.x & 31) == 0 && key != 0x7FFFFFFF) atomicMin(&vp->min_disp_key, key);
+    __shared__ int wk[8];
+    if ((threadIdx.x & 31) == 0) wk[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) key = min(key, wk[w]);
+        if (key != 0x7FFFFFFF) atomicMin(&vp->min_disp_key, key);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_vox_bbox(Source s, VoxParams* vp) {
@@ -118,13 +124,29 @@ __global__ void __launch_bounds__(256) k_vox_bbox(Source s, VoxParams* vp) {
         }
         ok += __shfl_xor_sync(0xffffffffu, ok, o);
     }
-    if ((threadIdx.x & 31) == 0 && ok) {
+    __shared__ int smn[8][3], smx[8][3];
+    __shared__ unsigned sok[8];
+    if ((threadIdx.x & 31) == 0) {
+        const int w = threadIdx.x >> 5;
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            atomicMin(&vp->bbox_key[c], mn[c]);
-            atomicMax(&vp->bbox_key[3 + c], mx[c]);
+        for (int c = 0; c < 3; c++) { smn[w][c] = mn[c]; smx[w][c] = mx[c]; }
+        sok[w] = ok;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) { mn[c] = min(mn[c], smn[w][c]); mx[c] = max(mx[c], smx[w][c]); }
+            ok += sok[w];
         }
-        atomicAdd(&vp->nvalid, ok);
+        if (ok) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                atomicMin(&vp->bbox_key[c], mn[c]);
+                atomicMax(&vp->bbox_key[3 + c], mx[c]);
+            }
+            atomicAdd(&vp->nvalid, ok);
+        }
     }
 }
 
@@ -222,6 +244,64 @@ __global__ void __launch_bounds__(1024) k_scan_block(uint32_t* data, int m, uint
         __syncthreads();
     }
     if (threadIdx.x == 0 && total) *total = carry;
+}
+
+// Device-wide exclusive scan in three small launches: per-tile sums, scan of the sums (one block), tile rescan.
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 16, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_sums, uint32_t& block_total) {
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t w = threadIdx.x < SCAN_THREADS / 32 ? warp_sums[threadIdx.x] : 0;
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (threadIdx.x >= o) wi += t;
+        }
+        if (threadIdx.x < SCAN_THREADS / 32) warp_sums[threadIdx.x] = wi - w;
+        if (threadIdx.x == SCAN_THREADS / 32 - 1) warp_sums[32] = wi;
+    }
+    __syncthreads();
+    block_total = warp_sums[32];
+    return warp_sums[threadIdx.x >> 5] + incl - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t* __restrict__ data, int m, uint32_t* __restrict__ sums) {
+    __shared__ uint32_t ws[33];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++)
+        if (base + k < m) v += data[base + k];
+    uint32_t total;
+    block_excl_scan(v, ws, total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_apply(uint32_t* __restrict__ data, int m, const uint32_t* __restrict__ sums) {
+    __shared__ uint32_t ws[33];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t x[SCAN_ITEMS], v = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        x[k] = base + k < m ? data[base + k] : 0;
+        v += x[k];
+    }
+    uint32_t total;
+    uint32_t run = block_excl_scan(v, ws, total) + sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < m) data[base + k] = run;
+        run += x[k];
+    }
 }
 
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n,
@@ -347,7 +427,7 @@ __global__ void __launch_bounds__(256) k_vox_passthrough(Source s, const VoxPara
 struct sdr_cloud {
     sdr_ctx* ctx = nullptr;
     DevBuf in_points, in_bgr, in_disp;
-    DevBuf keys[2], vals[2], hist, flags, params;
+    DevBuf keys[2], vals[2], hist, flags, params, scan_sums;
     DevBuf oxyz, orgb, oidx, ocnt;
     PinnedBuf host_params;
     cudaEvent_t done = nullptr;
@@ -368,11 +448,25 @@ extern "C" void sdr_cloud_destroy(sdr_cloud* c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
     for (DevBuf* b : {&c->in_points, &c->in_bgr, &c->in_disp, &c->keys[0], &c->keys[1], &c->vals[0], &c->vals[1], &c->hist, &c->flags,
-                      &c->params, &c->oxyz, &c->orgb, &c->oidx, &c->ocnt})
+                      &c->params, &c->scan_sums, &c->oxyz, &c->orgb, &c->oidx, &c->ocnt})
         b->release();
     c->host_params.release();
     if (c->done) cudaEventDestroy(c->done);
     delete c;
+}
+
+static int scan_u32(sdr_cloud* c, uint32_t* data, int m, uint32_t* total) {
+    sdr_ctx* ctx = c->ctx;
+    const int nt = div_up(m, SCAN_TILE);
+    int rc = c->scan_sums.reserve(ctx, (size_t)nt * 4);
+    if (rc) return rc;
+    k_scan_tile_sums<<<nt, SCAN_THREADS, 0, ctx->stream>>>(data, m, c->scan_sums.as<uint32_t>());
+    SDR_LAUNCHED(ctx);
+    k_scan_block<<<1, 1024, 0, ctx->stream>>>(c->scan_sums.as<uint32_t>(), nt, total);
+    SDR_LAUNCHED(ctx);
+    k_scan_tile_apply<<<nt, SCAN_THREADS, 0, ctx->stream>>>(data, m, c->scan_sums.as<uint32_t>());
+    SDR_LAUNCHED(ctx);
+    return SDR_OK;
 }
 
 // Enqueues the whole voxelisation on the ctx stream; the result header lands in c->host_params.
@@ -423,8 +517,7 @@ int sdr_cloud_enqueue(sdr_cloud* c, const uint8_t* points, size_t pstep, const u
         const int shift = pass * 8;
         k_rs_hist<<<nblocks, RS_THREADS, 0, st>>>(c->keys[cur].as<uint32_t>(), n, shift, c->hist.as<uint32_t>(), nblocks);
         SDR_LAUNCHED(ctx);
-        k_scan_block<<<1, 1024, 0, st>>>(c->hist.as<uint32_t>(), 256 * nblocks, nullptr);
-        SDR_LAUNCHED(ctx);
+        if ((rc = scan_u32(c, c->hist.as<uint32_t>(), 256 * nblocks, nullptr))) return rc;
         k_rs_scatter<<<nblocks, RS_THREADS, 0, st>>>(c->keys[cur].as<uint32_t>(), c->vals[cur].as<uint32_t>(), n, shift, c->hist.as<uint32_t>(),
                                                      nblocks, c->keys[cur ^ 1].as<uint32_t>(), c->vals[cur ^ 1].as<uint32_t>());
         SDR_LAUNCHED(ctx);
@@ -432,8 +525,7 @@ int sdr_cloud_enqueue(sdr_cloud* c, const uint8_t* points, size_t pstep, const u
     }
     k_vox_heads<<<g256, 256, 0, st>>>(c->keys[cur].as<uint32_t>(), n, c->flags.as<uint32_t>());
     SDR_LAUNCHED(ctx);
-    k_scan_block<<<1, 1024, 0, st>>>(c->flags.as<uint32_t>(), n, &vp->nvox);
-    SDR_LAUNCHED(ctx);
+    if ((rc = scan_u32(c, c->flags.as<uint32_t>(), n, &vp->nvox))) return rc;
     k_vox_reduce<<<g256, 256, 0, st>>>(s, vp, c->keys[cur].as<uint32_t>(), c->vals[cur].as<uint32_t>(), c->flags.as<uint32_t>(), n,
                                        c->oxyz.as<float>(), c->orgb.as<uint8_t>(), c->oidx.as<uint32_t>(), c->ocnt.as<uint32_t>());
     SDR_LAUNCHED(ctx);

@@ -5,6 +5,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+Z_MAX = 5000.0   # mm; a stray sub-pixel disparity would otherwise blow the bounding box past PCL's int32 guard
+
 
 def _oracle_chain(orc, calib, sbs, args, leaf):
     W = calib.image_width
@@ -14,7 +16,8 @@ def _oracle_chain(orc, calib, sbs, args, leaf):
         rect.append(orc.remap(sbs[:, eye * W:(eye + 1) * W], m1, m2))
     d16 = orc.sgbm_compute(orc.bgr2gray(rect[0]), orc.bgr2gray(rect[1]), orc.make_params(*args))
     pts = orc.reproject_to_3d(orc.disp_to_float(d16), calib.mat("Q"), True)
-    cloud = orc.voxelgrid(pts, rect[0], leaf, drop_mask=(d16 < args[0] * 16))
+    drop = (d16 < args[0] * 16) | ~((pts[..., 2] > 0) & (pts[..., 2] <= Z_MAX))
+    cloud = orc.voxelgrid(pts, rect[0], leaf, drop_mask=drop)
     return rect[0], d16, pts, cloud
 
 
@@ -30,7 +33,7 @@ def test_pipeline_batch_matches_oracle_chain(ctx, orc, calib_path):
     from stereo_depth_ruler_b200 import capi
     calib = capi.load_calibration(calib_path)
     args = (0, 128, 5, 600, 2400, 1, 63, 12, 200, 2, 0)
-    p = capi.Pipeline(ctx, calib, capi.make_params(*args), capi.voxel_options(5.0, drop_invalid=True), handle_missing=True, batch=2)
+    p = capi.Pipeline(ctx, calib, capi.make_params(*args), capi.voxel_options(5.0, drop_invalid=True, z_max=Z_MAX), handle_missing=True, batch=2)
     frames = [_raw_sbs(21), _raw_sbs(23)]
     disp = [np.empty((720, 1280), np.int16) for _ in frames]
     pts = [np.empty((720, 1280, 3), np.float32) for _ in frames]
@@ -46,7 +49,7 @@ def test_pipeline_batch_matches_oracle_chain(ctx, orc, calib_path):
         assert np.array_equal(got["idx"], cref["idx"]) and np.array_equal(got["cnt"], cref["cnt"])
         assert np.allclose(got["xyz"], cref["xyz"], rtol=1e-4, atol=0) and np.array_equal(got["rgb"], cref["rgb"])
     # frames are independent: the second slot equals a batch-of-one run of the same frame
-    p1 = capi.Pipeline(ctx, calib, capi.make_params(*args), capi.voxel_options(5.0, drop_invalid=True), handle_missing=True, batch=1)
+    p1 = capi.Pipeline(ctx, calib, capi.make_params(*args), capi.voxel_options(5.0, drop_invalid=True, z_max=Z_MAX), handle_missing=True, batch=1)
     d1 = [np.empty((720, 1280), np.int16)]
     p1.run(frames[1:], disp=d1)
     assert np.array_equal(d1[0], disp[1])
@@ -82,7 +85,13 @@ def test_interface_mirror_reads_like_the_reference(ctx, orc, calib_path):
     assert np.array_equal(depth_map.view(np.uint32), ref_pts.view(np.uint32))
     assert rectifier.rectify(np.empty((0, 0, 3), np.uint8), right_raw) is None     # empty input: message + return
     vg = VoxelGrid(ctx)
-    vg.setLeafSize(0.005, 0.005, 0.005)                       # the reference's literal leaf: PCL passes the cloud through
+    vg.setLeafSize(0.005, 0.005, 0.005)                       # the reference's literal leaf (pcd_write.cpp:123) on a mm cloud
     pts_true = disparity_computer.computeDepth(disp_float, handleMissingValues=True)
     out = vg.filter(pts_true, left_rect)
-    assert out["passthrough"] and out["xyz"].shape[0] == 720 * 1280
+    ref = orc.voxelgrid(pts_true, left_rect, 0.005)
+    if ref is None:     # PCL's int32 guard trips: the cloud is passed through unchanged
+        assert out["passthrough"] and out["xyz"].shape[0] == 720 * 1280
+    else:               # the int64 product wrapped below INT32_MAX: PCL voxelises with wrapped indices, and so do we
+        assert not out["passthrough"]
+        assert np.array_equal(out["idx"], ref["idx"]) and np.array_equal(out["cnt"], ref["cnt"])
+        assert np.allclose(out["xyz"], ref["xyz"], rtol=1e-4, atol=0)
