@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace {
 
@@ -367,6 +368,141 @@ __global__ void __launch_bounds__(128) k_path_v(Geom g, const int16_t* __restric
     }
 }
 
+// ---- fused top-down (or bottom-up) sweep: vertical + both diagonal paths in ONE pass over C -------------------
+// A CTA owns a strip of 32 columns of one frame and walks the rows; a column's D costs live in 8 lanes. The vertical
+// state stays in registers, the diagonal states move one column per row through shared memory, and across strip
+// borders through a small global halo guarded by per-strip progress flags (neighbours only ever wait for the
+// previous row, so every CTA of a launch must be co-resident: the kernel is launched cooperatively).
+// C is read once and S written once ("directions may run concurrently and add into S in any order").
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <int NP>
+__device__ __forceinline__ void load_regs_cg(const int16_t* p, uint32_t (&r)[NP]) {
+#pragma unroll
+    for (int i = 0; i < NP; i++) r[i] = __ldcg((const unsigned int*)p + i);
+}
+
+constexpr int V3_COLS = 32;
+constexpr int V3_SPIN_LIMIT = 1 << 22;
+
+// Halo words carry their own sequence number (row + 1) in the upper half of one 64-bit store, so no fence and no
+// separate flag is needed: the reader polls the word until the sequence matches (single-copy-atomic 8-byte accesses).
+__device__ __forceinline__ void halo_put(unsigned long long* p, uint32_t data, uint32_t seq) {
+    const unsigned long long v = ((unsigned long long)seq << 32) | data;
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// All NP words of a lane are requested back to back (one L2 round trip, not NP), then re-polled until every sequence
+// number matches. Bounded: a broken neighbour protocol sets *err and lets every waiter fall through instead of
+// hanging the GPU.
+template <int NP>
+__device__ __forceinline__ void halo_get(const unsigned long long* p, uint32_t seq, int* err, uint32_t (&out)[NP]) {
+    int spins = 0;
+    while (true) {
+        unsigned long long v[NP];
+#pragma unroll
+        for (int k = 0; k < NP; k++) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v[k]) : "l"(p + k) : "memory");
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            ok = ok && (uint32_t)(v[k] >> 32) == seq;
+            out[k] = (uint32_t)v[k];
+        }
+        if (ok) break;
+        ++spins;
+        if ((spins & 63) == 0 && *(volatile int*)err) break;
+        if (spins > V3_SPIN_LIMIT) { atomicExch(err, 1); break; }
+    }
+}
+
+template <int NP, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int diry,
+                                                       int accumulate, int b0, unsigned long long* halo, int* err) {
+    constexpr int G = 8;
+    extern __shared__ __align__(16) int16_t v3sm[];
+    const int D = g.D;
+    int16_t* Xa = v3sm;                              // [2][COLS+2][D]  state of the "from (x-1)" diagonal, slot = column+1
+    int16_t* Xb = v3sm + 2 * (V3_COLS + 2) * D;      // [2][COLS+2][D]  state of the "from (x+1)" diagonal
+    const int s = blockIdx.x, nstrips = gridDim.x, f = blockIdx.y, b = b0 + f;
+    const int gidx = threadIdx.x / G, lg = threadIdx.x & (G - 1);
+    const int x = s * V3_COLS + gidx;
+    const bool active = x < g.W1;
+    const int xl = min(x, g.W1 - 1);
+    for (int i = threadIdx.x; i < 4 * (V3_COLS + 2) * D / 2; i += blockDim.x) ((uint32_t*)v3sm)[i] = 0;
+    __syncthreads();
+    const uint32_t P1x2 = pack16(g.P1, g.P1), P2x2 = pack16(g.P2, g.P2);
+    const int pad = 32767 - g.P1;
+    const uint32_t PADx2 = pack16(pad, pad);
+    const size_t lane_off = (size_t)lg * 2 * NP;
+    // halo layout: [frame][strip][buf][a|b][G*NP] 64-bit words; (strip, a) = left halo OF that strip, (strip, b) = its right halo
+    const int HW = G * NP;
+    auto Hptr = [&](int strip, int buf, int which) {
+        return halo + ((((size_t)f * nstrips + strip) * 2 + buf) * 2 + which) * HW + (size_t)lg * NP;
+    };
+    const int16_t* Cb = C + (size_t)b * g.crows * g.W1 * D + (size_t)xl * D + lane_off;
+    int16_t* Sb = S + (size_t)b * g.H * g.W1 * D + (size_t)xl * D + lane_off;
+    const size_t rowstride = (size_t)g.W1 * D;
+    const bool left_edge = gidx == 0 && s > 0, right_edge = gidx == V3_COLS - 1 && s + 1 < nstrips;
+    uint32_t Pv[NP], pa[NP], pb[NP], c[NP], cn[NP], cnn[NP], so[NP], sn[NP], L[NP], acc[NP];
+#pragma unroll
+    for (int k = 0; k < NP; k++) { Pv[k] = 0; sn[k] = 0; cnn[k] = 0; }
+    int y = diry > 0 ? 0 : g.H - 1;
+    load_regs<NP>(Cb + (size_t)y * rowstride, cn);
+    if (g.H > 1) load_regs<NP>(Cb + (size_t)(y + diry) * rowstride, cnn);
+    if (accumulate) load_regs<NP>(Sb + (size_t)y * rowstride, sn);
+    for (int t = 0; t < g.H; t++) {
+        const int cur = t & 1, prv = cur ^ 1;
+#pragma unroll
+        for (int k = 0; k < NP; k++) { c[k] = cn[k]; cn[k] = cnn[k]; so[k] = sn[k]; }
+        if (t + 2 < g.H) load_regs<NP>(Cb + (size_t)(y + 2 * diry) * rowstride, cnn);   // C two rows ahead
+        if (accumulate && t + 1 < g.H) load_regs<NP>(Sb + (size_t)(y + diry) * rowstride, sn);
+        // previous-row diagonal states: from the neighbouring column through shared memory, across strips through the halo
+        if (left_edge && t > 0) {
+            halo_get<NP>(Hptr(s, prv, 0), (uint32_t)t, err, pa);
+        } else {
+            load_regs<NP>(Xa + ((size_t)prv * (V3_COLS + 2) + gidx) * D + lane_off, pa);
+        }
+        if (right_edge && t > 0) {
+            halo_get<NP>(Hptr(s, prv, 1), (uint32_t)t, err, pb);
+        } else {
+            load_regs<NP>(Xb + ((size_t)prv * (V3_COLS + 2) + gidx + 2) * D + lane_off, pb);
+        }
+        __syncwarp();
+        sgm_step<NP, G>(pa, c, L, P1x2, P2x2, PADx2, lg);
+        if (right_edge) {   // publish first: the right neighbour needs this for its next row
+            unsigned long long* hp = Hptr(s + 1, cur, 0);
+#pragma unroll
+            for (int k = 0; k < NP; k++) halo_put(hp + k, pa[k], (uint32_t)(t + 1));
+        }
+        sgm_step<NP, G>(pb, c, acc, P1x2, P2x2, PADx2, lg);
+        if (left_edge) {
+            unsigned long long* hp = Hptr(s - 1, cur, 1);
+#pragma unroll
+            for (int k = 0; k < NP; k++) halo_put(hp + k, pb[k], (uint32_t)(t + 1));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < NP; k++) acc[k] = __vminu2(__vadd2(acc[k], L[k]), 0x7FFF7FFFu);
+        sgm_step<NP, G>(Pv, c, L, P1x2, P2x2, PADx2, lg);
+#pragma unroll
+        for (int k = 0; k < NP; k++) acc[k] = __vminu2(__vadd2(__vminu2(__vadd2(acc[k], L[k]), 0x7FFF7FFFu), so[k]), 0x7FFF7FFFu);
+        if (active) store_regs<NP>(Sb + (size_t)y * rowstride, acc);
+        if (!active) {
+#pragma unroll
+            for (int k = 0; k < NP; k++) { pa[k] = 0; pb[k] = 0; }
+        }
+        store_regs<NP>(Xa + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D + lane_off, pa);
+        store_regs<NP>(Xb + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D + lane_off, pb);
+        __syncthreads();
+        y += diry;
+    }
+}
+
 // WTA + uniqueness + sub-pixel for one pixel whose final S is in registers (all lanes of the group
 // take part; results are uniform across the group).
 template <int NP, int G>
@@ -556,6 +692,48 @@ int launch_path_h(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int1
     return SDR_OK;
 }
 
+struct V3Scratch {
+    DevBuf halo, err;
+    PinnedBuf host_err;
+};
+
+// Returns SDR_OK, an error, or -1 when the cooperative grid cannot be co-resident (caller falls back).
+template <int NP>
+int launch_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int16_t* S, int diry, int acc, V3Scratch& sc) {
+    constexpr int MINB = NP <= 8 ? 2 : 1;
+    auto kern = k_path_v3<NP, MINB>;
+    const int nstrips = div_up(g.W1, V3_COLS);
+    const size_t smem = (size_t)4 * (V3_COLS + 2) * g.D * sizeof(int16_t);
+    if (smem > ctx->smem_optin) return -1;
+    SDR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SDR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    const int cap = per_sm * ctx->sm_count;
+    if (cap < nstrips) return -1;
+    const int fpl = std::min(batch, cap / nstrips);
+    int rc;
+    const size_t halo_bytes = (size_t)nstrips * 4 * 8 * NP * sizeof(unsigned long long);   // per frame
+    if ((rc = sc.halo.reserve(ctx, halo_bytes * fpl))) return rc;
+    if (!sc.err.p) {
+        if ((rc = sc.err.reserve(ctx, sizeof(int)))) return rc;
+        if ((rc = sc.host_err.reserve(ctx, sizeof(int)))) return rc;
+        *(int*)sc.host_err.p = 0;
+        SDR_CUDA(ctx, cudaMemsetAsync(sc.err.p, 0, sizeof(int), ctx->stream));
+    }
+    for (int b0 = 0; b0 < batch; b0 += fpl) {
+        const int F = std::min(fpl, batch - b0);
+        SDR_CUDA(ctx, cudaMemsetAsync(sc.halo.p, 0, halo_bytes * F, ctx->stream));   // sequence numbers back to 0
+        Geom gg = g;
+        unsigned long long* halo = sc.halo.as<unsigned long long>();
+        int* err = sc.err.as<int>();
+        void* args[] = {(void*)&gg, (void*)&C, (void*)&S, (void*)&diry, (void*)&acc, (void*)&b0, (void*)&halo, (void*)&err};
+        SDR_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3(nstrips, F, 1), dim3(256, 1, 1), args, smem, ctx->stream));
+        ctx->launches++;
+    }
+    SDR_CUDA(ctx, cudaMemcpyAsync(sc.host_err.p, sc.err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return SDR_OK;
+}
+
 #define NP_SWITCH(np, CALL)                                                              \
     switch (np) {                                                                        \
         case 1: { constexpr int NPc = 1; CALL; } break;                                  \
@@ -587,6 +765,8 @@ struct sdr_sgbm {
     sdr_sgbm_params p{};
     DevBuf inL, inR, PL, PR, C, S, dispraw, wta, matched, out;
     SpeckleScratch speckle;
+    V3Scratch v3;
+    bool use_fused_sweep = true;
     StageTimer timer;
     Geom g{};
     int last_batch = 0;
@@ -620,6 +800,7 @@ extern "C" int sdr_sgbm_create(sdr_ctx* ctx, const sdr_sgbm_params* params, sdr_
     sdr_sgbm* m = new sdr_sgbm();
     m->ctx = ctx;
     m->p = *params;
+    m->use_fused_sweep = getenv("SDR_DISABLE_FUSED_SWEEP") == nullptr;   // A/B switch for the cooperative sweep
     *out = m;
     return SDR_OK;
 }
@@ -628,8 +809,9 @@ extern "C" void sdr_sgbm_destroy(sdr_sgbm* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
     for (DevBuf* b : {&m->inL, &m->inR, &m->PL, &m->PR, &m->C, &m->S, &m->dispraw, &m->wta, &m->matched, &m->out,
-                      &m->speckle.parent, &m->speckle.count})
+                      &m->speckle.parent, &m->speckle.count, &m->v3.halo, &m->v3.err})
         b->release();
+    m->v3.host_err.release();
     m->timer.release();
     delete m;
 }
@@ -740,12 +922,25 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
             if (rc) return rc;
             m->timer.mark(st, "path_v");
         } else {
-            const int dirs[6][2] = {{0, +1}, {+1, +1}, {-1, +1}, {0, -1}, {+1, -1}, {-1, -1}};
-            const int nd = m->p.mode == SDR_MODE_HH ? 6 : 3;
-            for (int i = 0; i < nd; i++) {
-                NP_SWITCH(np, rc = launch_path_v<NPc>(ctx, g, batch, C, S, dirs[i][0], dirs[i][1], i > 0));
+            // a previous fused sweep that timed out on its neighbour flags poisons the handle
+            if (m->v3.host_err.p && *(volatile int*)m->v3.host_err.p)
+                return SDR_FAIL(ctx, SDR_ECUDA, "fused path sweep timed out waiting for a neighbouring strip");
+            const int npass = m->p.mode == SDR_MODE_HH ? 2 : 1;
+            bool fused = m->use_fused_sweep;
+            for (int pass = 0; pass < npass && fused; pass++) {
+                NP_SWITCH(np, rc = launch_path_v3<NPc>(ctx, g, batch, C, S, pass == 0 ? +1 : -1, pass, m->v3));
+                if (rc == -1) { fused = false; break; }   // grid cannot be co-resident: separate launches per direction
                 if (rc) return rc;
-                m->timer.mark(st, i == 0 ? "path_v0" : i == 1 ? "path_v1" : i == 2 ? "path_v2" : i == 3 ? "path_v3" : i == 4 ? "path_v4" : "path_v5");
+                m->timer.mark(st, pass == 0 ? "path_v_fused_down" : "path_v_fused_up");
+            }
+            if (!fused) {
+                const int dirs[6][2] = {{0, +1}, {+1, +1}, {-1, +1}, {0, -1}, {+1, -1}, {-1, -1}};
+                const int nd = m->p.mode == SDR_MODE_HH ? 6 : 3;
+                for (int i = 0; i < nd; i++) {
+                    NP_SWITCH(np, rc = launch_path_v<NPc>(ctx, g, batch, C, S, dirs[i][0], dirs[i][1], i > 0));
+                    if (rc) return rc;
+                    m->timer.mark(st, i == 0 ? "path_v0" : i == 1 ? "path_v1" : i == 2 ? "path_v2" : i == 3 ? "path_v3" : i == 4 ? "path_v4" : "path_v5");
+                }
             }
         }
         NP_SWITCH(np, rc = launch_path_h<NPc>(ctx, g, batch, C, S, +1, 1, false, nullptr, nullptr));
