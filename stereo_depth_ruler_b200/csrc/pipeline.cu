@@ -12,7 +12,7 @@ struct sdr_pipeline {
     sdr_pipeline_options opt{};
     sdr_rectifier* rect = nullptr;
     sdr_sgbm* sgbm = nullptr;
-    std::vector<sdr_cloud*> clouds;
+    sdr_cloud* cloud = nullptr;
     DevBuf sbs, rectL, rectR, grayL, grayR, disp, points, minkey;
     StageTimer timer;
 };
@@ -26,11 +26,7 @@ extern "C" int sdr_pipeline_create(sdr_ctx* ctx, const sdr_calibration* calib, c
     p->opt = *opt;
     int rc = sdr_rectifier_create(ctx, calib, &p->rect);
     if (rc == SDR_OK) rc = sdr_sgbm_create(ctx, &opt->sgbm, &p->sgbm);
-    for (int i = 0; rc == SDR_OK && i < opt->batch; i++) {
-        sdr_cloud* c = nullptr;
-        rc = sdr_cloud_create(ctx, &c);
-        if (rc == SDR_OK) p->clouds.push_back(c);
-    }
+    if (rc == SDR_OK) rc = sdr_cloud_create(ctx, &p->cloud);
     if (rc != SDR_OK) {
         sdr_pipeline_destroy(p);
         return rc;
@@ -44,7 +40,7 @@ extern "C" void sdr_pipeline_destroy(sdr_pipeline* p) {
     cudaSetDevice(p->ctx->device);
     if (p->rect) sdr_rectifier_destroy(p->rect);
     if (p->sgbm) sdr_sgbm_destroy(p->sgbm);
-    for (sdr_cloud* c : p->clouds) sdr_cloud_destroy(c);
+    if (p->cloud) sdr_cloud_destroy(p->cloud);
     for (DevBuf* b : {&p->sbs, &p->rectL, &p->rectR, &p->grayL, &p->grayR, &p->disp, &p->points, &p->minkey}) b->release();
     p->timer.release();
     delete p;
@@ -115,12 +111,9 @@ extern "C" int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sd
         p->timer.mark(st, "reproject");
     }
     if (views) {
-        for (int i = 0; i < n; i++) {
-            if ((rc = sdr_cloud_enqueue(p->clouds[i], nullptr, 0, p->disp.as<uint8_t>() + (size_t)i * gray_frame * 2, (size_t)W * 2,
-                                        p->rectL.as<uint8_t>() + (size_t)i * bgr_frame, (size_t)W * 3, W, H, p->calib.Q, p->opt.handle_missing,
-                                        &p->opt.voxel)))
-                return rc;
-        }
+        if ((rc = sdr_cloud_enqueue(p->cloud, n, nullptr, 0, 0, p->disp.as<uint8_t>(), (size_t)W * 2, gray_frame * 2, p->rectL.as<uint8_t>(),
+                                    (size_t)W * 3, bgr_frame, W, H, p->calib.Q, p->opt.handle_missing, &p->opt.voxel)))
+            return rc;
         p->timer.mark(st, "voxelgrid");
     }
     // 5. outputs
@@ -143,12 +136,11 @@ extern "C" int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sd
     }
     p->timer.mark(st, "d2h");
     int status = SDR_OK;
-    if (views)
-        for (int i = 0; i < n; i++) {
-            rc = sdr_cloud_finish(p->clouds[i], &views[i]);
-            if (rc == SDR_EVOXEL_OVERFLOW) status = rc;
-            else if (rc) return rc;
-        }
+    if (views) {
+        rc = sdr_cloud_finish(p->cloud, views);
+        if (rc == SDR_EVOXEL_OVERFLOW) status = rc;
+        else if (rc) return rc;
+    }
     SDR_CUDA(ctx, cudaStreamSynchronize(st));
     return status;
 }
@@ -166,6 +158,7 @@ extern "C" int sdr_pipeline_stage_times(sdr_pipeline* p, int cap, const char** n
 }
 
 extern "C" int sdr_pipeline_cloud_download(sdr_pipeline* p, int i, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt) {
-    if (!p || i < 0 || i >= (int)p->clouds.size()) return SDR_EINVAL;
-    return sdr_cloud_download(p->clouds[i], xyz, rgb, idx, cnt);
+    if (!p || !p->cloud) return SDR_EINVAL;
+    cudaSetDevice(p->ctx->device);
+    return sdr_cloud_download_frame(p->cloud, i, xyz, rgb, idx, cnt);
 }

@@ -60,27 +60,68 @@ __device__ __forceinline__ const int16_t* img_row(const int16_t* img, size_t pit
     return (const int16_t*)((const uint8_t*)img + (size_t)b * frame + (size_t)y * pitch);
 }
 
-__global__ void __launch_bounds__(256) k_speckle_init(int* parent, int* count, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { parent[(size_t)blockIdx.z * n + i] = i; count[(size_t)blockIdx.z * n + i] = 0; }
+// Row pass: every pixel's parent starts at the first pixel of its horizontal run (a max-scan of the run-start
+// positions along the row), so only vertical links remain to be merged and the trees start out flat.
+__global__ void __launch_bounds__(256) k_speckle_rows(const int16_t* img, size_t pitch, size_t frame, int W, int H, int new_val,
+                                                      int max_diff, int* parent, int* count) {
+    __shared__ int warp_max[8];
+    __shared__ int carry_s;
+    const int y = blockIdx.x, b = blockIdx.z;
+    const int16_t* r = img_row(img, pitch, frame, b, y);
+    int* par = parent + (size_t)b * W * H + (size_t)y * W;
+    int* cnt = count + (size_t)b * W * H + (size_t)y * W;
+    if (threadIdx.x == 0) carry_s = -1;
+    __syncthreads();
+    for (int x0 = 0; x0 < W; x0 += 256) {
+        const int x = x0 + threadIdx.x;
+        int start = -1;   // position of the most recent run start at or before x (within this chunk)
+        bool valid = false;
+        if (x < W) {
+            const int v = r[x];
+            valid = v != new_val;
+            bool conn_left = false;
+            if (valid && x > 0) {
+                const int u = r[x - 1];
+                conn_left = u != new_val && abs(u - v) <= max_diff;
+            }
+            if (!conn_left) start = x;
+        }
+        int m = start;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, m, o);
+            if ((threadIdx.x & 31) >= o) m = max(m, t);
+        }
+        if ((threadIdx.x & 31) == 31) warp_max[threadIdx.x >> 5] = m;
+        __syncthreads();
+        int pre = carry_s;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) pre = max(pre, warp_max[w]);
+        m = max(m, pre);
+        if (x < W) {
+            par[x] = valid ? y * W + m : y * W + x;
+            cnt[x] = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) carry_s = m;
+        __syncthreads();
+    }
 }
 
+// Vertical links. A link at x is implied by the one at x-1 when both rows continue their runs from x-1 to x.
 __global__ void __launch_bounds__(256) k_speckle_merge(const int16_t* img, size_t pitch, size_t frame, int W, int H, int new_val,
                                                        int max_diff, int* parent) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
-    if (x >= W) return;
+    if (x >= W || y + 1 >= H) return;
     int* par = parent + (size_t)b * W * H;
-    const int16_t* r = img_row(img, pitch, frame, b, y);
-    const int v = r[x];
-    if (v == new_val) return;
-    if (x + 1 < W) {
-        const int u = r[x + 1];
-        if (u != new_val && abs(u - v) <= max_diff) uf_union(par, y * W + x, y * W + x + 1);
+    const int16_t* r0 = img_row(img, pitch, frame, b, y);
+    const int16_t* r1 = img_row(img, pitch, frame, b, y + 1);
+    const int v = r0[x], u = r1[x];
+    if (v == new_val || u == new_val || abs(u - v) > max_diff) return;
+    if (x > 0) {
+        const int vl = r0[x - 1], ul = r1[x - 1];
+        if (vl != new_val && ul != new_val && abs(vl - v) <= max_diff && abs(ul - u) <= max_diff && abs(ul - vl) <= max_diff) return;
     }
-    if (y + 1 < H) {
-        const int u = img_row(img, pitch, frame, b, y + 1)[x];
-        if (u != new_val && abs(u - v) <= max_diff) uf_union(par, y * W + x, (y + 1) * W + x);
-    }
+    uf_union(par, y * W + x, (y + 1) * W + x);
 }
 
 // Flatten to roots and count component sizes (one atomic per distinct root per warp).
@@ -132,7 +173,8 @@ int sdr_launch_speckle(sdr_ctx* ctx, int16_t* img, size_t pitch, int W, int H, i
     if ((rc = s.parent.reserve(ctx, n * batch * sizeof(int)))) return rc;
     if ((rc = s.count.reserve(ctx, n * batch * sizeof(int)))) return rc;
     const dim3 grid(div_up(W, 256), H, batch);
-    k_speckle_init<<<dim3(div_up((int)n, 256), 1, batch), 256, 0, ctx->stream>>>(s.parent.as<int>(), s.count.as<int>(), (int)n);
+    k_speckle_rows<<<dim3(H, 1, batch), 256, 0, ctx->stream>>>(img, pitch, frame_bytes, W, H, new_val, max_diff, s.parent.as<int>(),
+                                                               s.count.as<int>());
     SDR_LAUNCHED(ctx);
     k_speckle_merge<<<grid, 256, 0, ctx->stream>>>(img, pitch, frame_bytes, W, H, new_val, max_diff, s.parent.as<int>());
     SDR_LAUNCHED(ctx);

@@ -101,7 +101,9 @@ int sdr_launch_rectify(sdr_rectifier* r, int batch, int channels, const uint8_t*
                        const size_t dst_frame[2], uint8_t* const gray[2], const size_t gray_step[2], const size_t gray_frame[2]);
 int sdr_launch_reproject(sdr_ctx* ctx, bool is16, const uint8_t* disp, size_t step, size_t frame, int W, int H, int batch,
                          const double* Q, int handle_missing, int* min_key, float* out, size_t ostep, size_t oframe);
-int sdr_cloud_enqueue(sdr_cloud* c, const uint8_t* points, size_t pstep, const uint8_t* disp, size_t dstep, const uint8_t* bgr, size_t cstep,
-                      int W, int H, const double* Q, int handle_missing, const sdr_voxel_options* opt);
-int sdr_cloud_finish(sdr_cloud* c, sdr_cloud_view* view);
+int sdr_cloud_enqueue(sdr_cloud* c, int frames, const uint8_t* points, size_t pstep, size_t pframe, const uint8_t* disp, size_t dstep,
+                      size_t dframe, const uint8_t* bgr, size_t cstep, size_t cframe, int W, int H, const double* Q, int handle_missing,
+                      const sdr_voxel_options* opt);
+int sdr_cloud_finish(sdr_cloud* c, sdr_cloud_view* views);
+int sdr_cloud_download_frame(sdr_cloud* c, int f, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt);
 StageTimer* sdr_sgbm_timer(sdr_sgbm* m);

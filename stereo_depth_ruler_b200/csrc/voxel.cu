@@ -35,6 +35,7 @@ struct Source {  // where a pixel's 3-D point comes from
     size_t dstep;
     const uint8_t* bgr;  // optional
     size_t cstep;
+    size_t pframe, dframe, cframe;  // bytes between consecutive frames of a batch
     int W, H;
     QMat Q;
     int handle_missing, from_disp;
@@ -49,10 +50,10 @@ __device__ __forceinline__ int fkey(float f) {
 __device__ __forceinline__ float kfloat(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
 
 // xyz of pixel i; returns false when the point does not enter the voxel grid.
-__device__ __forceinline__ bool fetch_point(const Source& s, const VoxParams* vp, int i, float& X, float& Y, float& Z) {
+__device__ __forceinline__ bool fetch_point(const Source& s, const VoxParams* vp, int fr, int i, float& X, float& Y, float& Z) {
     const int y = i / s.W, x = i - y * s.W;
     int d16 = 0;
-    if (s.disp) d16 = ((const int16_t*)(s.disp + (size_t)y * s.dstep))[x];
+    if (s.disp) d16 = ((const int16_t*)(s.disp + (size_t)fr * s.dframe + (size_t)y * s.dstep))[x];
     if (s.from_disp) {
         const float df = (float)d16 * 0.0625f;
         const double d = (double)df, dx = (double)x, dy = (double)y;
@@ -67,7 +68,7 @@ __device__ __forceinline__ bool fetch_point(const Source& s, const VoxParams* vp
         Z = (float)__dmul_rn((double)(float)h[2], iw);
         if (s.handle_missing && fabs(d - (double)kfloat(vp->min_disp_key)) <= 1.1920928955078125e-07) Z = 10000.f;
     } else {
-        const float* p = (const float*)(s.points + (size_t)y * s.pstep) + (size_t)x * 3;
+        const float* p = (const float*)(s.points + (size_t)fr * s.pframe + (size_t)y * s.pstep) + (size_t)x * 3;
         X = p[0]; Y = p[1]; Z = p[2];
     }
     if (!(isfinite(X) && isfinite(Y) && isfinite(Z))) return false;  // pcd_write.cpp:35 + PCL isXYZFinite
@@ -76,7 +77,8 @@ __device__ __forceinline__ bool fetch_point(const Source& s, const VoxParams* vp
     return true;
 }
 
-__global__ void k_vox_reset(VoxParams* vp) {
+__global__ void k_vox_reset(VoxParams* vp0) {
+    VoxParams* vp = vp0 + blockIdx.x;
     vp->bbox_key[0] = vp->bbox_key[1] = vp->bbox_key[2] = 0x7FFFFFFF;
     vp->bbox_key[3] = vp->bbox_key[4] = vp->bbox_key[5] = (int)0x80000000;
     vp->nvalid = 0;
@@ -85,12 +87,13 @@ __global__ void k_vox_reset(VoxParams* vp) {
     vp->min_disp_key = 0x7FFFFFFF;
 }
 
-__global__ void __launch_bounds__(256) k_vox_mindisp(Source s, VoxParams* vp) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_vox_mindisp(Source s, VoxParams* vp0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, fr = blockIdx.y;
+    VoxParams* vp = vp0 + fr;
     int key = 0x7FFFFFFF;
     if (i < s.W * s.H) {
         const int y = i / s.W, x = i - y * s.W;
-        key = fkey((float)((const int16_t*)(s.disp + (size_t)y * s.dstep))[x] * 0.0625f);
+        key = fkey((float)((const int16_t*)(s.disp + (size_t)fr * s.dframe + (size_t)y * s.dstep))[x] * 0.0625f);
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
@@ -103,13 +106,14 @@ __global__ void __launch_bounds__(256) k_vox_mindisp(Source s, VoxParams* vp) {
     }
 }
 
-__global__ void __launch_bounds__(256) k_vox_bbox(Source s, VoxParams* vp) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_vox_bbox(Source s, VoxParams* vp0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, fr = blockIdx.y;
+    VoxParams* vp = vp0 + fr;
     int mn[3] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF}, mx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
     unsigned ok = 0;
     if (i < s.W * s.H) {
         float p[3];
-        if (fetch_point(s, vp, i, p[0], p[1], p[2])) {
+        if (fetch_point(s, vp, fr, i, p[0], p[1], p[2])) {
             ok = 1;
 #pragma unroll
             for (int c = 0; c < 3; c++) mn[c] = mx[c] = fkey(p[c]);
@@ -151,7 +155,8 @@ __global__ void __launch_bounds__(256) k_vox_bbox(Source s, VoxParams* vp) {
 }
 
 // PCL: inverse leaf, int64 guard, min_b / div_b / divb_mul (all fp32 as in voxel_grid.hpp)
-__global__ void k_vox_params(VoxParams* vp, float lx, float ly, float lz) {
+__global__ void k_vox_params(VoxParams* vp0, float lx, float ly, float lz) {
+    VoxParams* vp = vp0 + blockIdx.x;
     const float leaf[3] = {lx, ly, lz};
     if (vp->nvalid == 0) {
         for (int c = 0; c < 3; c++) { vp->inv[c] = __fdiv_rn(1.0f, leaf[c]); vp->minb[c] = 0; vp->divb[c] = 1; vp->mul[c] = 1; }
@@ -175,13 +180,16 @@ __global__ void k_vox_params(VoxParams* vp, float lx, float ly, float lz) {
     vp->mul[2] = (int)((unsigned)vp->divb[0] * (unsigned)vp->divb[1]);
 }
 
-__global__ void __launch_bounds__(256) k_vox_keys(Source s, const VoxParams* vp, uint32_t* keys, uint32_t* vals, int npad) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_vox_keys(Source s, const VoxParams* vp0, uint32_t* keys, uint32_t* vals, int npad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, fr = blockIdx.y;
     if (i >= npad) return;
+    const VoxParams* vp = vp0 + fr;
+    keys += (size_t)fr * npad;
+    vals += (size_t)fr * npad;
     uint32_t key = 0xFFFFFFFFu;
     if (i < s.W * s.H && !vp->overflow) {
         float p[3];
-        if (fetch_point(s, vp, i, p[0], p[1], p[2])) {
+        if (fetch_point(s, vp, fr, i, p[0], p[1], p[2])) {
             const int i0 = (int)__fsub_rn(floorf(__fmul_rn(p[0], vp->inv[0])), (float)vp->minb[0]);
             const int i1 = (int)__fsub_rn(floorf(__fmul_rn(p[1], vp->inv[1])), (float)vp->minb[1]);
             const int i2 = (int)__fsub_rn(floorf(__fmul_rn(p[2], vp->inv[2])), (float)vp->minb[2]);
@@ -200,6 +208,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint32_t* __restri
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
+    keys += (size_t)blockIdx.y * n;
+    hist += (size_t)blockIdx.y * 256 * nblocks;
     const int base = blockIdx.x * RS_TILE;
 #pragma unroll
     for (int k = 0; k < RS_ITEMS; k++) {
@@ -211,9 +221,11 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint32_t* __restri
 }
 
 // exclusive scan of m uint32 values by one block (digit-major histogram, or head flags)
-__global__ void __launch_bounds__(1024) k_scan_block(uint32_t* data, int m, uint32_t* total) {
+__global__ void __launch_bounds__(1024) k_scan_block(uint32_t* data, int m, uint32_t* total, size_t total_stride_bytes) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
+    data += (size_t)blockIdx.x * m;
+    if (total) total = (uint32_t*)((uint8_t*)total + (size_t)blockIdx.x * total_stride_bytes);
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (int base = 0; base < m; base += 1024) {
@@ -276,6 +288,8 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_s
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t* __restrict__ data, int m, uint32_t* __restrict__ sums) {
     __shared__ uint32_t ws[33];
+    data += (size_t)blockIdx.y * m;
+    sums += (size_t)blockIdx.y * gridDim.x;
     const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint32_t v = 0;
 #pragma unroll
@@ -288,6 +302,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t*
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_apply(uint32_t* __restrict__ data, int m, const uint32_t* __restrict__ sums) {
     __shared__ uint32_t ws[33];
+    data += (size_t)blockIdx.y * m;
+    sums += (size_t)blockIdx.y * gridDim.x;
     const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint32_t x[SCAN_ITEMS], v = 0;
 #pragma unroll
@@ -309,6 +325,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t* __res
                                                            uint32_t* __restrict__ okeys, uint32_t* __restrict__ ovals) {
     constexpr int NW = RS_THREADS / 32;
     __shared__ uint32_t wcount[NW][256];
+    keys += (size_t)blockIdx.y * n; vals += (size_t)blockIdx.y * n;
+    okeys += (size_t)blockIdx.y * n; ovals += (size_t)blockIdx.y * n;
+    hist += (size_t)blockIdx.y * 256 * nblocks;
     for (int i = threadIdx.x; i < NW * 256; i += RS_THREADS) (&wcount[0][0])[i] = 0;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -362,16 +381,21 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t* __res
 __global__ void __launch_bounds__(256) k_vox_heads(const uint32_t* __restrict__ keys, int n, uint32_t* __restrict__ flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    keys += (size_t)blockIdx.y * n;
+    flags += (size_t)blockIdx.y * n;
     const uint32_t k = keys[i];
     flags[i] = (k != 0xFFFFFFFFu && (i == 0 || keys[i - 1] != k)) ? 1u : 0u;
 }
 
-__global__ void __launch_bounds__(256) k_vox_reduce(Source s, VoxParams* vp, const uint32_t* __restrict__ keys,
+__global__ void __launch_bounds__(256) k_vox_reduce(Source s, VoxParams* vp0, const uint32_t* __restrict__ keys,
                                                     const uint32_t* __restrict__ vals, const uint32_t* __restrict__ slot, int n,
                                                     float* __restrict__ oxyz, uint8_t* __restrict__ orgb, uint32_t* __restrict__ oidx,
                                                     uint32_t* __restrict__ ocnt) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, fr = blockIdx.y;
     if (i >= n) return;
+    VoxParams* vp = vp0 + fr;
+    keys += (size_t)fr * n; vals += (size_t)fr * n; slot += (size_t)fr * n;
+    oxyz += (size_t)fr * n * 3; orgb += (size_t)fr * n * 3; oidx += (size_t)fr * n; ocnt += (size_t)fr * n;
     const uint32_t key = keys[i];
     if (key == 0xFFFFFFFFu || (i > 0 && keys[i - 1] == key)) return;
     float sx = 0.f, sy = 0.f, sz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
@@ -379,11 +403,11 @@ __global__ void __launch_bounds__(256) k_vox_reduce(Source s, VoxParams* vp, con
     for (int j = i; j < n && keys[j] == key; j++) {
         const int pt = (int)vals[j];
         float X, Y, Z;
-        fetch_point(s, vp, pt, X, Y, Z);
+        fetch_point(s, vp, fr, pt, X, Y, Z);
         sx = __fadd_rn(sx, X); sy = __fadd_rn(sy, Y); sz = __fadd_rn(sz, Z);
         if (s.bgr) {
             const int y = pt / s.W, x = pt - y * s.W;
-            const uint8_t* c = s.bgr + (size_t)y * s.cstep + (size_t)x * 3;
+            const uint8_t* c = s.bgr + (size_t)fr * s.cframe + (size_t)y * s.cstep + (size_t)x * 3;
             sr = __fadd_rn(sr, (float)c[2]); sg = __fadd_rn(sg, (float)c[1]); sb = __fadd_rn(sb, (float)c[0]);
         }
         cnt++;
@@ -401,14 +425,17 @@ __global__ void __launch_bounds__(256) k_vox_reduce(Source s, VoxParams* vp, con
 }
 
 // PCL passthrough ("Leaf size is too small"): output = input cloud, organised, NaN where non-finite.
-__global__ void __launch_bounds__(256) k_vox_passthrough(Source s, const VoxParams* vp, float* __restrict__ oxyz, uint8_t* __restrict__ orgb) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_vox_passthrough(Source s, const VoxParams* vp0, float* __restrict__ oxyz, uint8_t* __restrict__ orgb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, fr = blockIdx.y;
+    const VoxParams* vp = vp0 + fr;
     if (i >= s.W * s.H || !vp->overflow) return;
+    oxyz += (size_t)fr * s.W * s.H * 3;
+    orgb += (size_t)fr * s.W * s.H * 3;
     Source t = s;
     t.drop_invalid = 0;
     t.z_max = 0.f;
     float X, Y, Z;
-    const bool fin = fetch_point(t, vp, i, X, Y, Z);
+    const bool fin = fetch_point(t, vp, fr, i, X, Y, Z);
     const float nan = __int_as_float(0x7FC00000);
     oxyz[(size_t)i * 3] = fin ? X : nan;
     oxyz[(size_t)i * 3 + 1] = fin ? Y : nan;
@@ -416,7 +443,7 @@ __global__ void __launch_bounds__(256) k_vox_passthrough(Source s, const VoxPara
     uint8_t r = 0, g = 0, b = 0;
     if (fin && s.bgr) {
         const int y = i / s.W, x = i - y * s.W;
-        const uint8_t* c = s.bgr + (size_t)y * s.cstep + (size_t)x * 3;
+        const uint8_t* c = s.bgr + (size_t)fr * s.cframe + (size_t)y * s.cstep + (size_t)x * 3;
         r = c[2]; g = c[1]; b = c[0];
     }
     orgb[(size_t)i * 3] = r; orgb[(size_t)i * 3 + 1] = g; orgb[(size_t)i * 3 + 2] = b;
@@ -431,8 +458,9 @@ struct sdr_cloud {
     DevBuf oxyz, orgb, oidx, ocnt;
     PinnedBuf host_params;
     cudaEvent_t done = nullptr;
-    int64_t last_n = 0;
-    int last_passthrough = 0;
+    int frames = 0;                 // frames of the last enqueue
+    std::vector<int64_t> last_n;
+    std::vector<int> last_passthrough;
     int W = 0, H = 0;
 };
 
@@ -455,43 +483,48 @@ extern "C" void sdr_cloud_destroy(sdr_cloud* c) {
     delete c;
 }
 
-static int scan_u32(sdr_cloud* c, uint32_t* data, int m, uint32_t* total) {
+// `frames` independent exclusive scans of m values each (data[f*m ...]); totals (optional) at total + f*stride bytes.
+static int scan_u32(sdr_cloud* c, int frames, uint32_t* data, int m, uint32_t* total, size_t total_stride) {
     sdr_ctx* ctx = c->ctx;
     const int nt = div_up(m, SCAN_TILE);
-    int rc = c->scan_sums.reserve(ctx, (size_t)nt * 4);
+    int rc = c->scan_sums.reserve(ctx, (size_t)nt * frames * 4);
     if (rc) return rc;
-    k_scan_tile_sums<<<nt, SCAN_THREADS, 0, ctx->stream>>>(data, m, c->scan_sums.as<uint32_t>());
+    k_scan_tile_sums<<<dim3(nt, frames), SCAN_THREADS, 0, ctx->stream>>>(data, m, c->scan_sums.as<uint32_t>());
     SDR_LAUNCHED(ctx);
-    k_scan_block<<<1, 1024, 0, ctx->stream>>>(c->scan_sums.as<uint32_t>(), nt, total);
+    k_scan_block<<<frames, 1024, 0, ctx->stream>>>(c->scan_sums.as<uint32_t>(), nt, total, total_stride);
     SDR_LAUNCHED(ctx);
-    k_scan_tile_apply<<<nt, SCAN_THREADS, 0, ctx->stream>>>(data, m, c->scan_sums.as<uint32_t>());
+    k_scan_tile_apply<<<dim3(nt, frames), SCAN_THREADS, 0, ctx->stream>>>(data, m, c->scan_sums.as<uint32_t>());
     SDR_LAUNCHED(ctx);
     return SDR_OK;
 }
 
-// Enqueues the whole voxelisation on the ctx stream; the result header lands in c->host_params.
-int sdr_cloud_enqueue(sdr_cloud* c, const uint8_t* points, size_t pstep, const uint8_t* disp, size_t dstep, const uint8_t* bgr, size_t cstep,
-                      int W, int H, const double* Q, int handle_missing, const sdr_voxel_options* opt) {
+// Enqueues the voxelisation of `frames` clouds (one per frame of the batch) on the ctx stream; every kernel covers the
+// whole batch. The result headers land in c->host_params.
+int sdr_cloud_enqueue(sdr_cloud* c, int frames, const uint8_t* points, size_t pstep, size_t pframe, const uint8_t* disp, size_t dstep,
+                      size_t dframe, const uint8_t* bgr, size_t cstep, size_t cframe, int W, int H, const double* Q, int handle_missing,
+                      const sdr_voxel_options* opt) {
     sdr_ctx* ctx = c->ctx;
     cudaStream_t st = ctx->stream;
     const int n = W * H;
     const int nblocks = div_up(n, RS_TILE);
+    const size_t F = (size_t)frames;
     int rc;
     for (int i = 0; i < 2; i++) {
-        if ((rc = c->keys[i].reserve(ctx, (size_t)n * 4))) return rc;
-        if ((rc = c->vals[i].reserve(ctx, (size_t)n * 4))) return rc;
+        if ((rc = c->keys[i].reserve(ctx, F * n * 4))) return rc;
+        if ((rc = c->vals[i].reserve(ctx, F * n * 4))) return rc;
     }
-    if ((rc = c->hist.reserve(ctx, (size_t)256 * nblocks * 4))) return rc;
-    if ((rc = c->flags.reserve(ctx, (size_t)n * 4))) return rc;
-    if ((rc = c->params.reserve(ctx, sizeof(VoxParams)))) return rc;
-    if ((rc = c->oxyz.reserve(ctx, (size_t)n * 12))) return rc;
-    if ((rc = c->orgb.reserve(ctx, (size_t)n * 3))) return rc;
-    if ((rc = c->oidx.reserve(ctx, (size_t)n * 4))) return rc;
-    if ((rc = c->ocnt.reserve(ctx, (size_t)n * 4))) return rc;
-    if ((rc = c->host_params.reserve(ctx, sizeof(VoxParams)))) return rc;
-    c->W = W; c->H = H;
+    if ((rc = c->hist.reserve(ctx, F * 256 * nblocks * 4))) return rc;
+    if ((rc = c->flags.reserve(ctx, F * n * 4))) return rc;
+    if ((rc = c->params.reserve(ctx, F * sizeof(VoxParams)))) return rc;
+    if ((rc = c->oxyz.reserve(ctx, F * n * 12))) return rc;
+    if ((rc = c->orgb.reserve(ctx, F * n * 3))) return rc;
+    if ((rc = c->oidx.reserve(ctx, F * n * 4))) return rc;
+    if ((rc = c->ocnt.reserve(ctx, F * n * 4))) return rc;
+    if ((rc = c->host_params.reserve(ctx, F * sizeof(VoxParams)))) return rc;
+    c->W = W; c->H = H; c->frames = frames;
     Source s{};
-    s.points = points; s.pstep = pstep; s.disp = disp; s.dstep = dstep; s.bgr = bgr; s.cstep = cstep; s.W = W; s.H = H;
+    s.points = points; s.pstep = pstep; s.pframe = pframe; s.disp = disp; s.dstep = dstep; s.dframe = dframe;
+    s.bgr = bgr; s.cstep = cstep; s.cframe = cframe; s.W = W; s.H = H;
     s.from_disp = points == nullptr;
     if (Q) memcpy(s.Q.q, Q, sizeof s.Q.q);
     s.handle_missing = s.from_disp ? handle_missing : 0;
@@ -499,8 +532,8 @@ int sdr_cloud_enqueue(sdr_cloud* c, const uint8_t* points, size_t pstep, const u
     s.min_valid16 = opt->min_disparity * 16;
     s.z_max = opt->z_max;
     VoxParams* vp = c->params.as<VoxParams>();
-    const int g256 = div_up(n, 256);
-    k_vox_reset<<<1, 1, 0, st>>>(vp);
+    const dim3 g256(div_up(n, 256), frames);
+    k_vox_reset<<<frames, 1, 0, st>>>(vp);
     SDR_LAUNCHED(ctx);
     if (s.from_disp && s.handle_missing) {
         k_vox_mindisp<<<g256, 256, 0, st>>>(s, vp);
@@ -508,55 +541,76 @@ int sdr_cloud_enqueue(sdr_cloud* c, const uint8_t* points, size_t pstep, const u
     }
     k_vox_bbox<<<g256, 256, 0, st>>>(s, vp);
     SDR_LAUNCHED(ctx);
-    k_vox_params<<<1, 1, 0, st>>>(vp, opt->leaf[0], opt->leaf[1], opt->leaf[2]);
+    k_vox_params<<<frames, 1, 0, st>>>(vp, opt->leaf[0], opt->leaf[1], opt->leaf[2]);
     SDR_LAUNCHED(ctx);
     k_vox_keys<<<g256, 256, 0, st>>>(s, vp, c->keys[0].as<uint32_t>(), c->vals[0].as<uint32_t>(), n);
     SDR_LAUNCHED(ctx);
     int cur = 0;
     for (int pass = 0; pass < 4; pass++) {
         const int shift = pass * 8;
-        k_rs_hist<<<nblocks, RS_THREADS, 0, st>>>(c->keys[cur].as<uint32_t>(), n, shift, c->hist.as<uint32_t>(), nblocks);
+        k_rs_hist<<<dim3(nblocks, frames), RS_THREADS, 0, st>>>(c->keys[cur].as<uint32_t>(), n, shift, c->hist.as<uint32_t>(), nblocks);
         SDR_LAUNCHED(ctx);
-        if ((rc = scan_u32(c, c->hist.as<uint32_t>(), 256 * nblocks, nullptr))) return rc;
-        k_rs_scatter<<<nblocks, RS_THREADS, 0, st>>>(c->keys[cur].as<uint32_t>(), c->vals[cur].as<uint32_t>(), n, shift, c->hist.as<uint32_t>(),
-                                                     nblocks, c->keys[cur ^ 1].as<uint32_t>(), c->vals[cur ^ 1].as<uint32_t>());
+        if ((rc = scan_u32(c, frames, c->hist.as<uint32_t>(), 256 * nblocks, nullptr, 0))) return rc;
+        k_rs_scatter<<<dim3(nblocks, frames), RS_THREADS, 0, st>>>(c->keys[cur].as<uint32_t>(), c->vals[cur].as<uint32_t>(), n, shift,
+                                                                   c->hist.as<uint32_t>(), nblocks, c->keys[cur ^ 1].as<uint32_t>(),
+                                                                   c->vals[cur ^ 1].as<uint32_t>());
         SDR_LAUNCHED(ctx);
         cur ^= 1;
     }
     k_vox_heads<<<g256, 256, 0, st>>>(c->keys[cur].as<uint32_t>(), n, c->flags.as<uint32_t>());
     SDR_LAUNCHED(ctx);
-    if ((rc = scan_u32(c, c->flags.as<uint32_t>(), n, &vp->nvox))) return rc;
+    if ((rc = scan_u32(c, frames, c->flags.as<uint32_t>(), n, &vp->nvox, sizeof(VoxParams)))) return rc;
     k_vox_reduce<<<g256, 256, 0, st>>>(s, vp, c->keys[cur].as<uint32_t>(), c->vals[cur].as<uint32_t>(), c->flags.as<uint32_t>(), n,
                                        c->oxyz.as<float>(), c->orgb.as<uint8_t>(), c->oidx.as<uint32_t>(), c->ocnt.as<uint32_t>());
     SDR_LAUNCHED(ctx);
     k_vox_passthrough<<<g256, 256, 0, st>>>(s, vp, c->oxyz.as<float>(), c->orgb.as<uint8_t>());
     SDR_LAUNCHED(ctx);
-    SDR_CUDA(ctx, cudaMemcpyAsync(c->host_params.p, vp, sizeof(VoxParams), cudaMemcpyDeviceToHost, st));
+    SDR_CUDA(ctx, cudaMemcpyAsync(c->host_params.p, vp, F * sizeof(VoxParams), cudaMemcpyDeviceToHost, st));
     if (!c->done) SDR_CUDA(ctx, cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
     SDR_CUDA(ctx, cudaEventRecord(c->done, st));
     return SDR_OK;
 }
 
-// Waits for the enqueued work and fills the view. Returns SDR_OK or SDR_EVOXEL_OVERFLOW.
-int sdr_cloud_finish(sdr_cloud* c, sdr_cloud_view* view) {
+// Waits for the enqueued work and fills the views (one per frame). Returns SDR_OK or SDR_EVOXEL_OVERFLOW.
+int sdr_cloud_finish(sdr_cloud* c, sdr_cloud_view* views) {
     sdr_ctx* ctx = c->ctx;
     SDR_CUDA(ctx, cudaEventSynchronize(c->done));
     const VoxParams* hp = (const VoxParams*)c->host_params.p;
-    c->last_passthrough = hp->overflow;
-    c->last_n = hp->overflow ? (int64_t)c->W * c->H : (int64_t)hp->nvox;
-    if (view) {
-        view->n = c->last_n;
-        view->xyz = c->oxyz.as<float>();
-        view->rgb = c->orgb.as<uint8_t>();
-        view->idx = hp->overflow ? nullptr : c->oidx.as<uint32_t>();
-        view->cnt = hp->overflow ? nullptr : c->ocnt.as<uint32_t>();
-        for (int i = 0; i < 3; i++) { view->min_b[i] = hp->minb[i]; view->div_b[i] = hp->divb[i]; }
-        view->passthrough = hp->overflow;
+    const size_t n = (size_t)c->W * c->H;
+    c->last_n.assign(c->frames, 0);
+    c->last_passthrough.assign(c->frames, 0);
+    int status = SDR_OK;
+    for (int f = 0; f < c->frames; f++) {
+        c->last_passthrough[f] = hp[f].overflow;
+        c->last_n[f] = hp[f].overflow ? (int64_t)n : (int64_t)hp[f].nvox;
+        if (views) {
+            sdr_cloud_view* view = views + f;
+            view->n = c->last_n[f];
+            view->xyz = c->oxyz.as<float>() + (size_t)f * n * 3;
+            view->rgb = c->orgb.as<uint8_t>() + (size_t)f * n * 3;
+            view->idx = hp[f].overflow ? nullptr : c->oidx.as<uint32_t>() + (size_t)f * n;
+            view->cnt = hp[f].overflow ? nullptr : c->ocnt.as<uint32_t>() + (size_t)f * n;
+            for (int i = 0; i < 3; i++) { view->min_b[i] = hp[f].minb[i]; view->div_b[i] = hp[f].divb[i]; }
+            view->passthrough = hp[f].overflow;
+        }
+        if (hp[f].overflow) status = SDR_EVOXEL_OVERFLOW;
     }
-    if (hp->overflow) {
+    if (status == SDR_EVOXEL_OVERFLOW)
         sdr_set_error(ctx, "[VoxelGrid] Leaf size is too small for the input dataset. Integer indices would overflow.");
-        return SDR_EVOXEL_OVERFLOW;
+    return status;
+}
+
+int sdr_cloud_download_frame(sdr_cloud* c, int f, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt) {
+    sdr_ctx* ctx = c->ctx;
+    if (f < 0 || f >= c->frames || f >= (int)c->last_n.size()) return SDR_FAIL(ctx, SDR_EINVAL, "cloud_download: no such frame %d", f);
+    const size_t n = (size_t)c->last_n[f], N = (size_t)c->W * c->H;
+    if (xyz) SDR_CUDA(ctx, cudaMemcpyAsync(xyz, c->oxyz.as<float>() + (size_t)f * N * 3, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rgb) SDR_CUDA(ctx, cudaMemcpyAsync(rgb, c->orgb.as<uint8_t>() + (size_t)f * N * 3, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!c->last_passthrough[f]) {
+        if (idx) SDR_CUDA(ctx, cudaMemcpyAsync(idx, c->oidx.as<uint32_t>() + (size_t)f * N, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (cnt) SDR_CUDA(ctx, cudaMemcpyAsync(cnt, c->ocnt.as<uint32_t>() + (size_t)f * N, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    SDR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SDR_OK;
 }
 
@@ -589,7 +643,7 @@ extern "C" int sdr_voxelgrid(sdr_cloud* c, const sdr_image* points, const sdr_im
     } else if (opt->drop_invalid) {
         return SDR_FAIL(ctx, SDR_EINVAL, "voxelgrid: drop_invalid needs the CV_16S disparity");
     }
-    if ((rc = sdr_cloud_enqueue(c, vp.p, vp.pitch, vd.p, vd.pitch, vc.p, vc.pitch, W, H, nullptr, 0, opt))) return rc;
+    if ((rc = sdr_cloud_enqueue(c, 1, vp.p, vp.pitch, 0, vd.p, vd.pitch, 0, vc.p, vc.pitch, 0, W, H, nullptr, 0, opt))) return rc;
     return sdr_cloud_finish(c, view);
 }
 
@@ -609,21 +663,12 @@ extern "C" int sdr_depth_cloud(sdr_cloud* c, const sdr_image* disp16, const sdr_
         if (bgr->cols != W || bgr->rows != H) return SDR_FAIL(ctx, SDR_ESIZE, "depth_cloud: colour image size differs");
         if ((rc = sdr_stage_in(ctx, bgr, c->in_bgr, &vc))) return rc;
     }
-    if ((rc = sdr_cloud_enqueue(c, nullptr, 0, vd.p, vd.pitch, vc.p, vc.pitch, W, H, Q, handle_missing, opt))) return rc;
+    if ((rc = sdr_cloud_enqueue(c, 1, nullptr, 0, 0, vd.p, vd.pitch, 0, vc.p, vc.pitch, 0, W, H, Q, handle_missing, opt))) return rc;
     return sdr_cloud_finish(c, view);
 }
 
 extern "C" int sdr_cloud_download(sdr_cloud* c, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt) {
     if (!c) return SDR_EINVAL;
-    sdr_ctx* ctx = c->ctx;
-    SDR_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t n = (size_t)c->last_n;
-    if (xyz) SDR_CUDA(ctx, cudaMemcpyAsync(xyz, c->oxyz.p, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
-    if (rgb) SDR_CUDA(ctx, cudaMemcpyAsync(rgb, c->orgb.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
-    if (!c->last_passthrough) {
-        if (idx) SDR_CUDA(ctx, cudaMemcpyAsync(idx, c->oidx.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (cnt) SDR_CUDA(ctx, cudaMemcpyAsync(cnt, c->ocnt.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    SDR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return SDR_OK;
+    SDR_CUDA(c->ctx, cudaSetDevice(c->ctx->device));
+    return sdr_cloud_download_frame(c, 0, xyz, rgb, idx, cnt);
 }
