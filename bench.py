@@ -133,7 +133,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from stereo_depth_ruler_b200 import capi
+    from stereo_depth_ruler_b200 import capi, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -174,7 +174,7 @@ def run_ours(args):
     n_pool = max(args.pool, 2 * B)
     frames_np = make_frames(n_pool)
     # frame i of the stream goes to rank i mod N: each rank builds the frames it owns (weak scaling: B per rank per step)
-    mine = [frames_np[(rank + j * world) % n_pool] for j in range(n_pool)]
+    mine = [frames_np[i % n_pool] for i in sharding.frames_for_rank(n_pool * world, rank, world)]
     dev_pool = torch.from_numpy(np.stack(mine)).cuda()                       # [P][H][2W][3] u8
     host_pool = torch.from_numpy(np.stack(mine)).pin_memory()
     host_np = host_pool.numpy()
@@ -208,12 +208,8 @@ def run_ours(args):
             e1.record(stream)
             barrier()
             t1 = time.perf_counter()
-        ms = e0.elapsed_time(e1)
+        ms = sharding.max_over_ranks(e0.elapsed_time(e1), dist if world > 1 else None)
         launches = ctx.kernel_launches - l0
-        if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
         return ms, launches, t0, t1
 
     # ---- value: frames resident in HBM ----
@@ -223,7 +219,7 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     ms, launches, t0, t1 = timed(step_dev, args.steps, args.warmup)
     clocks = sampler.stop(t0, t1) if sampler else None
-    fps = world * B * args.steps / (ms / 1e3)
+    fps = sharding.aggregate_throughput(B * args.steps, world, ms)
 
     # ---- per-kernel times of one step (CUDA events on the launching stream, inside the library) ----
     sg = capi.Sgbm(ctx, params)
@@ -293,7 +289,7 @@ def run_ours(args):
         cloud_bytes[0] = nb
 
     ms_e, _, _, _ = timed(step_host, args.steps, args.warmup)
-    fps_e = world * B * args.steps / (ms_e / 1e3)
+    fps_e = sharding.aggregate_throughput(B * args.steps, world, ms_e)
     h2d = B * H * 2 * W * 3
     d2h = B * H * W * 2 + cloud_bytes[0]
 
