@@ -442,6 +442,14 @@ class Pipeline:
             out.update(idx=idx, cnt=cnt)
         return out
 
+    def cloud_to_host_into(self, i, xyz, rgb, idx, cnt):
+        """Copies cloud i of the last run into caller-provided (ideally pinned) numpy buffers; returns the bytes copied."""
+        v = self.views[i]
+        self.ctx.check(lib().sdr_pipeline_cloud_download(self._h, int(i), xyz.ctypes.data_as(C.c_void_p), rgb.ctypes.data_as(C.c_void_p),
+                                                         idx.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)))
+        n = int(v.n)
+        return n * (12 + 3) + (0 if v.passthrough else n * 8)
+
     def set_profiling(self, on=True):
         lib().sdr_pipeline_set_profiling(self._h, int(on))
 
