@@ -198,7 +198,7 @@ def run_ours(args):
     # ---- two pipeline handles on two streams, one host thread each (a handle is one device <-> one stream; different
     # handles may run concurrently): kernels of one batch overlap kernels / copies of the other ----
     import threading
-    NSLOT = 2
+    NSLOT = args.slots
     slots = []
     for k in range(NSLOT):
         if k == 0:
@@ -371,6 +371,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8, help="frames per step per GPU")
     ap.add_argument("--pool", type=int, default=32, help="distinct frames resident per GPU (pool > L2)")
+    ap.add_argument("--slots", type=int, default=2, help="pipeline handles (streams + host threads) per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -284,9 +284,13 @@ __device__ __forceinline__ void store_regs(int16_t* p, const uint32_t (&r)[NP]) 
     }
 }
 
+// One path step, in place: on entry P = L of the previous pixel on the path and m = its minimum (packed in both halves);
+// on exit P = L of this pixel and m = its minimum.
+//   L[d] = C[d] + min( min(P[d], min(P[d-1], P[d+1]) + P1) - m, P2 )
+// which is OpenCV's C + min(Lr[d], Lr[d-1]+P1, Lr[d+1]+P1, minLr+P2) - (minLr+P2) with the +P2 bias folded out of C.
 template <int NP, int G>
-__device__ __forceinline__ void sgm_step(uint32_t (&P)[NP], const uint32_t (&c)[NP], uint32_t (&L)[NP], uint32_t P1x2,
-                                         uint32_t P2x2, uint32_t PADx2, int lg) {
+__device__ __forceinline__ void sgm_step(uint32_t (&P)[NP], uint32_t& m, const uint32_t (&c)[NP], uint32_t P1x2, uint32_t P2x2,
+                                         uint32_t PADx2, int lg) {
     uint32_t up = __shfl_up_sync(0xffffffffu, P[NP - 1], 1, G);
     uint32_t dn = __shfl_down_sync(0xffffffffu, P[0], 1, G);
     if (lg == 0) up = PADx2;
@@ -296,25 +300,22 @@ __device__ __forceinline__ void sgm_step(uint32_t (&P)[NP], const uint32_t (&c)[
 #pragma unroll
     for (int k = 1; k < NP; k++) T[k] = prmt(P[k - 1], P[k], 0x5432);
     T[NP] = prmt(P[NP - 1], dn, 0x5432);
-    uint32_t m = 0x7FFF7FFFu;
+    const uint32_t negm = __vadd2(~m, 0x00010001u);
+    uint32_t mm = 0x7FFF7FFFu;
 #pragma unroll
     for (int k = 0; k < NP; k++) {
         uint32_t t = __vmins2(T[k], T[k + 1]);
-        t = __viaddmin_s16x2(t, P1x2, P[k]);
-        t = __vmins2(t, P2x2);
-        L[k] = __vadd2(c[k], t);
-        m = __vmins2(m, L[k]);
+        t = __viaddmin_s16x2(t, P1x2, P[k]);      // min(t + P1, P[d])
+        t = __viaddmin_s16x2(t, negm, P2x2);      // min(. - m, P2)
+        P[k] = __vadd2(c[k], t);
+        if (k & 1) mm = __vimin3_s16x2(mm, P[k - 1], P[k]);
     }
-    m = __vmins2(m, prmt(m, m, 0x1032));
+    if (NP & 1) mm = __vmins2(mm, P[NP - 1]);
+    mm = __vmins2(mm, prmt(mm, mm, 0x1032));
 #pragma unroll
-    for (int o = G / 2; o >= 1; o >>= 1) m = __vmins2(m, __shfl_xor_sync(0xffffffffu, m, o, G));
-    const uint32_t negm = __vadd2(~m, 0x00010001u);
-#pragma unroll
-    for (int k = 0; k < NP; k++) P[k] = __vadd2(L[k], negm);
+    for (int o = G / 2; o >= 1; o >>= 1) mm = __vmins2(mm, __shfl_xor_sync(0xffffffffu, mm, o, G));
+    m = mm;
 }
-
-// vertical (dirx = 0) and diagonal (dirx = +-1) chains, top-down (diry = +1) or bottom-up (-1).
-// Chain c visits x = (c + dirx*step) mod W1; on wrap-around it restarts from the zero border.
 template <int NP, int G>
 __global__ void __launch_bounds__(128) k_path_v(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int dirx,
                                                 int diry, int accumulate) {
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(128) k_path_v(Geom g, const int16_t* __restric
     int x = min(chain, g.W1 - 1);
     const int nrows = sg.src_end - sg.src_start;
     int y = diry > 0 ? sg.src_start : sg.src_end - 1;
-    uint32_t P[NP], c[NP], s[NP], L[NP], cn[NP], sn[NP];
+    uint32_t P[NP], c[NP], s[NP], L[NP], cn[NP], sn[NP], m = 0;
 #pragma unroll
     for (int k = 0; k < NP; k++) { P[k] = 0; sn[k] = 0; }
     const size_t lane_off = (size_t)lg * 2 * NP;
@@ -351,17 +352,16 @@ __global__ void __launch_bounds__(128) k_path_v(Geom g, const int16_t* __restric
             load_regs<NP>(Cb + ((size_t)(yn - sg.src_start) * g.W1 + xn) * D, cn);
             if (accumulate && yn >= sg.dst_start) load_regs<NP>(Sb + ((size_t)yn * g.W1 + xn) * D, sn);
         }
-        sgm_step<NP, G>(P, c, L, P1x2, P2x2, PADx2, lg);
+        sgm_step<NP, G>(P, m, c, P1x2, P2x2, PADx2, lg);
         if (active && y >= sg.dst_start) {
-            if (accumulate) {
 #pragma unroll
-                for (int k = 0; k < NP; k++) L[k] = __vminu2(__vadd2(s[k], L[k]), 0x7FFF7FFFu);
-            }
+            for (int k = 0; k < NP; k++) L[k] = accumulate ? __vminu2(__vadd2(s[k], P[k]), 0x7FFF7FFFu) : P[k];
             store_regs<NP>(Sb + ((size_t)y * g.W1 + x) * D, L);
         }
         if (wrap) {
 #pragma unroll
             for (int k = 0; k < NP; k++) P[k] = 0;
+            m = 0;
         }
         x = xn;
         y = yn;
@@ -397,107 +397,151 @@ __device__ __forceinline__ void halo_put(unsigned long long* p, uint32_t data, u
     const unsigned long long v = ((unsigned long long)seq << 32) | data;
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// All NP words of a lane are requested back to back (one L2 round trip, not NP), then re-polled until every sequence
-// number matches. Bounded: a broken neighbour protocol sets *err and lets every waiter fall through instead of
-// hanging the GPU.
-template <int NP>
-__device__ __forceinline__ void halo_get(const unsigned long long* p, uint32_t seq, int* err, uint32_t (&out)[NP]) {
+// Halo reads: all words of a lane are requested back to back (one L2 round trip), the sequence numbers are checked
+// later (halo_ready), and only a stale word triggers the bounded re-poll.
+template <int NW>
+__device__ __forceinline__ void halo_issue(const unsigned long long* p, unsigned long long (&v)[NW]) {
+#pragma unroll
+    for (int k = 0; k < NW; k++) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v[k]) : "l"(p + k) : "memory");
+}
+template <int NW>
+__device__ __forceinline__ void halo_complete(const unsigned long long* p, uint32_t seq, int* err, unsigned long long (&v)[NW]) {
     int spins = 0;
     while (true) {
-        unsigned long long v[NP];
-#pragma unroll
-        for (int k = 0; k < NP; k++) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v[k]) : "l"(p + k) : "memory");
         bool ok = true;
 #pragma unroll
-        for (int k = 0; k < NP; k++) {
-            ok = ok && (uint32_t)(v[k] >> 32) == seq;
-            out[k] = (uint32_t)v[k];
-        }
+        for (int k = 0; k < NW; k++) ok = ok && (uint32_t)(v[k] >> 32) == seq;
         if (ok) break;
         ++spins;
         if ((spins & 63) == 0 && *(volatile int*)err) break;
-        if (spins > V3_SPIN_LIMIT) { atomicExch(err, 1); break; }
+        if (spins > V3_SPIN_LIMIT) { atomicExch(err, 1); break; }   // never hang the GPU on a broken protocol
+        halo_issue<NW>(p, v);
     }
 }
 
-template <int NP, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int diry,
-                                                       int accumulate, int b0, unsigned long long* halo, int* err) {
-    constexpr int G = 8;
+template <int NP, int MINB, bool ACC>
+__global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int diry, int b0,
+                                                       unsigned long long* halo, int* err) {
+    constexpr int G = 8, NW = NP + 1;   // halo words per lane: NP state registers + the path minimum
     extern __shared__ __align__(16) int16_t v3sm[];
     const int D = g.D;
-    int16_t* Xa = v3sm;                              // [2][COLS+2][D]  state of the "from (x-1)" diagonal, slot = column+1
-    int16_t* Xb = v3sm + 2 * (V3_COLS + 2) * D;      // [2][COLS+2][D]  state of the "from (x+1)" diagonal
+    int16_t* Xa = v3sm;                                     // [2][COLS+2][D]  state of the "from (x-1)" diagonal, slot = column+1
+    int16_t* Xb = v3sm + 2 * (V3_COLS + 2) * D;             // [2][COLS+2][D]  state of the "from (x+1)" diagonal
+    uint32_t* Ma = (uint32_t*)(v3sm + 4 * (V3_COLS + 2) * D);   // [2][COLS+2] path minima of Xa
+    uint32_t* Mb = Ma + 2 * (V3_COLS + 2);
     const int s = blockIdx.x, nstrips = gridDim.x, f = blockIdx.y, b = b0 + f;
     const int gidx = threadIdx.x / G, lg = threadIdx.x & (G - 1);
     const int x = s * V3_COLS + gidx;
     const bool active = x < g.W1;
     const int xl = min(x, g.W1 - 1);
-    for (int i = threadIdx.x; i < 4 * (V3_COLS + 2) * D / 2; i += blockDim.x) ((uint32_t*)v3sm)[i] = 0;
+    for (int i = threadIdx.x; i < (4 * (V3_COLS + 2) * D) / 2 + 4 * (V3_COLS + 2); i += blockDim.x) ((uint32_t*)v3sm)[i] = 0;
     __syncthreads();
     const uint32_t P1x2 = pack16(g.P1, g.P1), P2x2 = pack16(g.P2, g.P2);
     const int pad = 32767 - g.P1;
     const uint32_t PADx2 = pack16(pad, pad);
     const size_t lane_off = (size_t)lg * 2 * NP;
-    // halo layout: [frame][strip][buf][a|b][G*NP] 64-bit words; (strip, a) = left halo OF that strip, (strip, b) = its right halo
-    const int HW = G * NP;
+    // halo layout: [frame][strip][buf][a|b][G*NW] 64-bit words; (strip, a) = left halo OF that strip, (strip, b) = its right halo
+    const int HW = G * NW;
     auto Hptr = [&](int strip, int buf, int which) {
-        return halo + ((((size_t)f * nstrips + strip) * 2 + buf) * 2 + which) * HW + (size_t)lg * NP;
+        return halo + ((((size_t)f * nstrips + strip) * 2 + buf) * 2 + which) * HW + (size_t)lg * NW;
     };
     const int16_t* Cb = C + (size_t)b * g.crows * g.W1 * D + (size_t)xl * D + lane_off;
     int16_t* Sb = S + (size_t)b * g.H * g.W1 * D + (size_t)xl * D + lane_off;
     const size_t rowstride = (size_t)g.W1 * D;
     const bool left_edge = gidx == 0 && s > 0, right_edge = gidx == V3_COLS - 1 && s + 1 < nstrips;
-    uint32_t Pv[NP], pa[NP], pb[NP], c[NP], cn[NP], cnn[NP], so[NP], sn[NP], L[NP], acc[NP];
+    uint32_t Pv[NP], pa[NP], pb[NP], c[NP], cn[NP], cnn[NP], so[ACC ? NP : 1], sn[ACC ? NP : 1], acc[NP];
+    uint32_t mv = 0, ma = 0, mb = 0;
+    unsigned long long hq[NW];   // prefetched halo of the next row (edge groups only)
 #pragma unroll
-    for (int k = 0; k < NP; k++) { Pv[k] = 0; sn[k] = 0; cnn[k] = 0; }
+    for (int k = 0; k < NP; k++) { Pv[k] = 0; cnn[k] = 0; }
+    if constexpr (ACC) {
+#pragma unroll
+        for (int k = 0; k < NP; k++) sn[k] = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < NW; k++) hq[k] = 0;
     int y = diry > 0 ? 0 : g.H - 1;
     load_regs<NP>(Cb + (size_t)y * rowstride, cn);
     if (g.H > 1) load_regs<NP>(Cb + (size_t)(y + diry) * rowstride, cnn);
-    if (accumulate) load_regs<NP>(Sb + (size_t)y * rowstride, sn);
+    if constexpr (ACC) load_regs<NP>(Sb + (size_t)y * rowstride, sn);
     for (int t = 0; t < g.H; t++) {
         const int cur = t & 1, prv = cur ^ 1;
 #pragma unroll
-        for (int k = 0; k < NP; k++) { c[k] = cn[k]; cn[k] = cnn[k]; so[k] = sn[k]; }
+        for (int k = 0; k < NP; k++) { c[k] = cn[k]; cn[k] = cnn[k]; }
+        if constexpr (ACC) {
+#pragma unroll
+            for (int k = 0; k < NP; k++) so[k] = sn[k];
+        }
         if (t + 2 < g.H) load_regs<NP>(Cb + (size_t)(y + 2 * diry) * rowstride, cnn);   // C two rows ahead
-        if (accumulate && t + 1 < g.H) load_regs<NP>(Sb + (size_t)(y + diry) * rowstride, sn);
-        // previous-row diagonal states: from the neighbouring column through shared memory, across strips through the halo
+        if constexpr (ACC) {
+            if (t + 1 < g.H) load_regs<NP>(Sb + (size_t)(y + diry) * rowstride, sn);
+        }
+        // previous-row diagonal states: neighbouring column through shared memory, across strips from the prefetched halo
         if (left_edge && t > 0) {
-            halo_get<NP>(Hptr(s, prv, 0), (uint32_t)t, err, pa);
+#pragma unroll
+            for (int k = 0; k < NP; k++) pa[k] = (uint32_t)hq[k];
+            ma = (uint32_t)hq[NP];
         } else {
             load_regs<NP>(Xa + ((size_t)prv * (V3_COLS + 2) + gidx) * D + lane_off, pa);
+            ma = Ma[prv * (V3_COLS + 2) + gidx];
         }
         if (right_edge && t > 0) {
-            halo_get<NP>(Hptr(s, prv, 1), (uint32_t)t, err, pb);
+#pragma unroll
+            for (int k = 0; k < NP; k++) pb[k] = (uint32_t)hq[k];
+            mb = (uint32_t)hq[NP];
         } else {
             load_regs<NP>(Xb + ((size_t)prv * (V3_COLS + 2) + gidx + 2) * D + lane_off, pb);
+            mb = Mb[prv * (V3_COLS + 2) + gidx + 2];
         }
         __syncwarp();
-        sgm_step<NP, G>(pa, c, L, P1x2, P2x2, PADx2, lg);
+        sgm_step<NP, G>(pa, ma, c, P1x2, P2x2, PADx2, lg);
+        if (!active) {
+#pragma unroll
+            for (int k = 0; k < NP; k++) pa[k] = 0;   // columns beyond W1 act as the zero border
+            ma = 0;
+        }
         if (right_edge) {   // publish first: the right neighbour needs this for its next row
             unsigned long long* hp = Hptr(s + 1, cur, 0);
 #pragma unroll
             for (int k = 0; k < NP; k++) halo_put(hp + k, pa[k], (uint32_t)(t + 1));
+            halo_put(hp + NP, ma, (uint32_t)(t + 1));
         }
-        sgm_step<NP, G>(pb, c, acc, P1x2, P2x2, PADx2, lg);
+        store_regs<NP>(Xa + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D + lane_off, pa);
+        if (lg == 0) Ma[cur * (V3_COLS + 2) + gidx + 1] = ma;
+        sgm_step<NP, G>(pb, mb, c, P1x2, P2x2, PADx2, lg);
+        if (!active) {
+#pragma unroll
+            for (int k = 0; k < NP; k++) pb[k] = 0;
+            mb = 0;
+        }
         if (left_edge) {
             unsigned long long* hp = Hptr(s - 1, cur, 1);
 #pragma unroll
             for (int k = 0; k < NP; k++) halo_put(hp + k, pb[k], (uint32_t)(t + 1));
+            halo_put(hp + NP, mb, (uint32_t)(t + 1));
         }
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < NP; k++) acc[k] = __vminu2(__vadd2(acc[k], L[k]), 0x7FFF7FFFu);
-        sgm_step<NP, G>(Pv, c, L, P1x2, P2x2, PADx2, lg);
-#pragma unroll
-        for (int k = 0; k < NP; k++) acc[k] = __vminu2(__vadd2(__vminu2(__vadd2(acc[k], L[k]), 0x7FFF7FFFu), so[k]), 0x7FFF7FFFu);
-        if (active) store_regs<NP>(Sb + (size_t)y * rowstride, acc);
-        if (!active) {
-#pragma unroll
-            for (int k = 0; k < NP; k++) { pa[k] = 0; pb[k] = 0; }
-        }
-        store_regs<NP>(Xa + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D + lane_off, pa);
         store_regs<NP>(Xb + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D + lane_off, pb);
+        if (lg == 0) Mb[cur * (V3_COLS + 2) + gidx + 1] = mb;
+        // request the neighbour's state of THIS row now (it publishes early in its row); it is consumed next row, so the
+        // L2 round trip overlaps the vertical path below
+        if (t + 1 < g.H) {
+            if (left_edge) halo_issue<NW>(Hptr(s, cur, 0), hq);
+            if (right_edge) halo_issue<NW>(Hptr(s, cur, 1), hq);
+        }
+#pragma unroll
+        for (int k = 0; k < NP; k++) acc[k] = __vminu2(__vadd2(pa[k], pb[k]), 0x7FFF7FFFu);
+        __syncwarp();
+        sgm_step<NP, G>(Pv, mv, c, P1x2, P2x2, PADx2, lg);
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            acc[k] = __vminu2(__vadd2(acc[k], Pv[k]), 0x7FFF7FFFu);
+            if constexpr (ACC) acc[k] = __vminu2(__vadd2(acc[k], so[k]), 0x7FFF7FFFu);
+        }
+        if (active) store_regs<NP>(Sb + (size_t)y * rowstride, acc);
+        if (t + 1 < g.H) {
+            if (left_edge) halo_complete<NW>(Hptr(s, cur, 0), (uint32_t)(t + 1), err, hq);
+            if (right_edge) halo_complete<NW>(Hptr(s, cur, 1), (uint32_t)(t + 1), err, hq);
+        }
         __syncthreads();
         y += diry;
     }
@@ -573,7 +617,7 @@ __global__ void __launch_bounds__(128) k_path_h(Geom g, const int16_t* __restric
     const uint32_t P1x2 = pack16(g.P1, g.P1), P2x2 = pack16(g.P2, g.P2);
     const int pad = 32767 - g.P1;
     const uint32_t PADx2 = pack16(pad, pad);
-    uint32_t P[NP], c[NP], s[NP], L[NP], cn[NP], sn[NP];
+    uint32_t P[NP], c[NP], s[NP], L[NP], cn[NP], sn[NP], m = 0;
 #pragma unroll
     for (int k = 0; k < NP; k++) { P[k] = 0; sn[k] = 0; }
     const size_t lane_off = (size_t)lg * 2 * NP;
@@ -591,11 +635,9 @@ __global__ void __launch_bounds__(128) k_path_h(Geom g, const int16_t* __restric
             load_regs<NP>(Cb + (size_t)xn * D, cn);
             if (accumulate) load_regs<NP>(Sb + (size_t)xn * D, sn);
         }
-        sgm_step<NP, G>(P, c, L, P1x2, P2x2, PADx2, lg);
-        if (accumulate) {
+        sgm_step<NP, G>(P, m, c, P1x2, P2x2, PADx2, lg);
 #pragma unroll
-            for (int k = 0; k < NP; k++) L[k] = __vminu2(__vadd2(s[k], L[k]), 0x7FFF7FFFu);
-        }
+        for (int k = 0; k < NP; k++) L[k] = accumulate ? __vminu2(__vadd2(s[k], P[k]), 0x7FFF7FFFu) : P[k];
         if constexpr (WTA) {
             int dv;
             uint32_t wv;
@@ -701,9 +743,9 @@ struct V3Scratch {
 template <int NP>
 int launch_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int16_t* S, int diry, int acc, V3Scratch& sc) {
     constexpr int MINB = NP <= 8 ? 2 : 1;
-    auto kern = k_path_v3<NP, MINB>;
+    auto kern = acc ? k_path_v3<NP, MINB, true> : k_path_v3<NP, MINB, false>;
     const int nstrips = div_up(g.W1, V3_COLS);
-    const size_t smem = (size_t)4 * (V3_COLS + 2) * g.D * sizeof(int16_t);
+    const size_t smem = (size_t)4 * (V3_COLS + 2) * g.D * sizeof(int16_t) + (size_t)4 * (V3_COLS + 2) * sizeof(uint32_t);
     if (smem > ctx->smem_optin) return -1;
     SDR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -712,7 +754,7 @@ int launch_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int
     if (cap < nstrips) return -1;
     const int fpl = std::min(batch, cap / nstrips);
     int rc;
-    const size_t halo_bytes = (size_t)nstrips * 4 * 8 * NP * sizeof(unsigned long long);   // per frame
+    const size_t halo_bytes = (size_t)nstrips * 4 * 8 * (NP + 1) * sizeof(unsigned long long);   // per frame
     if ((rc = sc.halo.reserve(ctx, halo_bytes * fpl))) return rc;
     if (!sc.err.p) {
         if ((rc = sc.err.reserve(ctx, sizeof(int)))) return rc;
@@ -726,7 +768,7 @@ int launch_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int
         Geom gg = g;
         unsigned long long* halo = sc.halo.as<unsigned long long>();
         int* err = sc.err.as<int>();
-        void* args[] = {(void*)&gg, (void*)&C, (void*)&S, (void*)&diry, (void*)&acc, (void*)&b0, (void*)&halo, (void*)&err};
+        void* args[] = {(void*)&gg, (void*)&C, (void*)&S, (void*)&diry, (void*)&b0, (void*)&halo, (void*)&err};
         SDR_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3(nstrips, F, 1), dim3(256, 1, 1), args, smem, ctx->stream));
         ctx->launches++;
     }
