@@ -344,7 +344,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (frame pool %d MB, a different batch each step; volumes %d MB per step)" % (
                            n_pool * H * 2 * W * 3 >> 20, 2 * vol * B >> 20),
                        "sgbm": list(SGBM_ARGS), "leaf_mm": LEAF_MM, "z_max_mm": Z_MAX_MM, "sharding": "frame i -> rank i mod N, no collective",
-                       "concurrency": "2 pipeline handles / streams / host threads per GPU alternate batches (value and e2e alike), so the copies and the ALU-bound kernels of one batch overlap the HBM-bound kernels of the other"},
+                       "concurrency": "several (--slots) pipeline handles / streams / host threads per GPU alternate batches (value and e2e alike), so the copies and the ALU-bound kernels of one batch overlap the HBM-bound kernels of the other"},
             "e2e": {"value": fps_e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
@@ -371,7 +371,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8, help="frames per step per GPU")
     ap.add_argument("--pool", type=int, default=32, help="distinct frames resident per GPU (pool > L2)")
-    ap.add_argument("--slots", type=int, default=2, help="pipeline handles (streams + host threads) per GPU")
+    ap.add_argument("--slots", type=int, default=4, help="pipeline handles (streams + host threads) per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
