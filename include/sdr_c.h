@@ -120,6 +120,20 @@ SDR_API int sdr_sgbm_compute(sdr_sgbm* m, const sdr_image* left, const sdr_image
 /* n independent pairs of one size in one submission (frame-parallel batch; frames share no state). */
 SDR_API int sdr_sgbm_compute_batch(sdr_sgbm* m, int n, const sdr_image* lefts, const sdr_image* rights,
                                    sdr_image* disps);
+/* Row-strip split of one oversize frame (BASELINE config 5). MODE_SGBM_3WAY is four independent stripes by construction
+ * (OpenCV's computeDisparity3WaySGBM: stripe i reads source rows [src_start, row_end) and owns output rows
+ * [dst_start, row_end)); other modes are a single stripe. Each GPU matches its stripes from the input rows it needs,
+ * the raw strips are gathered, and the median / speckle post-filters run once over the assembled image.
+ * sdr_sgbm_stripe_rows returns the number of stripes for this size (and one stripe's rows); it needs no device. */
+SDR_API int sdr_sgbm_stripe_rows(const sdr_sgbm_params* params, int width, int height, int stripe, int* src_start, int* dst_start,
+                                 int* row_end);
+/* Raw matcher output (before median / speckle) of stripes [first, first + n): only their output rows of `raw`
+ * (int16, full image size) are written. left/right are the full images. */
+SDR_API int sdr_sgbm_match_stripes(sdr_sgbm* m, const sdr_image* left, const sdr_image* right, int first_stripe, int n_stripes,
+                                   sdr_image* raw);
+/* medianBlur(3) + filterSpeckles with the handle's parameters on an assembled raw map. */
+SDR_API int sdr_sgbm_postfilter(sdr_sgbm* m, const sdr_image* raw, sdr_image* disp);
+
 /* Per-kernel device times (ms) of the last compute, measured with CUDA events on the ctx stream.
  * Enable first; names[i] point to static strings. Returns the number of stages written (<= cap). */
 SDR_API int sdr_sgbm_set_profiling(sdr_sgbm* m, int enabled);

@@ -75,6 +75,7 @@ SYMBOLS = [
     "sdr_remap_with_maps", "sdr_bgr2gray",
     "sdr_sgbm_create", "sdr_sgbm_destroy", "sdr_sgbm_compute", "sdr_sgbm_compute_batch",
     "sdr_sgbm_set_profiling", "sdr_sgbm_stage_times", "sdr_sgbm_debug_read",
+    "sdr_sgbm_stripe_rows", "sdr_sgbm_match_stripes", "sdr_sgbm_postfilter",
     "sdr_median3_16s", "sdr_filter_speckles", "sdr_reproject_to_3d",
     "sdr_cloud_create", "sdr_cloud_destroy", "sdr_voxelgrid", "sdr_depth_cloud", "sdr_cloud_download",
     "sdr_pipeline_create", "sdr_pipeline_destroy", "sdr_pipeline_run", "sdr_pipeline_stage_times",
@@ -114,6 +115,17 @@ def make_params(minDisparity=0, numDisparities=128, blockSize=5, P1=600, P2=2400
     """Same positional order as cv::StereoSGBM::create (stereo_disparity.cpp:5-6)."""
     return SgbmParams(minDisparity, numDisparities, blockSize, P1, P2, disp12MaxDiff, preFilterCap,
                       uniquenessRatio, speckleWindowSize, speckleRange, mode)
+
+
+def stripe_rows(params, width, height):
+    """[(src_start, dst_start, row_end)] of the independent stripes StereoSGBM splits this image into (4 for 3-way)."""
+    n = lib().sdr_sgbm_stripe_rows(C.byref(params), int(width), int(height), -1, None, None, None)
+    out = []
+    for i in range(n):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        lib().sdr_sgbm_stripe_rows(C.byref(params), int(width), int(height), i, C.byref(a), C.byref(b), C.byref(c))
+        out.append((a.value, b.value, c.value))
+    return out
 
 
 def _is_torch(a):
@@ -230,6 +242,19 @@ class Sgbm:
         O = (Image * n)(*[as_image(outs[i], 1)[0] for i in range(n)])
         self.ctx.check(lib().sdr_sgbm_compute_batch(self._h, n, L, R, O))
         return outs
+
+    def match_stripes(self, left, right, first, count, raw):
+        """Raw matcher output of stripes [first, first+count) into the rows they own of `raw` (int16, full size)."""
+        li, _ = as_image(left, 1); ri, _ = as_image(right, 1); oi, _ = as_image(raw, 1)
+        self.ctx.check(lib().sdr_sgbm_match_stripes(self._h, C.byref(li), C.byref(ri), int(first), int(count), C.byref(oi)))
+        return raw
+
+    def postfilter(self, raw, out=None):
+        if out is None:
+            out = _empty_like_kind(raw, tuple(raw.shape), np.int16, "int16")
+        ri, _ = as_image(raw, 1); oi, _ = as_image(out, 1)
+        self.ctx.check(lib().sdr_sgbm_postfilter(self._h, C.byref(ri), C.byref(oi)))
+        return out
 
     def set_profiling(self, on=True):
         lib().sdr_sgbm_set_profiling(self._h, int(on))

@@ -606,13 +606,18 @@ __global__ void __launch_bounds__(128) k_path_h(Geom g, const int16_t* __restric
     __shared__ __align__(16) int16_t smS[WTA ? CPB * 2 * NP * G : 8];
     const int lane = threadIdx.x & 31, lg = lane & (G - 1);
     const int row = blockIdx.x * CPB + threadIdx.x / G;
-    const bool active = row < g.H;
-    const int y = min(row, g.H - 1);
+    bool active = row < g.H;
+    int y = min(row, g.H - 1);
     const int b = blockIdx.z;
     const int D = g.D;
-    int si = 0;
+    int si = -1;
     for (int i = 0; i < g.nseg; i++)
         if (y >= g.seg[i].dst_start && y < g.seg[i].src_end) si = i;
+    if (si < 0) {   // row outside the selected stripes: run on a valid row, write nothing
+        si = 0;
+        y = g.seg[0].dst_start;
+        active = false;
+    }
     const Seg sg = g.seg[si];
     const uint32_t P1x2 = pack16(g.P1, g.P1), P2x2 = pack16(g.P2, g.P2);
     const int pad = 32767 - g.P1;
@@ -657,9 +662,9 @@ __global__ void __launch_bounds__(128) k_path_h(Geom g, const int16_t* __restric
 // with atomicMin on (cost << 16 | 0xFFFF - x): smallest cost wins, ties go to the largest x,
 // which is what OpenCV's descending-x "disp2cost[x2] > minS" scan produces.
 __global__ void __launch_bounds__(256) k_lrcheck(Geom g, const int16_t* __restrict__ dispraw, const uint32_t* __restrict__ wta,
-                                                 int16_t* __restrict__ out, size_t opitch, size_t oframe) {
+                                                 int16_t* __restrict__ out, size_t opitch, size_t oframe, int y0) {
     extern __shared__ uint32_t keys[];
-    const int y = blockIdx.x, b = blockIdx.z;
+    const int y = y0 + blockIdx.x, b = blockIdx.z;
     const int INV = (g.minD - 1) * 16;
     for (int x = threadIdx.x; x < g.W; x += blockDim.x) keys[x] = 0xFFFFFFFFu;
     __syncthreads();
@@ -809,6 +814,9 @@ struct sdr_sgbm {
     SpeckleScratch speckle;
     V3Scratch v3;
     bool use_fused_sweep = true;
+    int stripe_first = 0, stripe_count = -1;   // MODE_SGBM_3WAY: subset of the four stripes to match (-1 = all)
+    bool skip_post = false;                    // stop after the raw matcher output (median / speckle run elsewhere)
+    DevBuf post_in;
     StageTimer timer;
     Geom g{};
     int last_batch = 0;
@@ -851,7 +859,7 @@ extern "C" void sdr_sgbm_destroy(sdr_sgbm* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
     for (DevBuf* b : {&m->inL, &m->inR, &m->PL, &m->PR, &m->C, &m->S, &m->dispraw, &m->wta, &m->matched, &m->out,
-                      &m->speckle.parent, &m->speckle.count, &m->v3.halo, &m->v3.err})
+                      &m->speckle.parent, &m->speckle.count, &m->v3.halo, &m->v3.err, &m->post_in})
         b->release();
     m->v3.host_err.release();
     m->timer.release();
@@ -903,6 +911,19 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
     sdr_ctx* ctx = m->ctx;
     Geom& g = m->g;
     make_geom(m->p, W, H, g);
+    if (m->stripe_count >= 0) {   // keep only the selected stripes; C rows are renumbered from 0
+        const int first = std::min(m->stripe_first, g.nseg), last = std::min(first + m->stripe_count, g.nseg);
+        if (first >= last) return SDR_FAIL(ctx, SDR_EINVAL, "stripe range [%d, %d) is empty (the image has %d stripes)", m->stripe_first,
+                                           m->stripe_first + m->stripe_count, g.nseg);
+        int crow = 0, k = 0;
+        for (int i = first; i < last; i++, k++) {
+            g.seg[k] = g.seg[i];
+            g.seg[k].crow0 = crow;
+            crow += g.seg[k].src_end - g.seg[k].src_start;
+        }
+        g.nseg = k;
+        g.crows = crow;
+    }
     m->last_batch = batch;
     cudaStream_t st = ctx->stream;
     m->timer.begin(st);
@@ -991,11 +1012,13 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
         NP_SWITCH(np, rc = launch_path_h<NPc>(ctx, g, batch, C, S, -1, 1, true, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>()));
         if (rc) return rc;
         m->timer.mark(st, "path_h_bwd_wta");
-        k_lrcheck<<<dim3(H, 1, batch), 256, (size_t)W * sizeof(uint32_t), st>>>(g, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>(),
-                                                                                  m->matched.as<int16_t>(), (size_t)W * 2, img16);
+        const int ry0 = g.seg[0].dst_start, ry1 = g.seg[g.nseg - 1].src_end;   // output rows of the selected stripes
+        k_lrcheck<<<dim3(ry1 - ry0, 1, batch), 256, (size_t)W * sizeof(uint32_t), st>>>(g, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>(),
+                                                                                          m->matched.as<int16_t>(), (size_t)W * 2, img16, ry0);
         SDR_LAUNCHED(ctx);
         m->timer.mark(st, "lrcheck");
     }
+    if (m->skip_post) return SDR_OK;
     if ((rc = sdr_launch_median3(ctx, m->matched.as<int16_t>(), (size_t)W * 2, out, opitch, W, H, batch, img16, oframe))) return rc;
     m->timer.mark(st, "median3");
     if (m->p.speckleWindowSize > 0) {
@@ -1082,6 +1105,64 @@ extern "C" int sdr_sgbm_compute_batch(sdr_sgbm* m, int n, const sdr_image* lefts
 
 extern "C" int sdr_sgbm_compute(sdr_sgbm* m, const sdr_image* left, const sdr_image* right, sdr_image* disp) {
     return sdr_sgbm_compute_batch(m, 1, left, right, disp);
+}
+
+extern "C" int sdr_sgbm_stripe_rows(const sdr_sgbm_params* params, int width, int height, int stripe, int* src_start, int* dst_start,
+                                    int* row_end) {
+    if (!params || width <= 0 || height <= 0) return -1;
+    Geom g{};
+    make_geom(*params, width, height, g);
+    if (stripe >= 0 && stripe < g.nseg) {
+        if (src_start) *src_start = g.seg[stripe].src_start;
+        if (dst_start) *dst_start = g.seg[stripe].dst_start;
+        if (row_end) *row_end = g.seg[stripe].src_end;
+    }
+    return g.nseg;
+}
+
+extern "C" int sdr_sgbm_match_stripes(sdr_sgbm* m, const sdr_image* left, const sdr_image* right, int first_stripe, int n_stripes,
+                                      sdr_image* raw) {
+    if (!m || !left || !right || !raw || first_stripe < 0 || n_stripes <= 0) return SDR_EINVAL;
+    sdr_ctx* ctx = m->ctx;
+    SDR_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = sdr_check_image(ctx, left, 1, 1, "left")) || (rc = sdr_check_image(ctx, right, 1, 1, "right")) ||
+        (rc = sdr_check_image(ctx, raw, 1, 2, "raw")))
+        return rc;
+    const int W = left->cols, H = left->rows;
+    if (right->cols != W || right->rows != H || raw->cols != W || raw->rows != H) return SDR_FAIL(ctx, SDR_ESIZE, "match_stripes: sizes differ");
+    DevView vl, vr;
+    if ((rc = sdr_stage_in(ctx, left, m->inL, &vl)) || (rc = sdr_stage_in(ctx, right, m->inR, &vr))) return rc;
+    m->stripe_first = first_stripe;
+    m->stripe_count = n_stripes;
+    m->skip_post = true;
+    rc = sgbm_run(m, 1, vl.p, vl.pitch, 0, vr.p, vr.pitch, 0, W, H, nullptr, 0, 0);
+    m->stripe_count = -1;
+    m->skip_post = false;
+    if (rc) return rc;
+    const int y0 = m->g.seg[0].dst_start, y1 = m->g.seg[m->g.nseg - 1].src_end;
+    SDR_CUDA(ctx, cudaMemcpy2DAsync((uint8_t*)raw->data + (size_t)y0 * raw->step_bytes, raw->step_bytes, m->matched.as<int16_t>() + (size_t)y0 * W,
+                                    (size_t)W * 2, (size_t)W * 2, y1 - y0, cudaMemcpyDefault, ctx->stream));
+    if (raw->mem != SDR_MEM_DEVICE) SDR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SDR_OK;
+}
+
+extern "C" int sdr_sgbm_postfilter(sdr_sgbm* m, const sdr_image* raw, sdr_image* disp) {
+    if (!m || !raw || !disp) return SDR_EINVAL;
+    sdr_ctx* ctx = m->ctx;
+    SDR_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = sdr_check_image(ctx, raw, 1, 2, "raw")) || (rc = sdr_check_image(ctx, disp, 1, 2, "disp"))) return rc;
+    const int W = raw->cols, H = raw->rows;
+    if (disp->cols != W || disp->rows != H) return SDR_FAIL(ctx, SDR_ESIZE, "postfilter: sizes differ");
+    DevView vi, vo;
+    if ((rc = sdr_stage_in(ctx, raw, m->post_in, &vi)) || (rc = sdr_stage_out_begin(ctx, disp, m->out, &vo))) return rc;
+    if ((rc = sdr_launch_median3(ctx, (const int16_t*)vi.p, vi.pitch, (int16_t*)vo.p, vo.pitch, W, H, 1, 0, 0))) return rc;
+    if (m->p.speckleWindowSize > 0 &&
+        (rc = sdr_launch_speckle(ctx, (int16_t*)vo.p, vo.pitch, W, H, 1, 0, (m->p.minDisparity - 1) * 16, m->p.speckleWindowSize,
+                                 16 * m->p.speckleRange, m->speckle)))
+        return rc;
+    return sdr_stage_out_end(ctx, disp, vo);
 }
 
 extern "C" int sdr_sgbm_set_profiling(sdr_sgbm* m, int enabled) {

@@ -1,0 +1,113 @@
+"""GPU: row-strip split of one frame (BASELINE config 5). Stripes are matched separately, gathered, post-filtered once;
+the result must equal the single-call result bit for bit."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_stripe_geometry_matches_opencv_rule():
+    from stereo_depth_ruler_b200 import capi
+    p = capi.make_params(0, 256, 5, 600, 2400, 1, 63, 12, 200, 2, capi.MODE_SGBM_3WAY)
+    rows = capi.stripe_rows(p, 3840, 2160)
+    # stripe i reads source rows [max(i*540-57, 0), (i+1)*540) and writes rows [i*540, (i+1)*540)
+    assert rows == [(0, 0, 540), (483, 540, 1080), (1023, 1080, 1620), (1563, 1620, 2160)]
+    assert capi.stripe_rows(capi.make_params(mode=capi.MODE_SGBM), 1280, 720) == [(0, 0, 720)]
+
+
+def test_stripes_on_separate_handles_equal_single_call(ctx, orc):
+    """Four handles (stand-ins for four GPUs) match one stripe each into one raw map."""
+    import torch
+    from stereo_depth_ruler_b200 import capi, synth
+    W, H, D = 640, 203, 64          # 203 rows: uneven last stripe
+    args = (0, D, 5, 600, 2400, 1, 63, 12, 100, 2, capi.MODE_SGBM_3WAY)
+    l, r = synth.stereo_pair(W, H, D, 4)
+    lt, rt = torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda()
+    whole = capi.Sgbm(ctx, capi.make_params(*args))
+    ref = whole.compute(l, r)
+    assert np.array_equal(ref, orc.sgbm_compute(l, r, orc.make_params(*args)))
+    raw = torch.full((H, W), -1234, dtype=torch.int16, device="cuda")
+    stripes = capi.stripe_rows(whole.params, W, H)
+    assert len(stripes) == 4
+    for i in range(4):
+        h = capi.Sgbm(ctx, capi.make_params(*args))
+        h.match_stripes(lt, rt, i, 1, raw)
+        ctx.synchronize()
+        got = raw.cpu().numpy()
+        assert (got[stripes[i][2]:] == -1234).all()          # rows of later stripes untouched
+        h.close()
+    assert np.array_equal(raw.cpu().numpy(), whole.debug_read(2, (H, W)))
+    out = whole.postfilter(raw)
+    ctx.synchronize()                 # device outputs are asynchronous on the handle's stream
+    assert np.array_equal(out.cpu().numpy(), ref)
+    # two stripes per call (the 2-GPU split)
+    raw2 = torch.empty_like(raw)
+    whole.match_stripes(lt, rt, 0, 2, raw2); whole.match_stripes(lt, rt, 2, 2, raw2)
+    out2 = whole.postfilter(raw2)
+    ctx.synchronize()
+    assert np.array_equal(out2.cpu().numpy(), ref)
+    with pytest.raises(capi.SdrError):
+        whole.match_stripes(lt, rt, 4, 1, raw2)
+    whole.close()
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    try:
+        _worker_body(rank, world, port, q)
+    except Exception as e:  # noqa: BLE001 -- report instead of leaving the parent waiting on the queue
+        if rank == 0:
+            q.put("rank 0 failed: %r" % (e,))
+        raise
+
+
+def _worker_body(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from stereo_depth_ruler_b200 import capi, synth, strip_split
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    W, H, D = 3840, 2160, 256
+    args = (0, D, 5, 600, 2400, 1, 63, 12, 200, 2, capi.MODE_SGBM_3WAY)
+    l, r = synth.stereo_pair(W, H, D, 6)
+    ctx = capi.Context(rank)
+    m = capi.Sgbm(ctx, capi.make_params(*args))
+    lt, rt = torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda()
+    out = strip_split.compute(m, lt, rt, rank, world, dist)
+    if rank == 0:
+        ref = m.compute(l, r)
+        q.put(bool(np.array_equal(out.cpu().numpy(), ref)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_strip_split_across_gpus_4k():
+    """config 5 (3840x2160, D=256, 3-way) split over every GPU of the box (needs >= 2)."""
+    import torch
+    import torch.multiprocessing as mp
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 4 if n >= 4 else 2
+    mpctx = mp.get_context("spawn")
+    q = mpctx.Queue()
+    port = _free_port()
+    procs = [mpctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        if p.is_alive():
+            p.kill()
+    assert ok is True, ok
