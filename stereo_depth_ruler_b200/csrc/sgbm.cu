@@ -27,8 +27,12 @@ struct Geom {
     int nseg, crows;
     Seg seg[4];
     int SW2, SH2, P1, P2, ftzero, uq, d12, three_way;
-    int Wp;  // padded width of the right-image byte planes
+    int Wp;  // padded width of the right-image byte planes (multiple of 16); PR = [b][y][Wp/16][24 plane-copies][16 B]
 };
+
+// One 16-byte chunk of the reversed right-image planes: 24 plane-copies x 16 B, padded to 400 B so that consecutive
+// chunks start 4 banks apart in shared memory (the cost kernel reads the same byte offset of 8 consecutive chunks).
+constexpr int PR_CHUNK = 400;
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 __device__ __forceinline__ uint32_t dup_lo(uint32_t a) { return __byte_perm(a, a, 0x1010); }
@@ -97,7 +101,7 @@ __global__ void __launch_bounds__(128) k_prefilter(Geom g, const uint8_t* left, 
         o.w = (int)pack16(-hi[1], lo[1] - 255);
         PL[((size_t)b * g.H + y) * g.W + x] = o;
     } else {
-        uint8_t* row = PR + ((size_t)b * g.H + y) * 24 * g.Wp;
+        uint8_t* row = PR + ((size_t)b * g.H + y) * (g.Wp >> 4) * PR_CHUNK;   // chunk (i/16): 16 bytes of each of the 24 plane-copies
         const int j = g.W - 1 - x;
 #pragma unroll
         for (int ch = 0; ch < 2; ch++) {
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(128) k_prefilter(Geom g, const uint8_t* left, 
 #pragma unroll
                 for (int sft = 0; sft < 4; sft++) {
                     int i = j - sft;
-                    if (i >= 0) row[((ch * 3 + pl) * 4 + sft) * g.Wp + i] = val[pl];
+                    if (i >= 0) row[(size_t)(i >> 4) * PR_CHUNK + ((ch * 3 + pl) * 4 + sft) * 16 + (i & 15)] = val[pl];
                 }
         }
     }
@@ -121,21 +125,47 @@ __global__ void __launch_bounds__(128) k_prefilter(Geom g, const uint8_t* left, 
 constexpr int COST_TXH = 64;   // columns per CTA including the 2*SW2 halo
 constexpr int COST_RB = 90;    // output rows per CTA (2*SH2 warm-up rows are recomputed per band)
 
-// BT cost of 8 consecutive disparities at one pixel (both channels) -> two u8x4 words.
-__device__ __forceinline__ void bt_item(const Geom& g, const int4* __restrict__ PLrow, const uint8_t* __restrict__ PRrow,
-                                        int ximg, int proff, uint32_t& out0, uint32_t& out1) {
-    const int4 k = __ldg(PLrow + ximg);
+// ---- TMA (bulk async copy) + mbarrier helpers: one elected thread moves a row tile global -> shared, the CTA waits on
+// the barrier's transaction count ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SDR_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SDR_MBAR_DONE;\n"
+        "bra SDR_MBAR_WAIT;\n"
+        "SDR_MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// BT cost of 8 consecutive disparities at one pixel (both channels) -> two u8x4 words. pl: the pixel's packed left
+// constants; pr: staged right-image chunks (16 B of each of the 24 plane-copies per chunk); o0 / o1: byte offsets of the
+// two aligned words inside the stage for plane 0, copy a (plane p adds 64 p).
+__device__ __forceinline__ void bt_item(const int4 k, const uint8_t* __restrict__ pr, int o0, int o1, uint32_t& out0, uint32_t& out1) {
     uint32_t acc[4];
 #pragma unroll
     for (int ch = 0; ch < 2; ch++) {
         const uint32_t kx = ch ? (uint32_t)k.z : (uint32_t)k.x, ky = ch ? (uint32_t)k.w : (uint32_t)k.y;
         const uint32_t negU = dup_lo(kx), Um = dup_hi(kx), negU1 = dup_lo(ky), U0m = dup_hi(ky);
-        const uint8_t* pv = PRrow + (ch * 3 + 0) * 4 * g.Wp + proff;
-        const uint8_t* pl = PRrow + (ch * 3 + 1) * 4 * g.Wp + proff;
-        const uint8_t* ph = PRrow + (ch * 3 + 2) * 4 * g.Wp + proff;
-        const uint32_t wv[2] = {__ldg((const uint32_t*)pv), __ldg((const uint32_t*)pv + 1)};
-        const uint32_t wl[2] = {__ldg((const uint32_t*)pl), __ldg((const uint32_t*)pl + 1)};
-        const uint32_t wh[2] = {__ldg((const uint32_t*)ph), __ldg((const uint32_t*)ph + 1)};
+        const int pv = (ch * 3 + 0) * 64, pl = (ch * 3 + 1) * 64, ph = (ch * 3 + 2) * 64;
+        const uint32_t wv[2] = {*(const uint32_t*)(pr + o0 + pv), *(const uint32_t*)(pr + o1 + pv)};
+        const uint32_t wl[2] = {*(const uint32_t*)(pr + o0 + pl), *(const uint32_t*)(pr + o1 + pl)};
+        const uint32_t wh[2] = {*(const uint32_t*)(pr + o0 + ph), *(const uint32_t*)(pr + o1 + ph)};
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const uint32_t sel = (i & 1) ? 0x4342u : 0x4140u;
@@ -155,18 +185,20 @@ __device__ __forceinline__ void bt_item(const Geom& g, const int4* __restrict__ 
     out1 = prmt(acc[2], acc[3], 0x6420);
 }
 
+constexpr int COST_STAGES = 2;
+
 // blockDim.x is a multiple of DQ = D/8: thread = (q, xg); it owns ITEMS columns xh = xg + k*XG of the 64-column tile for
 // the whole band, keeps their running vertical sums in registers and their last 2*SH2+1 pixel-cost rows in a
-// thread-private shared-memory ring (no synchronisation needed for it). One __syncthreads per output row (Vs is
-// double-buffered) separates the vertical and the horizontal box sums.
+// thread-private shared-memory ring (no synchronisation needed for it). The prefiltered image rows are staged in
+// shared memory by TMA bulk copies (two per row: the left constants and the right byte planes of the tile), two rows
+// ahead, completion signalled on an mbarrier.
 template <int ITEMS>
 __global__ void __launch_bounds__(256) k_cost(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ PR,
                                               int16_t* __restrict__ C) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full[COST_STAGES];
     const int D = g.D, DQ = D >> 3;
     const int n = 2 * g.SH2 + 1, TX = COST_TXH - 2 * g.SW2;
-    uint8_t* ring = smem;                                              // [n][64][D] u8
-    uint16_t* Vs = (uint16_t*)(smem + (size_t)n * COST_TXH * D);       // [2][64][D] u16
     const int b = blockIdx.z;
     int band = blockIdx.y, si = 0;
     for (; si < g.nseg; si++) {
@@ -179,53 +211,84 @@ __global__ void __launch_bounds__(256) k_cost(Geom g, const int4* __restrict__ P
     const int ya = sg.src_start + band * COST_RB, yb = min(ya + COST_RB, sg.src_end);
     const int ymin = sg.src_start, ymax = g.H - 1;
     const int x0 = blockIdx.x * TX;
+    // tile geometry (uniform): cost-space columns [lo, hi), staged right-image chunks [cs, cs + nchunks)
+    const int lo = max(x0 - g.SW2, 0), hi = min(x0 - g.SW2 + COST_TXH, g.W1);
+    const int j0_min = (g.W - 1 - (hi - 1 + g.minX1)) + g.minD, j0_max = (g.W - 1 - (lo + g.minX1)) + g.minD + 8 * (DQ - 1);
+    const int cs = max(j0_min - 3, 0) >> 4, nchunks = ((j0_max + 7) >> 4) - cs + 1;
+    const uint32_t pl_bytes = (uint32_t)(hi - lo) * 16, pr_bytes = (uint32_t)nchunks * PR_CHUNK;
+    const size_t stage_bytes = (size_t)COST_TXH * 16 + (size_t)((COST_TXH + D + 32) / 16 + 1) * PR_CHUNK;   // as sized by the host
+    uint8_t* stage = smem;                                                      // [STAGES][PL 64 x 16 B | PR chunks]
+    uint8_t* ring = smem + COST_STAGES * stage_bytes;                           // [n][64][D] u8
+    uint16_t* Vs = (uint16_t*)(ring + (size_t)n * COST_TXH * D);                // [64][D] u16
     const int q = threadIdx.x % DQ, xg = threadIdx.x / DQ, XG = blockDim.x / DQ;
-    int ximg[ITEMS], proff[ITEMS];
+    int ix[ITEMS], o0[ITEMS], o1[ITEMS];
     uint32_t V[ITEMS][4];
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
         const int xh = xg + k * XG;
         const int xc = min(max(x0 - g.SW2 + xh, 0), g.W1 - 1);
-        ximg[k] = xc + g.minX1;
-        const int j0 = (g.W - 1 - ximg[k]) + g.minD + 8 * q;
-        const int a = j0 & 3;
-        proff[k] = a * g.Wp + (j0 - a);
+        ix[k] = min(max(xc - lo, 0), COST_TXH - 1);
+        const int j0 = (g.W - 1 - (xc + g.minX1)) + g.minD + 8 * q;
+        const int a = j0 & 3, p0 = j0 - a, p1 = p0 + 4;
+        o0[k] = ((p0 >> 4) - cs) * PR_CHUNK + (p0 & 15) + a * 16;
+        o1[k] = ((p1 >> 4) - cs) * PR_CHUNK + (p1 & 15) + a * 16;
         V[k][0] = V[k][1] = V[k][2] = V[k][3] = 0;
         if (xh < COST_TXH)
             for (int s = 0; s < n; s++) *(uint2*)(ring + ((size_t)s * COST_TXH + xh) * D + 8 * q) = make_uint2(0, 0);
     }
+    const int kv0 = ya - g.SH2, NV = (yb - 1 + g.SH2) - kv0 + 1;
+    auto issue = [&](int i) {   // one thread: stage virtual row i
+        const int rc = min(max(kv0 + i, ymin), ymax);
+        uint8_t* st = stage + (size_t)(i % COST_STAGES) * stage_bytes;
+        uint64_t* bar = &full[i % COST_STAGES];
+        mbar_expect_tx(bar, pl_bytes + pr_bytes);
+        bulk_g2s(st, PL + ((size_t)b * g.H + rc) * g.W + lo + g.minX1, pl_bytes, bar);
+        bulk_g2s(st + COST_TXH * 16, PR + (((size_t)b * g.H + rc) * (g.Wp >> 4) + cs) * PR_CHUNK, pr_bytes, bar);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < COST_STAGES; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int i = 0; i < COST_STAGES && i < NV; i++) issue(i);
     int slot = 0;
-    for (int kv = ya - g.SH2; kv <= yb - 1 + g.SH2; kv++) {
-        const int rc = min(max(kv, ymin), ymax);
-        const int4* PLrow = PL + ((size_t)b * g.H + rc) * g.W;
-        const uint8_t* PRrow = PR + ((size_t)b * g.H + rc) * 24 * g.Wp;
+    for (int i = 0; i < NV; i++) {
+        const int kv = kv0 + i;
+        const uint8_t* st = stage + (size_t)(i % COST_STAGES) * stage_bytes;
+        mbar_wait(&full[i % COST_STAGES], (uint32_t)((i / COST_STAGES) & 1));
+        const int4* pls = (const int4*)st;
+        const uint8_t* prs = st + COST_TXH * 16;
 #pragma unroll
         for (int k = 0; k < ITEMS; k++) {
             const int xh = xg + k * XG;
             if (xh < COST_TXH) {
                 uint32_t n0, n1;
-                bt_item(g, PLrow, PRrow, ximg[k], proff[k], n0, n1);
+                bt_item(pls[ix[k]], prs, o0[k], o1[k], n0, n1);
                 uint2* rp = (uint2*)(ring + ((size_t)slot * COST_TXH + xh) * D + 8 * q);
                 const uint2 old = *rp;
                 *rp = make_uint2(n0, n1);
-                const uint32_t o0 = ~old.x, o1 = ~old.y;   // 255 - old per byte
+                const uint32_t c0 = ~old.x, c1 = ~old.y;   // 255 - old per byte
                 // V += new - old  ==  V + new + (255 - old) - 255 per 16-bit half
-                V[k][0] = __vadd2(__vadd2(__vadd2(V[k][0], prmt(n0, 0, 0x4140)), prmt(o0, 0, 0x4140)), 0xFF01FF01u);
-                V[k][1] = __vadd2(__vadd2(__vadd2(V[k][1], prmt(n0, 0, 0x4342)), prmt(o0, 0, 0x4342)), 0xFF01FF01u);
-                V[k][2] = __vadd2(__vadd2(__vadd2(V[k][2], prmt(n1, 0, 0x4140)), prmt(o1, 0, 0x4140)), 0xFF01FF01u);
-                V[k][3] = __vadd2(__vadd2(__vadd2(V[k][3], prmt(n1, 0, 0x4342)), prmt(o1, 0, 0x4342)), 0xFF01FF01u);
+                V[k][0] = __vadd2(__vadd2(__vadd2(V[k][0], prmt(n0, 0, 0x4140)), prmt(c0, 0, 0x4140)), 0xFF01FF01u);
+                V[k][1] = __vadd2(__vadd2(__vadd2(V[k][1], prmt(n0, 0, 0x4342)), prmt(c0, 0, 0x4342)), 0xFF01FF01u);
+                V[k][2] = __vadd2(__vadd2(__vadd2(V[k][2], prmt(n1, 0, 0x4140)), prmt(c1, 0, 0x4140)), 0xFF01FF01u);
+                V[k][3] = __vadd2(__vadd2(__vadd2(V[k][3], prmt(n1, 0, 0x4342)), prmt(c1, 0, 0x4342)), 0xFF01FF01u);
             }
         }
         slot = slot + 1 == n ? 0 : slot + 1;
         const int y = kv - g.SH2;
-        if (y >= ya) {   // uniform across the CTA
-            uint16_t* Vb = Vs + (size_t)(y & 1) * COST_TXH * D;
+        const bool out_row = y >= ya;   // uniform across the CTA
+        if (out_row) {
 #pragma unroll
             for (int k = 0; k < ITEMS; k++) {
                 const int xh = xg + k * XG;
-                if (xh < COST_TXH) *(uint4*)(Vb + (size_t)xh * D + 8 * q) = make_uint4(V[k][0], V[k][1], V[k][2], V[k][3]);
+                if (xh < COST_TXH) *(uint4*)(Vs + (size_t)xh * D + 8 * q) = make_uint4(V[k][0], V[k][1], V[k][2], V[k][3]);
             }
-            __syncthreads();
+        }
+        __syncthreads();   // every thread is done with this stage (and Vs is complete)
+        if (threadIdx.x == 0 && i + COST_STAGES < NV) issue(i + COST_STAGES);
+        if (out_row) {
             int16_t* Crow = C + ((size_t)b * g.crows + sg.crow0 + (y - sg.src_start)) * g.W1 * D;
 #pragma unroll
             for (int k = 0; k < ITEMS; k++) {
@@ -233,7 +296,7 @@ __global__ void __launch_bounds__(256) k_cost(Geom g, const int4* __restrict__ P
                 if (xl < TX && x0 + xl < g.W1) {
                     uint4 acc = make_uint4(0, 0, 0, 0);
                     for (int j = 0; j <= 2 * g.SW2; j++) {
-                        const uint4 w = *(const uint4*)(Vb + (size_t)(xl + j) * D + 8 * q);
+                        const uint4 w = *(const uint4*)(Vs + (size_t)(xl + j) * D + 8 * q);
                         acc.x = __vadd2(acc.x, w.x);
                         acc.y = __vadd2(acc.y, w.y);
                         acc.z = __vadd2(acc.z, w.z);
@@ -242,6 +305,7 @@ __global__ void __launch_bounds__(256) k_cost(Geom g, const int4* __restrict__ P
                     *(uint4*)(Crow + (size_t)(x0 + xl) * D + 8 * q) = acc;
                 }
             }
+            __syncthreads();   // Vs is single-buffered
         }
     }
 }
@@ -878,7 +942,7 @@ static void make_geom(const sdr_sgbm_params& p, int W, int H, Geom& g) {
     g.P2 = std::max(p.P2 > 0 ? p.P2 : 5, g.P1 + 1);
     g.ftzero = std::max(p.preFilterCap, 15) | 1;
     g.three_way = p.mode == SDR_MODE_SGBM_3WAY;
-    g.Wp = ((W + 3) & ~3) + 8;
+    g.Wp = ((W + 15) & ~15) + 16;
     if (g.three_way) {
         g.SW2 = g.SH2 = p.blockSize > 0 ? p.blockSize / 2 : 1;
         const int nstripes = 4;
@@ -945,7 +1009,7 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
     {
         const size_t vol = (size_t)g.W1 * g.D * sizeof(int16_t);
         if ((rc = m->PL.reserve(ctx, (size_t)batch * H * W * sizeof(int4)))) return rc;
-        if ((rc = m->PR.reserve(ctx, (size_t)batch * H * 24 * g.Wp))) return rc;
+        if ((rc = m->PR.reserve(ctx, (size_t)batch * H * (g.Wp >> 4) * PR_CHUNK))) return rc;
         if ((rc = m->C.reserve(ctx, vol * g.crows * batch))) return rc;
         if ((rc = m->S.reserve(ctx, vol * H * batch))) return rc;
         if ((rc = m->dispraw.reserve(ctx, img16 * batch))) return rc;
@@ -958,7 +1022,8 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
             const int n = 2 * g.SH2 + 1, DQ = g.D / 8;
             const int nthr = (256 / DQ) * DQ, XG = nthr / DQ;
             const int items = div_up(COST_TXH, XG);
-            const size_t smem = (size_t)n * COST_TXH * g.D + (size_t)2 * COST_TXH * g.D * 2;
+            const size_t stage_bytes = (size_t)COST_TXH * 16 + (size_t)((COST_TXH + g.D + 32) / 16 + 1) * PR_CHUNK;
+            const size_t smem = COST_STAGES * stage_bytes + (size_t)n * COST_TXH * g.D + (size_t)COST_TXH * g.D * 2;
             if (smem > ctx->smem_optin) return SDR_FAIL(ctx, SDR_EINVAL, "cost kernel needs %zu B shared memory", smem);
             int bands = 0;
             for (int i = 0; i < g.nseg; i++) bands += div_up(g.seg[i].src_end - g.seg[i].src_start, COST_RB);
