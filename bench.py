@@ -297,9 +297,13 @@ def run_ours(args):
     vol = W1 * H * D * 2                                   # bytes of one int16 volume per frame
     img = W * H
     # algorithmic bytes per frame of each SGBM kernel (DESIGN.md "Kernels"): distinct bytes it must read + write
-    algo = {"prefilter": 2 * img + (16 + 24) * img, "cost": (16 + 24) * img + vol, "path_v0": 2 * vol, "path_v1": 3 * vol,
-            "path_v2": 3 * vol, "path_h_fwd": 3 * vol, "path_h_bwd_wta": 2 * vol + 6 * img, "lrcheck": 8 * img,
-            "median3": 4 * img, "speckle": 24 * img}
+    algo = {"prefilter": 2 * img + (16 + 25) * img, "cost": (16 + 25) * img + vol, "path_v_fused_down": 2 * vol,
+            "path_v_fused_up": 3 * vol, "path_v0": 2 * vol, "path_v1": 3 * vol, "path_v2": 3 * vol, "path_h_fwd": 3 * vol,
+            "path_h_bwd_wta": 2 * vol + 6 * img, "lrcheck": 8 * img, "median3": 4 * img, "speckle": 24 * img}
+    # DRAM bytes per launch at 8 frames per launch from the committed `ncu --set full` capture of this build
+    # (profiles/r1_ncu_sgbm_kernels.txt: dram__bytes_read.sum + dram__bytes_write.sum); scaled to the batch in use.
+    ncu_traffic_b8 = {"cost": 0.314489e9 + 1.645265e9, "path_v_fused_down": 1.699039e9 + 1.656339e9,
+                      "path_h_fwd": 3.397397e9 + 1.658580e9, "path_h_bwd_wta": 3.397726e9 + 0.043919e9}
     dom = max(acc, key=acc.get)
     peaks = {}
     try:
@@ -311,7 +315,9 @@ def run_ours(args):
     sgbm_ms = sum(acc.values())
     core_bytes = (2 * vol + 4 * img) * B                   # compulsory 3.69 MB + one int16 volume round trip per frame
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
+                "traffic": (ncu_traffic_b8[dom] * B / 8.0) if dom in ncu_traffic_b8 else None,
+                "traffic_source": "profiles/r1_ncu_sgbm_kernels.txt (ncu --set full, per launch at 8 frames, scaled to this batch)",
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
                 "algorithmic_bytes_per_launch": algo.get(dom, 2 * vol) * B, "kernel_ms": acc[dom],
                 "kernel_share_of_sgbm": acc[dom] / sgbm_ms,
                 "sgbm_core": {"achieved": core_bytes / (sgbm_ms * 1e-3) / 1e9, "frac": core_bytes / (sgbm_ms * 1e-3) / 1e9 / peak,
