@@ -185,6 +185,23 @@ SDR_API int sdr_depth_cloud(sdr_cloud* c, const sdr_image* disp16, const sdr_ima
 /* Copy the last cloud to host buffers (any may be NULL). */
 SDR_API int sdr_cloud_download(sdr_cloud* c, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt);
 
+/* ---- consumers of the depth image: tiny reductions done on the device so the 11 MB point image
+ *      does not have to travel back ---- */
+/* StereoDisplayer::onMouseMeasure (stereo_displayer.cpp:41-47): distance between the reprojected pixels (x1,y1), (x2,y2)
+ * = cv::norm(xyz1 - xyz2): float differences, squares summed in double. points: f32 3-ch. Same units as the cloud (mm;
+ * the reference prints dist/10 as cm). Out-of-range clicks return SDR_EINVAL (the reference ignores them, :33). */
+SDR_API int sdr_measure_distance(sdr_ctx* ctx, const sdr_image* points, int x1, int y1, int x2, int y2, double* dist);
+/* StereoDisplayer::depth_coverage (stereo_displayer.cpp:105-118): pixels with column >= first_col (the reference hard-codes
+ * 80), 0 <= Z <= z_max (12000) and Z not NaN; coverage_percent = count / (rows*cols) * 100. */
+SDR_API int sdr_depth_coverage(sdr_ctx* ctx, const sdr_image* points, int first_col, float z_min, float z_max, int64_t* count,
+                               double* coverage_percent);
+/* pcl::io::savePCDFileBinary(path, cloud) for the last cloud of `c` (pcd_write.cpp:134-142): PCD v0.7 header
+ * (FIELDS x y z rgb / SIZE 4 4 4 4 / TYPE F F F U / COUNT 1 1 1 1 / WIDTH n / HEIGHT 1 / VIEWPOINT 0 0 0 1 0 0 0 /
+ * POINTS n / DATA binary) + packed 16-byte records, rgb = 0xFF<<24 | r<<16 | g<<8 | b. The header is restated from PCL's
+ * pcd_io as recalled (no PCL and no sample file here): PARITY UNPINNED. Returns SDR_EINVAL for an empty cloud
+ * (the reference prints "No points to save" and returns, :143-146). */
+SDR_API int sdr_cloud_save_pcd_binary(sdr_cloud* c, int frame, const char* path);
+
 /* ---- whole path per frame (stereo_displayer.cpp:155-162 + pcd_write.cpp:82-130) ---- */
 typedef struct sdr_pipeline_options {
     sdr_sgbm_params sgbm;

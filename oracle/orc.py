@@ -38,6 +38,8 @@ def lib():
         build()
         _lib = C.CDLL(_LIB)
         _lib.orc_voxelgrid.restype = C.c_long
+        _lib.orc_measure_distance.restype = C.c_double
+        _lib.orc_depth_coverage.restype = C.c_double
     return _lib
 
 
@@ -161,3 +163,15 @@ def voxelgrid(points, bgr, leaf, drop_mask=None):
     assert nv >= 0
     return dict(xyz=xyz[:nv].copy(), rgb=rgb[:nv].copy(), idx=idx[:nv].copy(), cnt=cnt[:nv].copy(),
                 minb=mb[:3].copy(), divb=mb[3:].copy())
+
+
+def measure_distance(points, p1, p2):
+    pts = np.ascontiguousarray(points, np.float32)
+    return lib().orc_measure_distance(_p(pts), pts.shape[1], int(p1[0]), int(p1[1]), int(p2[0]), int(p2[1]))
+
+
+def depth_coverage(points):
+    pts = np.ascontiguousarray(points, np.float32)
+    n = C.c_long()
+    pct = lib().orc_depth_coverage(_p(pts), pts.shape[1], pts.shape[0], C.byref(n))
+    return n.value, pct

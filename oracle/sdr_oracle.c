@@ -703,3 +703,31 @@ ORC_API long orc_voxelgrid(const float* points, const uint8_t* bgr, const uint8_
     free(keys);
     return nv;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Consumers of the depth image that live in the reference's own sources:      */
+/*   onMouseMeasure  stereo_vision/src/stereo_displayer.cpp:41-47               */
+/*   depth_coverage  stereo_vision/src/stereo_displayer.cpp:105-118             */
+/* ------------------------------------------------------------------------- */
+ORC_API double orc_measure_distance(const float* points, int W, int x1, int y1, int x2, int y2) {
+    const float* a = points + ((size_t)y1 * W + x1) * 3;
+    const float* b = points + ((size_t)y2 * W + x2) * 3;
+    double s = 0;
+    for (int i = 0; i < 3; i++) {
+        float d = a[i] - b[i];            /* cv::Vec3f xyz1 - xyz2 */
+        s += (double)d * (double)d;       /* cv::norm: squares accumulated in double */
+    }
+    return sqrt(s);
+}
+
+ORC_API double orc_depth_coverage(const float* points, int W, int H, long* count_out) {
+    int counter = 0, num_dis = 80;
+    const int total_pixels = H * W;
+    for (int i = 0; i < H; ++i)
+        for (int j = num_dis; j < W; ++j) {
+            float z = points[((size_t)i * W + j) * 3 + 2];
+            if (z >= 0.0 && z <= 12000.0 && !isnan(z)) counter++;
+        }
+    if (count_out) *count_out = counter;
+    return ((double)counter / total_pixels) * 100;
+}

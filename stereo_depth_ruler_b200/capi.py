@@ -80,6 +80,7 @@ SYMBOLS = [
     "sdr_cloud_create", "sdr_cloud_destroy", "sdr_voxelgrid", "sdr_depth_cloud", "sdr_cloud_download",
     "sdr_pipeline_create", "sdr_pipeline_destroy", "sdr_pipeline_run", "sdr_pipeline_stage_times",
     "sdr_pipeline_cloud_download", "sdr_pipeline_set_profiling",
+    "sdr_measure_distance", "sdr_depth_coverage", "sdr_cloud_save_pcd_binary",
 ]
 
 _lib = None
@@ -376,6 +377,22 @@ def reproject_to_3d(ctx, disp, Q, handle_missing=False):
     return out
 
 
+def measure_distance(ctx, points, p1, p2):
+    """Distance between two reprojected pixels p = (x, y), as the reference's mouse ruler (stereo_displayer.cpp:41-47)."""
+    pi, _ = as_image(points, 3)
+    out = C.c_double()
+    ctx.check(lib().sdr_measure_distance(ctx._h, C.byref(pi), int(p1[0]), int(p1[1]), int(p2[0]), int(p2[1]), C.byref(out)))
+    return out.value
+
+
+def depth_coverage(ctx, points, first_col=80, z_min=0.0, z_max=12000.0):
+    """(count, percent) of StereoDisplayer::depth_coverage (stereo_displayer.cpp:105-118)."""
+    pi, _ = as_image(points, 3)
+    n, pct = C.c_int64(), C.c_double()
+    ctx.check(lib().sdr_depth_coverage(ctx._h, C.byref(pi), int(first_col), C.c_float(z_min), C.c_float(z_max), C.byref(n), C.byref(pct)))
+    return n.value, pct.value
+
+
 def voxel_options(leaf, drop_invalid=False, z_max=0.0, min_disparity=0):
     leaf = (leaf,) * 3 if np.isscalar(leaf) else tuple(leaf)
     return VoxelOptions((C.c_float * 3)(*leaf), int(bool(drop_invalid)), float(z_max), int(min_disparity))
@@ -410,6 +427,9 @@ class Cloud:
                                  C.byref(opt), C.byref(self.view))
         self.ctx.check(rc, ok=(SDR_OK, SDR_EVOXEL_OVERFLOW))
         return self._download() if download else self.view
+
+    def save_pcd_binary(self, path, frame=0):
+        self.ctx.check(lib().sdr_cloud_save_pcd_binary(self._h, int(frame), str(path).encode()))
 
     def depth_cloud(self, disp16, bgr, Q, opt, handle_missing=False, download=True):
         di, _ = as_image(disp16, 1)

@@ -225,6 +225,24 @@ __global__ void __launch_bounds__(256) k_reproject(const uint8_t* __restrict__ d
     orow[2] = o[2];
 }
 
+__global__ void __launch_bounds__(256) k_coverage(const uint8_t* __restrict__ pts, size_t step, int W, int H, int first_col, float zmin, float zmax,
+                                                  unsigned long long* count) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    unsigned ok = 0;
+    if (x < W && x >= first_col) {
+        const float z = ((const float*)(pts + (size_t)y * step))[(size_t)x * 3 + 2];
+        ok = (z >= zmin && z <= zmax && !(z != z)) ? 1u : 0u;
+    }
+    const unsigned n = __popc(__ballot_sync(0xffffffffu, ok));
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(count, (unsigned long long)n);
+}
+
+__global__ void k_pick2(const uint8_t* __restrict__ pts, size_t step, int x1, int y1, int x2, int y2, float* out) {
+    const int i = threadIdx.x;
+    if (i < 3) out[i] = ((const float*)(pts + (size_t)y1 * step))[(size_t)x1 * 3 + i];
+    else if (i < 6) out[i] = ((const float*)(pts + (size_t)y2 * step))[(size_t)x2 * 3 + i - 3];
+}
+
 // cv::invert(DECOMP_LU) of a 3x3 (partial pivoting), fp64, on the host
 bool invert3(const double* m, double* inv) {
     double a[3][6];
@@ -483,4 +501,62 @@ extern "C" int sdr_reproject_to_3d(sdr_ctx* ctx, const sdr_image* disp, const do
     cudaStreamSynchronize(ctx->stream);
     bin.release(); bout.release(); bmin.release();
     return rc;
+}
+
+extern "C" int sdr_measure_distance(sdr_ctx* ctx, const sdr_image* points, int x1, int y1, int x2, int y2, double* dist) {
+    if (!ctx || !points || !dist) return SDR_EINVAL;
+    SDR_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = sdr_check_image(ctx, points, 3, 4, "points"))) return rc;
+    if (x1 < 0 || x1 >= points->cols || y1 < 0 || y1 >= points->rows || x2 < 0 || x2 >= points->cols || y2 < 0 || y2 >= points->rows)
+        return SDR_FAIL(ctx, SDR_EINVAL, "measure_distance: point outside the image");
+    float v[6];
+    if (points->mem == SDR_MEM_DEVICE) {
+        DevBuf tmp;
+        if ((rc = tmp.reserve(ctx, 64))) return rc;
+        k_pick2<<<1, 32, 0, ctx->stream>>>((const uint8_t*)points->data, points->step_bytes, x1, y1, x2, y2, tmp.as<float>());
+        ctx->launches++;
+        cudaError_t e = cudaMemcpyAsync(v, tmp.p, sizeof v, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        tmp.release();
+        if (e != cudaSuccess) return SDR_FAIL(ctx, SDR_ECUDA, "measure_distance: %s", cudaGetErrorString(e));
+    } else {
+        const float* a = (const float*)((const uint8_t*)points->data + (size_t)y1 * points->step_bytes) + (size_t)x1 * 3;
+        const float* b = (const float*)((const uint8_t*)points->data + (size_t)y2 * points->step_bytes) + (size_t)x2 * 3;
+        for (int i = 0; i < 3; i++) { v[i] = a[i]; v[3 + i] = b[i]; }
+    }
+    double s = 0;
+    for (int i = 0; i < 3; i++) {
+        const float d = v[i] - v[3 + i];   // Vec3f subtraction
+        s += (double)d * (double)d;        // cv::norm accumulates squares in double
+    }
+    *dist = std::sqrt(s);
+    return SDR_OK;
+}
+
+extern "C" int sdr_depth_coverage(sdr_ctx* ctx, const sdr_image* points, int first_col, float z_min, float z_max, int64_t* count,
+                                  double* coverage_percent) {
+    if (!ctx || !points) return SDR_EINVAL;
+    SDR_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = sdr_check_image(ctx, points, 3, 4, "points"))) return rc;
+    DevBuf bin, bcnt;
+    DevView vi;
+    unsigned long long n = 0;
+    rc = bcnt.reserve(ctx, 64);
+    if (rc == SDR_OK) rc = sdr_stage_in(ctx, points, bin, &vi);
+    if (rc == SDR_OK) {
+        cudaMemsetAsync(bcnt.p, 0, 8, ctx->stream);
+        k_coverage<<<dim3(div_up(points->cols, 256), points->rows), 256, 0, ctx->stream>>>(vi.p, vi.pitch, points->cols, points->rows, first_col, z_min,
+                                                                                           z_max, bcnt.as<unsigned long long>());
+        ctx->launches++;
+        cudaError_t e = cudaMemcpyAsync(&n, bcnt.p, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = SDR_FAIL(ctx, SDR_ECUDA, "depth_coverage: %s", cudaGetErrorString(e));
+    }
+    bin.release(); bcnt.release();
+    if (rc) return rc;
+    if (count) *count = (int64_t)n;
+    if (coverage_percent) *coverage_percent = ((double)n / ((double)points->rows * points->cols)) * 100;
+    return SDR_OK;
 }

@@ -672,3 +672,31 @@ extern "C" int sdr_cloud_download(sdr_cloud* c, float* xyz, uint8_t* rgb, uint32
     SDR_CUDA(c->ctx, cudaSetDevice(c->ctx->device));
     return sdr_cloud_download_frame(c, 0, xyz, rgb, idx, cnt);
 }
+
+extern "C" int sdr_cloud_save_pcd_binary(sdr_cloud* c, int frame, const char* path) {
+    if (!c || !path) return SDR_EINVAL;
+    sdr_ctx* ctx = c->ctx;
+    SDR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (frame < 0 || frame >= c->frames || frame >= (int)c->last_n.size()) return SDR_FAIL(ctx, SDR_EINVAL, "save_pcd: no such frame %d", frame);
+    const size_t n = (size_t)c->last_n[frame];
+    if (n == 0) return SDR_FAIL(ctx, SDR_EINVAL, "No points to save after downsampling!");   // pcd_write.cpp:143-146
+    std::vector<float> xyz(n * 3);
+    std::vector<uint8_t> rgb(n * 3);
+    int rc = sdr_cloud_download_frame(c, frame, xyz.data(), rgb.data(), nullptr, nullptr);
+    if (rc) return rc;
+    const bool organised = c->last_passthrough[frame] != 0;
+    const size_t width = organised ? (size_t)c->W : n, height = organised ? (size_t)c->H : 1;
+    FILE* f = fopen(path, "wb");
+    if (!f) return SDR_FAIL(ctx, SDR_EIO, "save_pcd: cannot open %s", path);
+    fprintf(f, "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z rgb\nSIZE 4 4 4 4\nTYPE F F F U\nCOUNT 1 1 1 1\n"
+               "WIDTH %zu\nHEIGHT %zu\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %zu\nDATA binary\n", width, height, n);
+    std::vector<uint8_t> rec(n * 16);
+    for (size_t i = 0; i < n; i++) {
+        memcpy(&rec[i * 16], &xyz[i * 3], 12);
+        const uint32_t packed = 0xFF000000u | ((uint32_t)rgb[i * 3] << 16) | ((uint32_t)rgb[i * 3 + 1] << 8) | (uint32_t)rgb[i * 3 + 2];
+        memcpy(&rec[i * 16 + 12], &packed, 4);
+    }
+    const bool ok = fwrite(rec.data(), 1, rec.size(), f) == rec.size();
+    fclose(f);
+    return ok ? SDR_OK : SDR_FAIL(ctx, SDR_EIO, "save_pcd: short write to %s", path);
+}

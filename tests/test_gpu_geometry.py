@@ -183,3 +183,52 @@ def test_voxelgrid_full_size_properties(ctx, orc, golden):
     ref = orc.voxelgrid(orc.reproject_to_3d(orc.disp_to_float(d16), golden["Q"], True), bgr, 5.0, drop_mask=(d16 < 0))
     _check_cloud(got, ref)
     cloud.close()
+
+
+def test_ruler_and_coverage_consumers(ctx, orc, golden):
+    """the mouse ruler (stereo_displayer.cpp:41-47) and depth_coverage (:105-118) on the device."""
+    import torch
+    from stereo_depth_ruler_b200 import capi
+    d16 = golden["reproj_disp16"]
+    pts = capi.reproject_to_3d(ctx, d16, golden["Q"], False)
+    H, W = d16.shape
+    assert capi.depth_coverage(ctx, pts) == orc.depth_coverage(pts)
+    assert capi.depth_coverage(ctx, pts)[0] > 0
+    rng = np.random.default_rng(2)
+    dev = torch.from_numpy(pts).cuda()
+    for _ in range(20):
+        (x1, x2), (y1, y2) = rng.integers(0, W, 2), rng.integers(0, H, 2)
+        ref = orc.measure_distance(pts, (x1, y1), (x2, y2))
+        for src in (pts, dev):
+            got = capi.measure_distance(ctx, src, (x1, y1), (x2, y2))
+            assert (np.isnan(ref) and np.isnan(got)) or got == ref
+    assert capi.depth_coverage(ctx, dev) == orc.depth_coverage(pts)
+    with pytest.raises(capi.SdrError):
+        capi.measure_distance(ctx, pts, (W, 0), (0, 0))      # the reference ignores clicks outside the image
+
+
+def test_pcd_binary_writer(ctx, orc, golden, tmp_path):
+    """savePCDFileBinary of the filtered cloud (header restated from PCL: parity unpinned)."""
+    from stereo_depth_ruler_b200 import capi
+    l, r, bgr = _scene(golden, 160, 96, 32)
+    d16 = orc.sgbm_compute(l, r, orc.make_params(0, 32, 5, 600, 2400, 1, 63, 12, 200, 2, 0))
+    cloud = capi.Cloud(ctx)
+    # D=32 at this baseline puts the scene beyond 5.7 m: a 50 mm leaf and a 60 m clip keep the int32 guard quiet
+    got = cloud.depth_cloud(d16, bgr, golden["Q"], capi.voxel_options(50.0, drop_invalid=True, z_max=60000.0), handle_missing=True)
+    assert not got["passthrough"] and len(got["idx"]) > 100
+    path = tmp_path / "frame_00100.pcd"
+    cloud.save_pcd_binary(path)
+    raw = path.read_bytes()
+    head, body = raw.split(b"DATA binary\n", 1)
+    n = len(got["idx"])
+    assert b"FIELDS x y z rgb\nSIZE 4 4 4 4\nTYPE F F F U\nCOUNT 1 1 1 1\n" in head
+    assert ("WIDTH %d\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\n" % (n, n)).encode() in head
+    rec = np.frombuffer(body, dtype=np.dtype([("xyz", "<f4", 3), ("rgb", "<u4")]))
+    assert len(rec) == n and np.array_equal(rec["xyz"], got["xyz"])
+    packed = (0xFF << 24) | (got["rgb"][:, 0].astype(np.uint32) << 16) | (got["rgb"][:, 1].astype(np.uint32) << 8) | got["rgb"][:, 2]
+    assert np.array_equal(rec["rgb"], packed)
+    empty = capi.Cloud(ctx)
+    empty.voxelgrid(np.full((4, 4, 3), np.nan, np.float32), None, capi.voxel_options(1.0))
+    with pytest.raises(capi.SdrError):
+        empty.save_pcd_binary(tmp_path / "none.pcd")
+    cloud.close(); empty.close()
