@@ -453,6 +453,7 @@ __device__ __forceinline__ void load_regs_cg(const int16_t* p, uint32_t (&r)[NP]
 }
 
 constexpr int V3_COLS = 32;
+constexpr int V3_STAGES_MAX = 6;   // rows of C in flight per CTA (TMA ring); 3 when S is staged too (keeps 2 CTAs/SM)
 constexpr int V3_SPIN_LIMIT = 1 << 22;
 
 // Halo words carry their own sequence number (row + 1) in the upper half of one 64-bit store, so no fence and no
@@ -487,12 +488,18 @@ template <int NP, int MINB, bool ACC>
 __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int diry, int b0,
                                                        unsigned long long* halo, int* err) {
     constexpr int G = 8, NW = NP + 1;   // halo words per lane: NP state registers + the path minimum
+    constexpr int V3_STAGES = ACC ? 3 : V3_STAGES_MAX;
     extern __shared__ __align__(16) int16_t v3sm[];
     const int D = g.D;
     int16_t* Xa = v3sm;                                     // [2][COLS+2][D]  state of the "from (x-1)" diagonal, slot = column+1
     int16_t* Xb = v3sm + 2 * (V3_COLS + 2) * D;             // [2][COLS+2][D]  state of the "from (x+1)" diagonal
     uint32_t* Ma = (uint32_t*)(v3sm + 4 * (V3_COLS + 2) * D);   // [2][COLS+2] path minima of Xa
     uint32_t* Mb = Ma + 2 * (V3_COLS + 2);
+    // ring of C (and, when accumulating, S) row tiles filled by TMA bulk copies V3_STAGES rows ahead: the strip's 32
+    // columns of one row are one contiguous 32*D*2-byte run in global memory
+    int16_t* ringC = (int16_t*)(Mb + 2 * (V3_COLS + 2));        // [STAGES][COLS][D]
+    int16_t* ringS = ringC + (size_t)V3_STAGES * V3_COLS * D;   // [STAGES][COLS][D] (ACC only)
+    __shared__ __align__(8) uint64_t full[V3_STAGES];
     const int s = blockIdx.x, nstrips = gridDim.x, f = blockIdx.y, b = b0 + f;
     const int gidx = threadIdx.x / G, lg = threadIdx.x & (G - 1);
     const int x = s * V3_COLS + gidx;
@@ -509,37 +516,41 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
     auto Hptr = [&](int strip, int buf, int which) {
         return halo + ((((size_t)f * nstrips + strip) * 2 + buf) * 2 + which) * HW + (size_t)lg * NW;
     };
-    const int16_t* Cb = C + (size_t)b * g.crows * g.W1 * D + (size_t)xl * D + lane_off;
     int16_t* Sb = S + (size_t)b * g.H * g.W1 * D + (size_t)xl * D + lane_off;
     const size_t rowstride = (size_t)g.W1 * D;
+    const int x0 = s * V3_COLS;
+    const uint32_t tile_bytes = (uint32_t)(min(V3_COLS, g.W1 - x0) * D * 2);
+    const int16_t* Ctile = C + (size_t)b * g.crows * g.W1 * D + (size_t)x0 * D;    // + row * rowstride
+    const int16_t* Stile = S + (size_t)b * g.H * g.W1 * D + (size_t)x0 * D;
+    const int ystart = diry > 0 ? 0 : g.H - 1;
+    auto issue = [&](int t) {   // one thread: stage row t of the sweep
+        const int yy = ystart + t * diry, st = t % V3_STAGES;
+        mbar_expect_tx(&full[st], ACC ? 2 * tile_bytes : tile_bytes);
+        bulk_g2s(ringC + (size_t)st * V3_COLS * D, Ctile + (size_t)yy * rowstride, tile_bytes, &full[st]);
+        if (ACC) bulk_g2s(ringS + (size_t)st * V3_COLS * D, Stile + (size_t)yy * rowstride, tile_bytes, &full[st]);
+    };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < V3_STAGES; i++) mbar_init(&full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int i = 0; i < V3_STAGES && i < g.H; i++) issue(i);
     const bool left_edge = gidx == 0 && s > 0, right_edge = gidx == V3_COLS - 1 && s + 1 < nstrips;
-    uint32_t Pv[NP], pa[NP], pb[NP], c[NP], cn[NP], cnn[NP], so[ACC ? NP : 1], sn[ACC ? NP : 1], acc[NP];
+    uint32_t Pv[NP], pa[NP], pb[NP], c[NP], so[ACC ? NP : 1], acc[NP];
     uint32_t mv = 0, ma = 0, mb = 0;
     unsigned long long hq[NW];   // prefetched halo of the next row (edge groups only)
 #pragma unroll
-    for (int k = 0; k < NP; k++) { Pv[k] = 0; cnn[k] = 0; }
-    if constexpr (ACC) {
-#pragma unroll
-        for (int k = 0; k < NP; k++) sn[k] = 0;
-    }
+    for (int k = 0; k < NP; k++) Pv[k] = 0;
 #pragma unroll
     for (int k = 0; k < NW; k++) hq[k] = 0;
-    int y = diry > 0 ? 0 : g.H - 1;
-    load_regs<NP>(Cb + (size_t)y * rowstride, cn);
-    if (g.H > 1) load_regs<NP>(Cb + (size_t)(y + diry) * rowstride, cnn);
-    if constexpr (ACC) load_regs<NP>(Sb + (size_t)y * rowstride, sn);
+    int y = ystart;
     for (int t = 0; t < g.H; t++) {
         const int cur = t & 1, prv = cur ^ 1;
-#pragma unroll
-        for (int k = 0; k < NP; k++) { c[k] = cn[k]; cn[k] = cnn[k]; }
-        if constexpr (ACC) {
-#pragma unroll
-            for (int k = 0; k < NP; k++) so[k] = sn[k];
-        }
-        if (t + 2 < g.H) load_regs<NP>(Cb + (size_t)(y + 2 * diry) * rowstride, cnn);   // C two rows ahead
-        if constexpr (ACC) {
-            if (t + 1 < g.H) load_regs<NP>(Sb + (size_t)(y + diry) * rowstride, sn);
-        }
+        const int stg = t % V3_STAGES;
+        mbar_wait(&full[stg], (uint32_t)((t / V3_STAGES) & 1));
+        load_regs<NP>(ringC + ((size_t)stg * V3_COLS + gidx) * D + lane_off, c);
+        if constexpr (ACC) load_regs<NP>(ringS + ((size_t)stg * V3_COLS + gidx) * D + lane_off, so);
         // previous-row diagonal states: neighbouring column through shared memory, across strips from the prefetched halo
         if (left_edge && t > 0) {
 #pragma unroll
@@ -606,7 +617,8 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
             if (left_edge) halo_complete<NW>(Hptr(s, cur, 0), (uint32_t)(t + 1), err, hq);
             if (right_edge) halo_complete<NW>(Hptr(s, cur, 1), (uint32_t)(t + 1), err, hq);
         }
-        __syncthreads();
+        __syncthreads();   // also: every thread is done with ring stage `stg`
+        if (threadIdx.x == 0 && t + V3_STAGES < g.H) issue(t + V3_STAGES);
         y += diry;
     }
 }
@@ -814,7 +826,8 @@ int launch_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int
     constexpr int MINB = NP <= 8 ? 2 : 1;
     auto kern = acc ? k_path_v3<NP, MINB, true> : k_path_v3<NP, MINB, false>;
     const int nstrips = div_up(g.W1, V3_COLS);
-    const size_t smem = (size_t)4 * (V3_COLS + 2) * g.D * sizeof(int16_t) + (size_t)4 * (V3_COLS + 2) * sizeof(uint32_t);
+    const size_t smem = (size_t)4 * (V3_COLS + 2) * g.D * sizeof(int16_t) + (size_t)4 * (V3_COLS + 2) * sizeof(uint32_t) +
+                        (size_t)(acc ? 2 * 3 : V3_STAGES_MAX) * V3_COLS * g.D * sizeof(int16_t);
     if (smem > ctx->smem_optin) return -1;
     SDR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
