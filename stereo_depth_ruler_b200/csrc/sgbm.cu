@@ -27,6 +27,7 @@ struct Geom {
     int nseg, crows;
     Seg seg[4];
     int SW2, SH2, P1, P2, ftzero, uq, d12, three_way;
+    uint32_t uq_magic;  // ceil(2^32 / (100 - uq)): exact n / (100 - uq) for n < 2^32 / 100 by one __umulhi
     int Wp;  // padded width of the right-image byte planes (multiple of 16); PR = [b][y][Wp/16][24 plane-copies][16 B]
 };
 
@@ -35,6 +36,13 @@ struct Geom {
 constexpr int PR_CHUNK = 400;
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+// prmt.b32 with the full 4-bit selectors (msb of a nibble = replicate the sign bit of the selected byte), which
+// __byte_perm does not expose
+__device__ __forceinline__ uint32_t prmt_full(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
 __device__ __forceinline__ uint32_t dup_lo(uint32_t a) { return __byte_perm(a, a, 0x1010); }
 __device__ __forceinline__ uint32_t dup_hi(uint32_t a) { return __byte_perm(a, a, 0x3232); }
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
@@ -628,29 +636,33 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
 template <int NP, int G>
 __device__ __forceinline__ void wta_pixel(const uint32_t (&Sr)[NP], int lg, const Geom& g, int16_t* sm, int& disp_out,
                                           uint32_t& wta_out) {
+    // first minimum: keys (S << 8 | d) built with one PRMT per half, reduced with 3-input minima
     uint32_t key = 0xFFFFFFFFu;
     const int d0 = lg * 2 * NP;
+    const uint32_t dw0 = (uint32_t)d0 | ((uint32_t)(d0 + 1) << 8);   // bytes: d of the low half, d of the high half, 0, 0
 #pragma unroll
     for (int k = 0; k < NP; k++) {
-        const uint32_t klo = ((Sr[k] & 0xFFFFu) << 8) | (uint32_t)(d0 + 2 * k);
-        const uint32_t khi = ((Sr[k] >> 16) << 8) | (uint32_t)(d0 + 2 * k + 1);
-        key = min(key, min(klo, khi));
+        const uint32_t dw = dw0 + 0x0202u * k;
+        key = __vimin3_u32(key, prmt(Sr[k], dw, 0x6104), prmt(Sr[k], dw, 0x6325));
     }
 #pragma unroll
     for (int o = G / 2; o >= 1; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o, G));
     const int minS = (int)(key >> 8), best = (int)(key & 0xFFu);
-    // S[d] < thr  <=>  the uniqueness predicate of the mode
+    // S[d] < thr  <=>  the uniqueness predicate of the mode; the division by 100 - uq is one
+    // multiply-high with a precomputed reciprocal (exact in this range)
     const int q = 100 - g.uq;
-    int thr = g.three_way ? (g.uq > 0 ? (100 * minS) / q + 1 : 0) : (minS * 100 + q - 1) / q;
+    const uint32_t num = g.three_way ? (uint32_t)(100 * minS) : (uint32_t)(minS * 100 + q - 1);
+    const int quot = q == 1 ? (int)num : (int)__umulhi(num, g.uq_magic);
+    int thr = g.three_way ? (g.uq > 0 ? quot + 1 : 0) : quot;
     thr = min(thr, 0x8000);
     const uint32_t cst = 0x80008000u - pack16(thr, thr);  // per half: 0x8000 - thr, no borrow
-    uint32_t cnt = 0;
+    uint32_t nge2 = 0;   // per half: minus the number of entries >= thr
 #pragma unroll
     for (int k = 0; k < NP; k++) {
-        const uint32_t t = Sr[k] + cst;  // bit15 / bit31 set <=> S >= thr
-        cnt += (~t >> 15) & 0x00010001u;
+        const uint32_t t = Sr[k] + cst;                     // bit15 / bit31 set <=> S >= thr
+        nge2 = __vadd2(nge2, prmt_full(t, t, 0xBB99));      // sign-replicating PRMT: 0xFFFF (= -1) per flagged half
     }
-    int nlt = (int)((cnt & 0xFFFFu) + (cnt >> 16));
+    int nlt = 2 * NP + (int)(int16_t)(nge2 & 0xFFFFu) + (int)(int16_t)(nge2 >> 16);
 #pragma unroll
     for (int o = G / 2; o >= 1; o >>= 1) nlt += __shfl_xor_sync(0xffffffffu, nlt, o, G);
     // neighbours of the minimum through shared memory
@@ -666,8 +678,18 @@ __device__ __forceinline__ void wta_pixel(const uint32_t (&Sr)[NP], int lg, cons
     }
     int d = best * 16;
     if (best > 0 && best < g.D - 1) {
-        const int denom2 = max(Sm + Sp - 2 * minS, 1);
-        d += ((Sm - Sp) * 16 + denom2) / (denom2 * 2);
+        // C truncating division ((Sm - Sp) * 16 + den) / (2 * den) by a float quotient plus an exact fix-up
+        const int den2 = 2 * max(Sm + Sp - 2 * minS, 1), numr = (Sm - Sp) * 16 + (den2 >> 1);
+        int qd = __float2int_rz(__fdividef((float)numr, (float)den2));
+        int rem = numr - qd * den2;
+        if (numr >= 0) {
+            if (rem < 0) qd--;
+            else if (rem >= den2) qd++;
+        } else {
+            if (rem > 0) qd++;
+            else if (rem <= -den2) qd--;
+        }
+        d += qd;
     }
     disp_out = d + g.minD * 16;
     wta_out = ((uint32_t)minS << 16) | (uint32_t)best;
@@ -955,6 +977,7 @@ static void make_geom(const sdr_sgbm_params& p, int W, int H, Geom& g) {
     g.P2 = std::max(p.P2 > 0 ? p.P2 : 5, g.P1 + 1);
     g.ftzero = std::max(p.preFilterCap, 15) | 1;
     g.three_way = p.mode == SDR_MODE_SGBM_3WAY;
+    g.uq_magic = (uint32_t)(((1ull << 32) + (uint64_t)(100 - g.uq) - 1) / (uint64_t)(100 - g.uq));   // unused when 100 - uq == 1
     g.Wp = ((W + 15) & ~15) + 16;
     if (g.three_way) {
         g.SW2 = g.SH2 = p.blockSize > 0 ? p.blockSize / 2 : 1;
