@@ -756,6 +756,101 @@ __global__ void __launch_bounds__(128) k_path_h(Geom g, const int16_t* __restric
     }
 }
 
+// Horizontal chains with a TMA-fed shared-memory ring (default): a warp owns 4 rows (8 lanes each); lane 0 of every row
+// group stages the next chunks of K steps of its row (K*D*2 contiguous bytes of C, and of S) with bulk async copies,
+// H_STAGES chunks deep, completion on a per-warp mbarrier. That keeps ~16 KB per warp in flight instead of the 2 KB a
+// one-step register prefetch gives, which is what the single-chain-per-row parallelism needs to reach HBM speed.
+constexpr int H_STAGES = 3;
+
+template <int NP, bool WTA>
+__global__ void __launch_bounds__(128) k_path_h2(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int dir, int accumulate,
+                                                 int K, int16_t* __restrict__ dispraw, uint32_t* __restrict__ wta) {
+    constexpr int G = 8, ROWS = 4, NWARP = 4;
+    extern __shared__ __align__(128) uint8_t hsm[];
+    __shared__ __align__(8) uint64_t full[NWARP][H_STAGES];
+    __shared__ __align__(16) int16_t smS[WTA ? NWARP * ROWS * 2 * NP * G : 8];
+    const int D = g.D;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gidx = lane / G, lg = lane & (G - 1);
+    const int row = (blockIdx.x * NWARP + warp) * ROWS + gidx;
+    bool active = row < g.H;
+    int y = min(row, g.H - 1);
+    const int b = blockIdx.z;
+    int si = -1;
+    for (int i = 0; i < g.nseg; i++)
+        if (y >= g.seg[i].dst_start && y < g.seg[i].src_end) si = i;
+    if (si < 0) {   // row outside the selected stripes: run on a valid row, write nothing
+        si = 0;
+        y = g.seg[0].dst_start;
+        active = false;
+    }
+    const Seg sg = g.seg[si];
+    const uint32_t P1x2 = pack16(g.P1, g.P1), P2x2 = pack16(g.P2, g.P2);
+    const int pad = 32767 - g.P1;
+    const uint32_t PADx2 = pack16(pad, pad);
+    const size_t lane_off = (size_t)lg * 2 * NP;
+    const int16_t* Crow = C + (((size_t)b * g.crows + sg.crow0 + (y - sg.src_start)) * g.W1) * D;
+    int16_t* Srow = S + (((size_t)b * g.H + y) * g.W1) * D;
+    // ring: [warp][stage][C|S][row][K][D]
+    const size_t arr_bytes = (size_t)ROWS * K * D * 2, stage_bytes = 2 * arr_bytes;
+    uint8_t* ring = hsm + (size_t)warp * H_STAGES * stage_bytes;
+    const int nchunks = (g.W1 + K - 1) / K;
+    auto chunk_range = [&](int c, int& xlo, int& n) {   // memory range [xlo, xlo + n) of chunk c in traversal order
+        if (dir > 0) { xlo = c * K; n = min(K, g.W1 - xlo); }
+        else { const int xhi = g.W1 - 1 - c * K; xlo = max(xhi - K + 1, 0); n = xhi - xlo + 1; }
+    };
+    auto issue = [&](int c) {   // lanes with lg == 0: one per row
+        int xlo, n;
+        chunk_range(c, xlo, n);
+        const int st = c % H_STAGES;
+        uint8_t* base = ring + (size_t)st * stage_bytes + (size_t)gidx * K * D * 2;
+        const uint32_t bytes = (uint32_t)n * D * 2;
+        mbar_expect_tx(&full[warp][st], accumulate ? 2 * bytes : bytes);
+        bulk_g2s(base, Crow + (size_t)xlo * D, bytes, &full[warp][st]);
+        if (accumulate) bulk_g2s(base + arr_bytes, Srow + (size_t)xlo * D, bytes, &full[warp][st]);
+    };
+    if (lane == 0) {
+        for (int i = 0; i < H_STAGES; i++) mbar_init(&full[warp][i], ROWS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (lg == 0)
+        for (int c = 0; c < H_STAGES && c < nchunks; c++) issue(c);
+    uint32_t P[NP], c_[NP], s_[NP], L[NP], m = 0;
+#pragma unroll
+    for (int k = 0; k < NP; k++) { P[k] = 0; s_[k] = 0; }
+    int16_t* sm = smS + (warp * ROWS + gidx) * 2 * NP * G;
+    int x = dir > 0 ? 0 : g.W1 - 1;
+    for (int c = 0; c < nchunks; c++) {
+        int xlo, n;
+        chunk_range(c, xlo, n);
+        const int st = c % H_STAGES;
+        mbar_wait(&full[warp][st], (uint32_t)((c / H_STAGES) & 1));
+        const uint8_t* base = ring + (size_t)st * stage_bytes + (size_t)gidx * K * D * 2;
+        for (int j = 0; j < n; j++) {
+            const int jm = x - xlo;   // position of this step inside the staged run
+            load_regs<NP>((const int16_t*)(base + (size_t)jm * D * 2) + lane_off, c_);
+            if (accumulate) load_regs<NP>((const int16_t*)(base + arr_bytes + (size_t)jm * D * 2) + lane_off, s_);
+            sgm_step<NP, G>(P, m, c_, P1x2, P2x2, PADx2, lg);
+#pragma unroll
+            for (int k = 0; k < NP; k++) L[k] = accumulate ? __vminu2(__vadd2(s_[k], P[k]), 0x7FFF7FFFu) : P[k];
+            if constexpr (WTA) {
+                int dv;
+                uint32_t wv;
+                wta_pixel<NP, G>(L, lg, g, sm, dv, wv);
+                if (active && lg == 0) {
+                    dispraw[((size_t)b * g.H + y) * g.W + x + g.minX1] = (int16_t)dv;
+                    wta[((size_t)b * g.H + y) * g.W1 + x] = wv;
+                }
+            } else {
+                if (active) store_regs<NP>(Srow + (size_t)x * D + lane_off, L);
+            }
+            x += dir;
+        }
+        __syncwarp();   // every lane is done reading this stage
+        if (lg == 0 && c + H_STAGES < nchunks) issue(c + H_STAGES);
+    }
+}
+
 // Right-view disparity + left-right check for one row. disp2 is reduced
 // with atomicMin on (cost << 16 | 0xFFFF - x): smallest cost wins, ties go to the largest x,
 // which is what OpenCV's descending-x "disp2cost[x2] > minS" scan produces.
@@ -828,6 +923,23 @@ template <int NP>
 int launch_path_h(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int16_t* S, int dir, int acc, bool wta_on,
                   int16_t* dispraw, uint32_t* wta) {
     constexpr int G = 8;
+    static const bool legacy = getenv("SDR_PATH_H_LEGACY") != nullptr;   // A/B switch: register-prefetch version
+    const int K = std::max(1, 512 / g.D);                                 // steps per staged chunk: about 1 KB per row
+    const size_t smem = (size_t)4 * H_STAGES * 2 * 4 * K * g.D * 2;       // [warp][stage][C|S][row][K][D]
+    // measured (1280x720x128, batch 8): L->R 1.12 -> 1.01 ms with the ring; the R->L + WTA kernel is bound by its own
+    // dependent arithmetic and loses with the extra shared-memory hop (0.94 -> 1.52 ms), so it keeps the register prefetch
+    if (!legacy && !wta_on && smem <= ctx->smem_optin) {
+        dim3 grid(div_up(g.H, 16), 1, batch);
+        if (wta_on) {
+            SDR_CUDA(ctx, cudaFuncSetAttribute(k_path_h2<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_path_h2<NP, true><<<grid, 128, smem, ctx->stream>>>(g, C, S, dir, acc, K, dispraw, wta);
+        } else {
+            SDR_CUDA(ctx, cudaFuncSetAttribute(k_path_h2<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_path_h2<NP, false><<<grid, 128, smem, ctx->stream>>>(g, C, S, dir, acc, K, dispraw, wta);
+        }
+        SDR_LAUNCHED(ctx);
+        return SDR_OK;
+    }
     dim3 grid(div_up(g.H, 128 / G), 1, batch);
     if (wta_on)
         k_path_h<NP, G, true><<<grid, 128, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
