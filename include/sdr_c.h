@@ -225,6 +225,26 @@ SDR_API int sdr_pipeline_stage_times(sdr_pipeline* p, int cap, const char** name
 /* Copy cloud i of the last run to host buffers (any may be NULL); sized by views[i].n. */
 SDR_API int sdr_pipeline_cloud_download(sdr_pipeline* p, int i, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt);
 
+/* ---- frame-parallel stream over the GPUs of one box (BASELINE config 4; the video loop of stereo_displayer.cpp:145-198
+ *      with frames sharded by index, no collective: frames share no state) ----
+ * One host worker thread per (device, handle): each owns a context, a stream and a pipeline, pulls the next batch of
+ * frame indices from a shared counter, asks `source` for the frames, runs the path and hands every result to `sink`.
+ * Callbacks are called from worker threads (concurrently for different frames). `source` fills *sbs with a view of
+ * frame `index` (u8 BGR, cols = 2 * image_width, host / pinned / device memory that stays valid until the matching
+ * sink call) and returns SDR_OK, or non-zero to drop the frame. `sink` receives the CV_16S map in pinned host memory
+ * (valid during the call) and the cloud view (device pointers, valid during the call). */
+typedef int (*sdr_frame_source)(void* user, int64_t index, sdr_image* sbs);
+typedef void (*sdr_frame_sink)(void* user, int64_t index, int device, const sdr_image* disp, const sdr_cloud_view* cloud);
+typedef struct sdr_stream_stats {
+    int64_t frames;        /* frames processed */
+    double seconds;        /* wall time of the whole run */
+    double frames_per_s;
+    int64_t per_device[16];
+} sdr_stream_stats;
+SDR_API int sdr_stream_run(const int* devices, int n_devices, int handles_per_device, const sdr_calibration* calib,
+                           const sdr_pipeline_options* opt, int64_t n_frames, sdr_frame_source source, sdr_frame_sink sink, void* user,
+                           sdr_stream_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

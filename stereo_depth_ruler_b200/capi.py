@@ -80,7 +80,7 @@ SYMBOLS = [
     "sdr_cloud_create", "sdr_cloud_destroy", "sdr_voxelgrid", "sdr_depth_cloud", "sdr_cloud_download",
     "sdr_pipeline_create", "sdr_pipeline_destroy", "sdr_pipeline_run", "sdr_pipeline_stage_times",
     "sdr_pipeline_cloud_download", "sdr_pipeline_set_profiling",
-    "sdr_measure_distance", "sdr_depth_coverage", "sdr_cloud_save_pcd_binary",
+    "sdr_measure_distance", "sdr_depth_coverage", "sdr_cloud_save_pcd_binary", "sdr_stream_run",
 ]
 
 _lib = None
@@ -514,3 +514,39 @@ class Pipeline:
             self.close()
         except Exception:
             pass
+
+
+class StreamStats(C.Structure):
+    _fields_ = [("frames", C.c_int64), ("seconds", C.c_double), ("frames_per_s", C.c_double), ("per_device", C.c_int64 * 16)]
+
+
+FRAME_SOURCE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.POINTER(Image))
+FRAME_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int, C.POINTER(Image), C.POINTER(CloudView))
+
+
+def stream_run(devices, handles_per_device, calib, sgbm_params, voxel_opt, frames, n_frames=None, handle_missing=True, batch=4,
+               on_result=None):
+    """Frame-parallel run over several GPUs in one process (sdr_stream_run). frames: list of SBS numpy arrays (cycled when
+    n_frames exceeds its length). on_result(index, device, disp_numpy_view, n_cloud_points) is called from worker threads."""
+    n_frames = len(frames) if n_frames is None else n_frames
+    imgs = [as_image(f, 3)[0] for f in frames]
+
+    def src(_u, i, out):
+        out[0] = imgs[i % len(imgs)]
+        return SDR_OK
+
+    def snk(_u, i, dev, disp, cloud):
+        if on_result is not None:
+            d = disp[0]
+            arr = np.ctypeslib.as_array(C.cast(d.data, C.POINTER(C.c_int16)), shape=(d.rows, d.cols))
+            on_result(int(i), int(dev), arr, int(cloud[0].n))
+
+    opt = PipelineOptions(sgbm_params, voxel_opt, int(bool(handle_missing)), int(batch), 0)
+    devs = (C.c_int * len(devices))(*devices)
+    st = StreamStats()
+    cb_src, cb_snk = FRAME_SOURCE(src), FRAME_SINK(snk)
+    rc = lib().sdr_stream_run(devs, len(devices), int(handles_per_device), C.byref(calib), C.byref(opt), C.c_int64(n_frames), cb_src, cb_snk,
+                              None, C.byref(st))
+    if rc != SDR_OK:
+        raise SdrError(rc, "sdr_stream_run failed")
+    return st

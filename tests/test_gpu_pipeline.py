@@ -95,3 +95,39 @@ def test_interface_mirror_reads_like_the_reference(ctx, orc, calib_path):
         assert not out["passthrough"]
         assert np.array_equal(out["idx"], ref["idx"]) and np.array_equal(out["cnt"], ref["cnt"])
         assert np.allclose(out["xyz"], ref["xyz"], rtol=1e-4, atol=0)
+
+
+def test_stream_runner_shards_frames_over_devices(ctx, orc, calib_path):
+    """sdr_stream_run (BASELINE config 4): worker threads per (device, handle) pull frame batches from a shared cursor;
+    every frame is processed exactly once and equals the single-pipeline result, whatever device took it."""
+    import threading
+    import torch
+    from stereo_depth_ruler_b200 import capi
+    calib = capi.load_calibration(calib_path)
+    args = (0, 128, 5, 600, 2400, 1, 63, 12, 200, 2, 0)
+    vox = capi.voxel_options(5.0, drop_invalid=True, z_max=Z_MAX)
+    frames = [_raw_sbs(41), _raw_sbs(43), _raw_sbs(47)]
+    # expected results from one ordinary pipeline
+    p = capi.Pipeline(ctx, calib, capi.make_params(*args), vox, handle_missing=True, batch=1)
+    expect = []
+    for f in frames:
+        d = [np.empty((720, 1280), np.int16)]
+        p.run([f], disp=d)
+        expect.append((d[0].copy(), int(p.views[0].n)))
+    p.close()
+    n_dev = torch.cuda.device_count()
+    devices = list(range(min(n_dev, 4)))
+    seen, lock = {}, threading.Lock()
+
+    def on_result(i, dev, disp, n_cloud):
+        ok = bool(np.array_equal(disp, expect[i % 3][0])) and n_cloud == expect[i % 3][1]
+        with lock:
+            seen.setdefault(i, []).append((dev, ok))
+
+    n_frames = 22
+    st = capi.stream_run(devices, 2, calib, capi.make_params(*args), vox, frames, n_frames=n_frames, batch=3, on_result=on_result)
+    assert st.frames == n_frames and sorted(seen) == list(range(n_frames))
+    assert all(len(v) == 1 and v[0][1] for v in seen.values())           # exactly once, bit-identical
+    assert sum(st.per_device[:len(devices)]) == n_frames and st.frames_per_s > 0
+    if len(devices) > 1:
+        assert len({v[0][0] for v in seen.values()}) > 1                   # more than one GPU took frames
