@@ -212,8 +212,7 @@ def run_ours(args):
         n_px = H * W
         cl = dict(xyz=torch.empty((B, n_px, 3), dtype=torch.float32).pin_memory().numpy(),
                   rgb=torch.empty((B, n_px, 3), dtype=torch.uint8).pin_memory().numpy(),
-                  idx=torch.empty((B, n_px), dtype=torch.int32).pin_memory().numpy().view(np.uint32),
-                  cnt=torch.empty((B, n_px), dtype=torch.int32).pin_memory().numpy().view(np.uint32))
+                  )
         slots.append(dict(ctx=c_k, stream=st_k, pipe=p_k, disp=[dh.numpy()[i] for i in range(B)], cloud=cl, d2h=0, keep=dh))
 
     def dev_step(slot, s):
@@ -222,10 +221,9 @@ def run_ours(args):
     def e2e_step(slot, s):
         sl = slots[slot]
         sl["pipe"].run(batch_host(s), disp=sl["disp"])
-        nb = 0
-        for i in range(B):
-            nb += sl["pipe"].cloud_to_host_into(i, sl["cloud"]["xyz"][i], sl["cloud"]["rgb"][i], sl["cloud"]["idx"][i], sl["cloud"]["cnt"][i])
-        sl["d2h"] = nb
+        # the step's result, as the reference keeps it: the CV_16S maps and the filtered clouds (xyz + rgb, what
+        # pcl::PointCloud<PointXYZRGB> holds); the voxel index / count arrays are diagnostics and stay on the device
+        sl["d2h"] = sl["pipe"].clouds_to_host_into(B, sl["cloud"]["xyz"], sl["cloud"]["rgb"], None, None)
 
     def run_slots(fn, steps, first):
         errs = []

@@ -224,6 +224,10 @@ SDR_API int sdr_pipeline_set_profiling(sdr_pipeline* p, int enabled);
 SDR_API int sdr_pipeline_stage_times(sdr_pipeline* p, int cap, const char** names, float* ms);
 /* Copy cloud i of the last run to host buffers (any may be NULL); sized by views[i].n. */
 SDR_API int sdr_pipeline_cloud_download(sdr_pipeline* p, int i, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt);
+/* The clouds of frames 0..n-1 of the last run in one go (arrays of n host pointers, any array may be NULL): the copies are
+ * queued back to back and waited for once. */
+SDR_API int sdr_pipeline_clouds_download(sdr_pipeline* p, int n, float* const* xyz, uint8_t* const* rgb, uint32_t* const* idx,
+                                         uint32_t* const* cnt);
 
 /* ---- frame-parallel stream over the GPUs of one box (BASELINE config 4; the video loop of stereo_displayer.cpp:145-198
  *      with frames sharded by index, no collective: frames share no state) ----

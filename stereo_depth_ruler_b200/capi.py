@@ -79,7 +79,7 @@ SYMBOLS = [
     "sdr_median3_16s", "sdr_filter_speckles", "sdr_reproject_to_3d",
     "sdr_cloud_create", "sdr_cloud_destroy", "sdr_voxelgrid", "sdr_depth_cloud", "sdr_cloud_download",
     "sdr_pipeline_create", "sdr_pipeline_destroy", "sdr_pipeline_run", "sdr_pipeline_stage_times",
-    "sdr_pipeline_cloud_download", "sdr_pipeline_set_profiling",
+    "sdr_pipeline_cloud_download", "sdr_pipeline_clouds_download", "sdr_pipeline_set_profiling",
     "sdr_measure_distance", "sdr_depth_coverage", "sdr_cloud_save_pcd_binary", "sdr_stream_run",
 ]
 
@@ -494,6 +494,19 @@ class Pipeline:
                                                          idx.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)))
         n = int(v.n)
         return n * (12 + 3) + (0 if v.passthrough else n * 8)
+
+    def clouds_to_host_into(self, n, xyz, rgb, idx, cnt):
+        """All n clouds of the last run into caller buffers [n][...] (ideally pinned) with ONE host wait; returns bytes copied."""
+        P = C.c_void_p * n
+        ptrs = [None if a is None else P(*[a[i].ctypes.data for i in range(n)]) for a in (xyz, rgb, idx, cnt)]
+        self.ctx.check(lib().sdr_pipeline_clouds_download(self._h, int(n), *ptrs))
+        per_pt = (12 if xyz is not None else 0) + (3 if rgb is not None else 0)
+        per_vox = (4 if idx is not None else 0) + (4 if cnt is not None else 0)
+        nb = 0
+        for i in range(n):
+            v = self.views[i]
+            nb += int(v.n) * per_pt + (0 if v.passthrough else int(v.n) * per_vox)
+        return nb
 
     def set_profiling(self, on=True):
         lib().sdr_pipeline_set_profiling(self._h, int(on))

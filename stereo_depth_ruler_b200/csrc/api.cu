@@ -20,6 +20,16 @@ void sdr_set_error(sdr_ctx* ctx, const char* fmt, ...) {
     if (ctx) ctx->err = buf;
 }
 
+cudaError_t sdr_wait(sdr_ctx* ctx) {
+    if (!ctx->wait_ev) {
+        cudaError_t e = cudaEventCreateWithFlags(&ctx->wait_ev, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaEventRecord(ctx->wait_ev, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ctx->wait_ev);
+}
+
 int DevBuf::reserve(sdr_ctx* ctx, size_t bytes) {
     if (bytes <= cap) return SDR_OK;
     if (p) {
@@ -140,7 +150,7 @@ int sdr_stage_out_end(sdr_ctx* ctx, const sdr_image* im, const DevView& v) {
     if (im->mem == SDR_MEM_DEVICE) return SDR_OK;
     const size_t rowb = (size_t)im->cols * im->channels * im->elem_size;
     SDR_CUDA(ctx, cudaMemcpy2DAsync(im->data, im->step_bytes, v.p, v.pitch, rowb, im->rows, cudaMemcpyDeviceToHost, ctx->stream));
-    SDR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SDR_CUDA(ctx, sdr_wait(ctx));
     return SDR_OK;
 }
 
@@ -178,6 +188,7 @@ extern "C" void sdr_destroy(sdr_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->wait_ev) cudaEventDestroy(ctx->wait_ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -191,7 +202,7 @@ extern "C" void* sdr_get_stream(sdr_ctx* ctx) { return ctx ? (void*)ctx->stream 
 extern "C" int sdr_synchronize(sdr_ctx* ctx) {
     if (!ctx) return SDR_EINVAL;
     SDR_CUDA(ctx, cudaSetDevice(ctx->device));
-    SDR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SDR_CUDA(ctx, sdr_wait(ctx));
     return SDR_OK;
 }
 extern "C" const char* sdr_last_error(sdr_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }

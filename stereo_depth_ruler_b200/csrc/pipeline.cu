@@ -141,7 +141,7 @@ extern "C" int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sd
         if (rc == SDR_EVOXEL_OVERFLOW) status = rc;
         else if (rc) return rc;
     }
-    SDR_CUDA(ctx, cudaStreamSynchronize(st));
+    SDR_CUDA(ctx, sdr_wait(ctx));
     return status;
 }
 
@@ -160,5 +160,19 @@ extern "C" int sdr_pipeline_stage_times(sdr_pipeline* p, int cap, const char** n
 extern "C" int sdr_pipeline_cloud_download(sdr_pipeline* p, int i, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt) {
     if (!p || !p->cloud) return SDR_EINVAL;
     cudaSetDevice(p->ctx->device);
-    return sdr_cloud_download_frame(p->cloud, i, xyz, rgb, idx, cnt);
+    return sdr_cloud_download_frame(p->cloud, i, xyz, rgb, idx, cnt, true);
+}
+
+extern "C" int sdr_pipeline_clouds_download(sdr_pipeline* p, int n, float* const* xyz, uint8_t* const* rgb, uint32_t* const* idx,
+                                            uint32_t* const* cnt) {
+    if (!p || !p->cloud || n <= 0) return SDR_EINVAL;
+    sdr_ctx* ctx = p->ctx;
+    SDR_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < n; i++) {
+        int rc = sdr_cloud_download_frame(p->cloud, i, xyz ? xyz[i] : nullptr, rgb ? rgb[i] : nullptr, idx ? idx[i] : nullptr,
+                                          cnt ? cnt[i] : nullptr, false);
+        if (rc) return rc;
+    }
+    SDR_CUDA(ctx, sdr_wait(ctx));   // one host wait for the whole batch
+    return SDR_OK;
 }

@@ -18,7 +18,12 @@ struct sdr_ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
+    cudaEvent_t wait_ev = nullptr;   // cudaEventBlockingSync: host waits sleep instead of spinning
 };
+
+// Host wait for everything queued on the ctx stream. Sleeps on a blocking-sync event: with several handles per GPU and
+// one process per GPU the waiting threads would otherwise spin on every core of the box.
+cudaError_t sdr_wait(sdr_ctx* ctx);
 
 #define SDR_FAIL(ctx, code, ...) (sdr_set_error((ctx), __VA_ARGS__), (int)(code))
 void sdr_set_error(sdr_ctx* ctx, const char* fmt, ...);
@@ -105,5 +110,5 @@ int sdr_cloud_enqueue(sdr_cloud* c, int frames, const uint8_t* points, size_t ps
                       size_t dframe, const uint8_t* bgr, size_t cstep, size_t cframe, int W, int H, const double* Q, int handle_missing,
                       const sdr_voxel_options* opt);
 int sdr_cloud_finish(sdr_cloud* c, sdr_cloud_view* views);
-int sdr_cloud_download_frame(sdr_cloud* c, int f, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt);
+int sdr_cloud_download_frame(sdr_cloud* c, int f, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt, bool wait);
 StageTimer* sdr_sgbm_timer(sdr_sgbm* m);

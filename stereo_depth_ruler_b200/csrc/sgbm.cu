@@ -1311,7 +1311,7 @@ extern "C" int sdr_sgbm_compute_batch(sdr_sgbm* m, int n, const sdr_image* lefts
                                             cudaMemcpyDefault, ctx->stream));
             any_host |= disps[i].mem != SDR_MEM_DEVICE;
         }
-        if (any_host) SDR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (any_host) SDR_CUDA(ctx, sdr_wait(ctx));
     }
     return SDR_OK;
 }
@@ -1356,7 +1356,7 @@ extern "C" int sdr_sgbm_match_stripes(sdr_sgbm* m, const sdr_image* left, const 
     const int y0 = m->g.seg[0].dst_start, y1 = m->g.seg[m->g.nseg - 1].src_end;
     SDR_CUDA(ctx, cudaMemcpy2DAsync((uint8_t*)raw->data + (size_t)y0 * raw->step_bytes, raw->step_bytes, m->matched.as<int16_t>() + (size_t)y0 * W,
                                     (size_t)W * 2, (size_t)W * 2, y1 - y0, cudaMemcpyDefault, ctx->stream));
-    if (raw->mem != SDR_MEM_DEVICE) SDR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (raw->mem != SDR_MEM_DEVICE) SDR_CUDA(ctx, sdr_wait(ctx));
     return SDR_OK;
 }
 

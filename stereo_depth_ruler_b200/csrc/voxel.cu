@@ -566,7 +566,7 @@ int sdr_cloud_enqueue(sdr_cloud* c, int frames, const uint8_t* points, size_t ps
     k_vox_passthrough<<<g256, 256, 0, st>>>(s, vp, c->oxyz.as<float>(), c->orgb.as<uint8_t>());
     SDR_LAUNCHED(ctx);
     SDR_CUDA(ctx, cudaMemcpyAsync(c->host_params.p, vp, F * sizeof(VoxParams), cudaMemcpyDeviceToHost, st));
-    if (!c->done) SDR_CUDA(ctx, cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
+    if (!c->done) SDR_CUDA(ctx, cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming | cudaEventBlockingSync));
     SDR_CUDA(ctx, cudaEventRecord(c->done, st));
     return SDR_OK;
 }
@@ -600,7 +600,7 @@ int sdr_cloud_finish(sdr_cloud* c, sdr_cloud_view* views) {
     return status;
 }
 
-int sdr_cloud_download_frame(sdr_cloud* c, int f, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt) {
+int sdr_cloud_download_frame(sdr_cloud* c, int f, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt, bool wait) {
     sdr_ctx* ctx = c->ctx;
     if (f < 0 || f >= c->frames || f >= (int)c->last_n.size()) return SDR_FAIL(ctx, SDR_EINVAL, "cloud_download: no such frame %d", f);
     const size_t n = (size_t)c->last_n[f], N = (size_t)c->W * c->H;
@@ -610,7 +610,7 @@ int sdr_cloud_download_frame(sdr_cloud* c, int f, float* xyz, uint8_t* rgb, uint
         if (idx) SDR_CUDA(ctx, cudaMemcpyAsync(idx, c->oidx.as<uint32_t>() + (size_t)f * N, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
         if (cnt) SDR_CUDA(ctx, cudaMemcpyAsync(cnt, c->ocnt.as<uint32_t>() + (size_t)f * N, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    SDR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (wait) SDR_CUDA(ctx, sdr_wait(ctx));
     return SDR_OK;
 }
 
@@ -670,7 +670,7 @@ extern "C" int sdr_depth_cloud(sdr_cloud* c, const sdr_image* disp16, const sdr_
 extern "C" int sdr_cloud_download(sdr_cloud* c, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt) {
     if (!c) return SDR_EINVAL;
     SDR_CUDA(c->ctx, cudaSetDevice(c->ctx->device));
-    return sdr_cloud_download_frame(c, 0, xyz, rgb, idx, cnt);
+    return sdr_cloud_download_frame(c, 0, xyz, rgb, idx, cnt, true);
 }
 
 extern "C" int sdr_cloud_save_pcd_binary(sdr_cloud* c, int frame, const char* path) {
@@ -682,7 +682,7 @@ extern "C" int sdr_cloud_save_pcd_binary(sdr_cloud* c, int frame, const char* pa
     if (n == 0) return SDR_FAIL(ctx, SDR_EINVAL, "No points to save after downsampling!");   // pcd_write.cpp:143-146
     std::vector<float> xyz(n * 3);
     std::vector<uint8_t> rgb(n * 3);
-    int rc = sdr_cloud_download_frame(c, frame, xyz.data(), rgb.data(), nullptr, nullptr);
+    int rc = sdr_cloud_download_frame(c, frame, xyz.data(), rgb.data(), nullptr, nullptr, true);
     if (rc) return rc;
     const bool organised = c->last_passthrough[frame] != 0;
     const size_t width = organised ? (size_t)c->W : n, height = organised ? (size_t)c->H : 1;
