@@ -300,8 +300,8 @@ def run_ours(args):
             "path_h_bwd_wta": 2 * vol + 6 * img, "lrcheck": 8 * img, "median3": 4 * img, "speckle": 24 * img}
     # DRAM bytes per launch at 8 frames per launch from the committed `ncu --set full` capture of this build
     # (profiles/r1_ncu_sgbm_kernels.txt: dram__bytes_read.sum + dram__bytes_write.sum); scaled to the batch in use.
-    ncu_traffic_b8 = {"cost": 0.314489e9 + 1.645265e9, "path_v_fused_down": 1.699039e9 + 1.656339e9,
-                      "path_h_fwd": 3.397397e9 + 1.658580e9, "path_h_bwd_wta": 3.397726e9 + 0.043919e9}
+    ncu_traffic_b8 = {"cost": 0.314232e9 + 1.644994e9, "path_v_fused_down": 1.699093e9 + 1.653423e9,
+                      "path_h_fwd": 3.397469e9 + 1.660488e9, "path_h_bwd_wta": 3.397700e9 + 0.044476e9}
     dom = max(acc, key=acc.get)
     peaks = {}
     try:
