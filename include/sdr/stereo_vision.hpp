@@ -223,11 +223,7 @@ class StereoDisparity {
         Mat lg = gray(left), rg = gray(right), d16;
         matcher_->compute(lg, rg, d16);
         Mat out(d16.rows(), d16.cols(), 1, 4);
-        for (int y = 0; y < d16.rows(); y++) {
-            const int16_t* s = d16.ptr<int16_t>(y);
-            float* d = out.ptr<float>(y);
-            for (int x = 0; x < d16.cols(); x++) d[x] = (float)s[x] * 0.0625f;  // convertTo(CV_32F, 1/16) is exact
-        }
+        ctx_.check(sdr_disp_to_float(ctx_.get(), d16.c(), out.c()));   // convertTo(CV_32F, 1/16) on the device
         return out;
     }
     // cv::reprojectImageTo3D(disparity, depth, Q)

@@ -149,6 +149,8 @@ SDR_API int sdr_filter_speckles(sdr_ctx* ctx, sdr_image* img, int new_val, int m
 
 /* ---- depth: convertTo(CV_32F, 1/16) + cv::reprojectImageTo3D
  *      (stereo_disparity.cpp:34,76-80; pcd_write.cpp:112,116) ---- */
+/* Mat::convertTo(CV_32F, 1.0/16.0) of the CV_16S map (stereo_disparity.cpp:34, pcd_write.cpp:112): exact in fp32. */
+SDR_API int sdr_disp_to_float(sdr_ctx* ctx, const sdr_image* disp16, sdr_image* disp32f);
 /* disp: int16 (CV_16S, divided by 16 internally, i.e. convertTo + reproject fused) or f32 (used as is).
  * Q: 16 doubles row-major. points: f32 3-ch. */
 SDR_API int sdr_reproject_to_3d(sdr_ctx* ctx, const sdr_image* disp, const double* Q, int handle_missing,

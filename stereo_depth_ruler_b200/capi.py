@@ -76,7 +76,7 @@ SYMBOLS = [
     "sdr_sgbm_create", "sdr_sgbm_destroy", "sdr_sgbm_compute", "sdr_sgbm_compute_batch",
     "sdr_sgbm_set_profiling", "sdr_sgbm_stage_times", "sdr_sgbm_debug_read",
     "sdr_sgbm_stripe_rows", "sdr_sgbm_match_stripes", "sdr_sgbm_postfilter",
-    "sdr_median3_16s", "sdr_filter_speckles", "sdr_reproject_to_3d",
+    "sdr_median3_16s", "sdr_filter_speckles", "sdr_disp_to_float", "sdr_reproject_to_3d",
     "sdr_cloud_create", "sdr_cloud_destroy", "sdr_voxelgrid", "sdr_depth_cloud", "sdr_cloud_download",
     "sdr_pipeline_create", "sdr_pipeline_destroy", "sdr_pipeline_run", "sdr_pipeline_stage_times",
     "sdr_pipeline_cloud_download", "sdr_pipeline_clouds_download", "sdr_pipeline_set_profiling",
@@ -365,6 +365,14 @@ def bgr2gray(ctx, bgr):
     out = _empty_like_kind(bgr, tuple(bgr.shape[:2]), np.uint8, "uint8")
     si, _ = as_image(bgr, 3); di, _ = as_image(out, 1)
     ctx.check(lib().sdr_bgr2gray(ctx._h, C.byref(si), C.byref(di)))
+    return out
+
+
+def disp_to_float(ctx, disp16):
+    """convertTo(CV_32F, 1/16) on the device."""
+    out = _empty_like_kind(disp16, tuple(disp16.shape), np.float32, "float32")
+    di, _ = as_image(disp16, 1); oi, _ = as_image(out, 1)
+    ctx.check(lib().sdr_disp_to_float(ctx._h, C.byref(di), C.byref(oi)))
     return out
 
 

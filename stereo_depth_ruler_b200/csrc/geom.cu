@@ -243,6 +243,12 @@ __global__ void k_pick2(const uint8_t* __restrict__ pts, size_t step, int x1, in
     else if (i < 6) out[i] = ((const float*)(pts + (size_t)y2 * step))[(size_t)x2 * 3 + i - 3];
 }
 
+__global__ void __launch_bounds__(256) k_disp_to_float(const uint8_t* __restrict__ src, size_t sstep, uint8_t* __restrict__ dst, size_t dstep, int W,
+                                                       int H) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x < W) ((float*)(dst + (size_t)y * dstep))[x] = (float)((const int16_t*)(src + (size_t)y * sstep))[x] * 0.0625f;
+}
+
 // cv::invert(DECOMP_LU) of a 3x3 (partial pivoting), fp64, on the host
 bool invert3(const double* m, double* inv) {
     double a[3][6];
@@ -559,4 +565,27 @@ extern "C" int sdr_depth_coverage(sdr_ctx* ctx, const sdr_image* points, int fir
     if (count) *count = (int64_t)n;
     if (coverage_percent) *coverage_percent = ((double)n / ((double)points->rows * points->cols)) * 100;
     return SDR_OK;
+}
+
+extern "C" int sdr_disp_to_float(sdr_ctx* ctx, const sdr_image* disp16, sdr_image* disp32f) {
+    if (!ctx || !disp16 || !disp32f) return SDR_EINVAL;
+    SDR_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = sdr_check_image(ctx, disp16, 1, 2, "disp16"))) return rc;
+    if ((rc = sdr_check_image(ctx, disp32f, 1, 4, "disp32f"))) return rc;
+    if (disp16->cols != disp32f->cols || disp16->rows != disp32f->rows) return SDR_FAIL(ctx, SDR_ESIZE, "disp_to_float: size mismatch");
+    DevBuf bin, bout;
+    DevView vi, vo;
+    rc = sdr_stage_in(ctx, disp16, bin, &vi);
+    if (rc == SDR_OK) rc = sdr_stage_out_begin(ctx, disp32f, bout, &vo);
+    if (rc == SDR_OK) {
+        k_disp_to_float<<<dim3(div_up(disp16->cols, 256), disp16->rows), 256, 0, ctx->stream>>>(vi.p, vi.pitch, vo.p, vo.pitch, disp16->cols,
+                                                                                                disp16->rows);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = SDR_FAIL(ctx, SDR_ECUDA, "disp_to_float launch failed");
+    }
+    if (rc == SDR_OK) rc = sdr_stage_out_end(ctx, disp32f, vo);
+    sdr_wait(ctx);
+    bin.release(); bout.release();
+    return rc;
 }

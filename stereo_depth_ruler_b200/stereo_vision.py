@@ -149,10 +149,7 @@ class StereoDisparity:
         return self.matcher.compute(left, right)
 
     def computeDisparity(self, left, right):
-        d16 = self.computeDisparity16(left, right)
-        if capi._is_torch(d16):
-            return d16.float() * 0.0625
-        return d16.astype(np.float32) * np.float32(0.0625)
+        return capi.disp_to_float(self.ctx, self.computeDisparity16(left, right))   # convertTo(CV_32F, 1/16) on the device
 
     def computeDepth(self, disparity, handleMissingValues=False):
         """disparity: CV_32F (as the reference passes) or CV_16S (the /16 is then fused)."""
