@@ -296,7 +296,7 @@ def run_ours(args):
     img = W * H
     # algorithmic bytes per frame of each SGBM kernel (DESIGN.md "Kernels"): distinct bytes it must read + write
     algo = {"prefilter": 2 * img + (16 + 25) * img, "cost": (16 + 25) * img + vol, "path_v_fused_down": 2 * vol,
-            "path_v_fused_up": 3 * vol, "path_v0": 2 * vol, "path_v1": 3 * vol, "path_v2": 3 * vol, "path_h_fwd": 3 * vol,
+            "cost_path_v_fused": (16 + 25) * img + 2 * vol, "path_v_fused_up": 3 * vol, "path_v0": 2 * vol, "path_v1": 3 * vol, "path_v2": 3 * vol, "path_h_fwd": 3 * vol,
             "path_h_bwd_wta": 2 * vol + 6 * img, "lrcheck": 8 * img, "median3": 4 * img, "speckle": 24 * img}
     # DRAM bytes per launch at 8 frames per launch from the committed `ncu --set full` capture of this build
     # (profiles/r1_ncu_sgbm_kernels.txt: dram__bytes_read.sum + dram__bytes_write.sum); scaled to the batch in use.

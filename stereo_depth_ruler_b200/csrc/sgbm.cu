@@ -461,7 +461,8 @@ __device__ __forceinline__ void load_regs_cg(const int16_t* p, uint32_t (&r)[NP]
 }
 
 constexpr int V3_COLS = 32;
-constexpr int V3_STAGES_MAX = 6;   // rows of C in flight per CTA (TMA ring); 3 when S is staged too (keeps 2 CTAs/SM)
+constexpr int V3_STAGES_MAX = 6;       // rows of C in flight per CTA (TMA ring); 3 when S is staged too (keeps 2 CTAs/SM)
+constexpr int V3_STAGES_DEFAULT = 6;
 constexpr int V3_SPIN_LIMIT = 1 << 22;
 
 // Halo words carry their own sequence number (row + 1) in the upper half of one 64-bit store, so no fence and no
@@ -494,9 +495,8 @@ __device__ __forceinline__ void halo_complete(const unsigned long long* p, uint3
 
 template <int NP, int MINB, bool ACC>
 __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int diry, int b0,
-                                                       unsigned long long* halo, int* err) {
+                                                       unsigned long long* halo, int* err, int V3_STAGES) {
     constexpr int G = 8, NW = NP + 1;   // halo words per lane: NP state registers + the path minimum
-    constexpr int V3_STAGES = ACC ? 3 : V3_STAGES_MAX;
     extern __shared__ __align__(16) int16_t v3sm[];
     const int D = g.D;
     int16_t* Xa = v3sm;                                     // [2][COLS+2][D]  state of the "from (x-1)" diagonal, slot = column+1
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
     // columns of one row are one contiguous 32*D*2-byte run in global memory
     int16_t* ringC = (int16_t*)(Mb + 2 * (V3_COLS + 2));        // [STAGES][COLS][D]
     int16_t* ringS = ringC + (size_t)V3_STAGES * V3_COLS * D;   // [STAGES][COLS][D] (ACC only)
-    __shared__ __align__(8) uint64_t full[V3_STAGES];
+    __shared__ __align__(8) uint64_t full[V3_STAGES_MAX];
     const int s = blockIdx.x, nstrips = gridDim.x, f = blockIdx.y, b = b0 + f;
     const int gidx = threadIdx.x / G, lg = threadIdx.x & (G - 1);
     const int x = s * V3_COLS + gidx;
@@ -531,8 +531,8 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
     const int16_t* Ctile = C + (size_t)b * g.crows * g.W1 * D + (size_t)x0 * D;    // + row * rowstride
     const int16_t* Stile = S + (size_t)b * g.H * g.W1 * D + (size_t)x0 * D;
     const int ystart = diry > 0 ? 0 : g.H - 1;
-    auto issue = [&](int t) {   // one thread: stage row t of the sweep
-        const int yy = ystart + t * diry, st = t % V3_STAGES;
+    auto issue = [&](int t, int st) {   // one thread: stage row t of the sweep into ring slot st (= t mod V3_STAGES)
+        const int yy = ystart + t * diry;
         mbar_expect_tx(&full[st], ACC ? 2 * tile_bytes : tile_bytes);
         bulk_g2s(ringC + (size_t)st * V3_COLS * D, Ctile + (size_t)yy * rowstride, tile_bytes, &full[st]);
         if (ACC) bulk_g2s(ringS + (size_t)st * V3_COLS * D, Stile + (size_t)yy * rowstride, tile_bytes, &full[st]);
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
     }
     __syncthreads();
     if (threadIdx.x == 0)
-        for (int i = 0; i < V3_STAGES && i < g.H; i++) issue(i);
+        for (int i = 0; i < V3_STAGES && i < g.H; i++) issue(i, i);
     const bool left_edge = gidx == 0 && s > 0, right_edge = gidx == V3_COLS - 1 && s + 1 < nstrips;
     uint32_t Pv[NP], pa[NP], pb[NP], c[NP], so[ACC ? NP : 1], acc[NP];
     uint32_t mv = 0, ma = 0, mb = 0;
@@ -553,10 +553,11 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
 #pragma unroll
     for (int k = 0; k < NW; k++) hq[k] = 0;
     int y = ystart;
+    int stg = 0;
+    uint32_t ring_phase = 0;
     for (int t = 0; t < g.H; t++) {
         const int cur = t & 1, prv = cur ^ 1;
-        const int stg = t % V3_STAGES;
-        mbar_wait(&full[stg], (uint32_t)((t / V3_STAGES) & 1));
+        mbar_wait(&full[stg], ring_phase);
         load_regs<NP>(ringC + ((size_t)stg * V3_COLS + gidx) * D + lane_off, c);
         if constexpr (ACC) load_regs<NP>(ringS + ((size_t)stg * V3_COLS + gidx) * D + lane_off, so);
         // previous-row diagonal states: neighbouring column through shared memory, across strips from the prefetched halo
@@ -626,8 +627,303 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
             if (right_edge) halo_complete<NW>(Hptr(s, cur, 1), (uint32_t)(t + 1), err, hq);
         }
         __syncthreads();   // also: every thread is done with ring stage `stg`
-        if (threadIdx.x == 0 && t + V3_STAGES < g.H) issue(t + V3_STAGES);
+        if (threadIdx.x == 0 && t + V3_STAGES < g.H) issue(t + V3_STAGES, stg);
+        if (++stg == V3_STAGES) { stg = 0; ring_phase ^= 1; }
         y += diry;
+    }
+}
+
+// ---- fused cost + top-down sweep ---------------------------------------------------------------------------------
+// One CTA = one 32-column strip of one frame, 12 warps in two roles:
+//   warps 8-11 (producer, 128 threads): BT pixel cost -> vertical running box sum -> horizontal box sum for the strip's
+//       32 columns (+2*SW2 halo columns), one image row after the other, into a ring of C row tiles in shared memory;
+//       every finished tile is also written to the C volume in HBM (one TMA bulk store) for the horizontal kernels;
+//   warps 0-7 (consumer, 256 threads): the three top-down paths of k_path_v3 reading C from that ring.
+// The sweep alone leaves ~60 % of the issue slots idle (it waits for its neighbours' halos every row) and the cost
+// kernel alone is issue-bound: in one kernel the producer fills those slots, and the sweep's read of C from HBM
+// (one volume pass) disappears. Registers are split with setmaxnreg (producer 64, consumer 88 per thread).
+constexpr int CF_NST = 3;          // C row tiles in flight between producer and consumer
+constexpr int CF_PROD = 128;       // producer threads
+constexpr int CF_CONS = 256;       // consumer threads (32 columns x 8 lanes)
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+
+struct CfLayout {   // shared-memory carve-up (bytes), computed identically on host and device
+    int cw, nchunks_max, stage_bytes;
+    size_t off_ma, off_ring_c, off_stage, off_ring8, off_vs, total;
+};
+__host__ __device__ inline CfLayout cf_layout(int D, int SW2, int SH2) {
+    CfLayout L;
+    L.cw = V3_COLS + 2 * SW2;
+    L.nchunks_max = (L.cw + D + 32) / 16 + 1;
+    L.stage_bytes = ((L.cw * 16 + L.nchunks_max * PR_CHUNK) + 127) & ~127;
+    size_t o = (size_t)4 * (V3_COLS + 2) * D * 2;          // Xa, Xb
+    L.off_ma = o;  o += (size_t)4 * (V3_COLS + 2) * 4;     // Ma, Mb
+    o = (o + 127) & ~(size_t)127;
+    L.off_ring_c = o;  o += (size_t)CF_NST * V3_COLS * D * 2;
+    L.off_stage = o;   o += (size_t)2 * L.stage_bytes;
+    L.off_ring8 = o;   o += (size_t)(2 * SH2 + 1) * L.cw * D;
+    o = (o + 15) & ~(size_t)15;
+    L.off_vs = o;      o += (size_t)L.cw * D * 2;
+    L.total = o;
+    return L;
+}
+
+template <int NP, int SW2>
+__global__ void __launch_bounds__(CF_PROD + CF_CONS, 2)
+k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ PR, int16_t* __restrict__ C, int16_t* __restrict__ S, int b0,
+               unsigned long long* halo, int* err) {
+    constexpr int G = 8, NW = NP + 1, D = 16 * NP, DQ = D / 8;
+    constexpr int XG = CF_PROD / DQ;            // producer column groups
+    constexpr int CPT = V3_COLS / XG;           // consecutive output columns per producer thread
+    constexpr int NX = 2 * SW2;                 // halo columns of the strip (box-sum window minus one)
+    constexpr int CW = V3_COLS + NX;
+    static_assert(CF_PROD % DQ == 0 && V3_COLS % XG == 0 && NX <= XG, "producer tiling");
+    extern __shared__ __align__(128) uint8_t cfsm[];
+    __shared__ __align__(8) uint64_t fullC[CF_NST], emptyC[CF_NST], fullIn[2];
+    const CfLayout lay = cf_layout(D, SW2, g.SH2);
+    int16_t* Xa = (int16_t*)cfsm;
+    int16_t* Xb = Xa + 2 * (V3_COLS + 2) * D;
+    uint32_t* Ma = (uint32_t*)(cfsm + lay.off_ma);
+    uint32_t* Mb = Ma + 2 * (V3_COLS + 2);
+    int16_t* ringC = (int16_t*)(cfsm + lay.off_ring_c);
+    const int s = blockIdx.x, nstrips = gridDim.x, f = blockIdx.y, b = b0 + f;
+    const int x0 = s * V3_COLS;
+    const int n = 2 * g.SH2 + 1;
+    // ---- prologue (all threads): zero the diagonal states and the pixel-cost ring, set up the barriers
+    for (int i = threadIdx.x; i < (int)(lay.off_ring_c / 4); i += blockDim.x) ((uint32_t*)cfsm)[i] = 0;
+    for (int i = threadIdx.x; i < (int)((lay.off_vs - lay.off_ring8) / 4); i += blockDim.x) ((uint32_t*)(cfsm + lay.off_ring8))[i] = 0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < CF_NST; i++) { mbar_init(&fullC[i], 1); mbar_init(&emptyC[i], CF_CONS / 32); }
+        mbar_init(&fullIn[0], 1);
+        mbar_init(&fullIn[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t tile_bytes = (uint32_t)(min(V3_COLS, g.W1 - x0) * D * 2);
+
+    if (threadIdx.x >= CF_CONS) {
+        // =============================== producer: cost rows ===============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
+        const int tid = threadIdx.x - CF_CONS;
+        const int q = tid % DQ, xg = tid / DQ;
+        uint8_t* stage = cfsm + lay.off_stage;
+        uint8_t* ring8 = cfsm + lay.off_ring8;                 // [n][CW][D] u8
+        uint16_t* Vs = (uint16_t*)(cfsm + lay.off_vs);         // [CW][D] u16
+        const int lo = max(x0 - SW2, 0), hi = min(x0 - SW2 + CW, g.W1);
+        const int j0_min = (g.W - 1 - (hi - 1 + g.minX1)) + g.minD, j0_max = (g.W - 1 - (lo + g.minX1)) + g.minD + 8 * (DQ - 1);
+        const int cs = max(j0_min - 3, 0) >> 4, nchunks = ((j0_max + 7) >> 4) - cs + 1;
+        const uint32_t pl_bytes = (uint32_t)(hi - lo) * 16, pr_bytes = (uint32_t)nchunks * PR_CHUNK;
+        constexpr int ITEMS = CPT + 1;
+        // item k < CPT: strip column h = CPT*xg + k (h counts from x0 - SW2); item CPT: halo column h = 32 + xg (xg < NX)
+        uint32_t tab[ITEMS];   // per item: o0 (low 16 bits) | ix << 16 | "second word is in the next chunk" << 31
+        uint32_t V[ITEMS][4];
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+            const int h = k < CPT ? CPT * xg + k : V3_COLS + xg;
+            const int xc = min(max(x0 - SW2 + h, 0), g.W1 - 1);
+            const int ix = min(max(xc - lo, 0), CW - 1);
+            const int j0 = (g.W - 1 - (xc + g.minX1)) + g.minD + 8 * q;
+            const int a = j0 & 3, p0 = j0 - a;
+            const int o0 = ((p0 >> 4) - cs) * PR_CHUNK + (p0 & 15) + a * 16;
+            tab[k] = (uint32_t)o0 | ((uint32_t)ix << 16) | ((p0 & 15) == 12 ? 0x80000000u : 0u);
+            V[k][0] = V[k][1] = V[k][2] = V[k][3] = 0;
+        }
+        const int NV = g.H + 2 * g.SH2;
+        auto issue_in = [&](int i) {   // one thread: stage virtual row i (image row clamp(i - SH2))
+            const int rc = min(max(i - g.SH2, 0), g.H - 1);
+            uint8_t* st = stage + (size_t)(i & 1) * lay.stage_bytes;
+            mbar_expect_tx(&fullIn[i & 1], pl_bytes + pr_bytes);
+            bulk_g2s(st, PL + ((size_t)b * g.H + rc) * g.W + lo + g.minX1, pl_bytes, &fullIn[i & 1]);
+            bulk_g2s(st + CW * 16, PR + (((size_t)b * g.H + rc) * (g.Wp >> 4) + cs) * PR_CHUNK, pr_bytes, &fullIn[i & 1]);
+        };
+        if (tid == 0) {
+            issue_in(0);
+            if (NV > 1) issue_in(1);
+        }
+        int slot = 0, cst = 0;
+        uint32_t cphase = 0;
+        for (int i = 0; i < NV; i++) {
+            const uint8_t* st = stage + (size_t)(i & 1) * lay.stage_bytes;
+            mbar_wait(&fullIn[i & 1], (uint32_t)((i >> 1) & 1));
+            const int4* pls = (const int4*)st;
+            const uint8_t* prs = st + CW * 16;
+#pragma unroll
+            for (int k = 0; k < ITEMS; k++) {
+                if (k < CPT || xg < NX) {
+                    const int h = k < CPT ? CPT * xg + k : V3_COLS + xg;
+                    const int o0 = (int)(tab[k] & 0xFFFFu), ix = (int)((tab[k] >> 16) & 0x7FFFu);
+                    const int o1 = o0 + ((int)tab[k] < 0 ? PR_CHUNK - 12 : 4);
+                    uint32_t n0, n1;
+                    bt_item(pls[ix], prs, o0, o1, n0, n1);
+                    uint2* rp = (uint2*)(ring8 + ((size_t)slot * CW + h) * D + 8 * q);
+                    const uint2 old = *rp;
+                    *rp = make_uint2(n0, n1);
+                    // V += new - old per 16-bit half: new (bytes, zero-extended) minus old (bytes, zero-extended)
+                    V[k][0] = __vsub2(__vadd2(V[k][0], prmt(n0, 0, 0x4140)), prmt(old.x, 0, 0x4140));
+                    V[k][1] = __vsub2(__vadd2(V[k][1], prmt(n0, 0, 0x4342)), prmt(old.x, 0, 0x4342));
+                    V[k][2] = __vsub2(__vadd2(V[k][2], prmt(n1, 0, 0x4140)), prmt(old.y, 0, 0x4140));
+                    V[k][3] = __vsub2(__vadd2(V[k][3], prmt(n1, 0, 0x4342)), prmt(old.y, 0, 0x4342));
+                }
+            }
+            slot = slot + 1 == n ? 0 : slot + 1;
+            const int y = i - 2 * g.SH2;          // output row finished by this virtual row
+            if (y >= 0) {
+#pragma unroll
+                for (int k = 0; k < ITEMS; k++)
+                    if (k < CPT || xg < NX) {
+                        const int h = k < CPT ? CPT * xg + k : V3_COLS + xg;
+                        *(uint4*)(Vs + (size_t)h * D + 8 * q) = make_uint4(V[k][0], V[k][1], V[k][2], V[k][3]);
+                    }
+                // the bulk store that last read ring slot cst must be done reading before the slot is rewritten
+                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(CF_NST - 1) : "memory");
+            }
+            named_bar_sync(2, CF_PROD);   // Vs complete; every producer thread is done with this input stage
+            if (tid == 0 && i + 2 < NV) issue_in(i + 2);
+            if (y >= 0) {
+                if (y >= CF_NST) mbar_wait(&emptyC[cst], cphase ^ 1);   // consumers released the slot (use number y/NST - 1)
+                // horizontal box sum: window of CPT + NX columns = own columns (registers) + NX right neighbours (Vs)
+                uint32_t w[CPT + NX][4];
+#pragma unroll
+                for (int k = 0; k < CPT; k++) { w[k][0] = V[k][0]; w[k][1] = V[k][1]; w[k][2] = V[k][2]; w[k][3] = V[k][3]; }
+#pragma unroll
+                for (int j = 0; j < NX; j++) {
+                    const uint4 v = *(const uint4*)(Vs + (size_t)(CPT * xg + CPT + j) * D + 8 * q);
+                    w[CPT + j][0] = v.x; w[CPT + j][1] = v.y; w[CPT + j][2] = v.z; w[CPT + j][3] = v.w;
+                }
+                uint32_t acc[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    acc[r] = w[0][r];
+#pragma unroll
+                    for (int j = 1; j <= NX; j++) acc[r] = __vadd2(acc[r], w[j][r]);
+                }
+                int16_t* ct = ringC + (size_t)cst * V3_COLS * D;
+#pragma unroll
+                for (int k = 0; k < CPT; k++) {
+                    if (k > 0) {
+#pragma unroll
+                        for (int r = 0; r < 4; r++) acc[r] = __vsub2(__vadd2(acc[r], w[k + NX][r]), w[k - 1][r]);
+                    }
+                    *(uint4*)(ct + (size_t)(CPT * xg + k) * D + 8 * q) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
+                named_bar_sync(3, CF_PROD);   // tile complete (and every read of Vs is done)
+                if (tid == 0) {
+                    bulk_s2g(C + (((size_t)b * g.crows + y) * g.W1 + x0) * D, ct, tile_bytes);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    mbar_arrive(&fullC[cst]);
+                }
+                if (++cst == CF_NST) { cst = 0; cphase ^= 1; }
+            }
+        }
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        return;
+    }
+
+    // =============================== consumer: the three top-down paths ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;\n");
+    const int gidx = threadIdx.x / G, lg = threadIdx.x & (G - 1);
+    const int x = x0 + gidx;
+    const bool active = x < g.W1;
+    const int xl = min(x, g.W1 - 1);
+    const uint32_t P1x2 = pack16(g.P1, g.P1), P2x2 = pack16(g.P2 , g.P2);
+    const int pad = 32767 - g.P1;
+    const uint32_t PADx2 = pack16(pad, pad);
+    const size_t lane_off = (size_t)lg * 2 * NP;
+    const int HW = G * NW;
+    auto Hptr = [&](int strip, int buf, int which) {
+        return halo + ((((size_t)f * nstrips + strip) * 2 + buf) * 2 + which) * HW + (size_t)lg * NW;
+    };
+    int16_t* Sb = S + (size_t)b * g.H * g.W1 * D + (size_t)xl * D + lane_off;
+    const size_t rowstride = (size_t)g.W1 * D;
+    const bool left_edge = gidx == 0 && s > 0, right_edge = gidx == V3_COLS - 1 && s + 1 < nstrips;
+    // the +P2 bias of OpenCV's C is folded out of the stored volume, exactly as in k_cost / k_path_v3
+    uint32_t Pv[NP], pa[NP], pb[NP], c[NP], acc[NP];
+    uint32_t mv = 0, ma = 0, mb = 0;
+    unsigned long long hq[NW];
+#pragma unroll
+    for (int k = 0; k < NP; k++) Pv[k] = 0;
+#pragma unroll
+    for (int k = 0; k < NW; k++) hq[k] = 0;
+    int stg = 0;
+    uint32_t ring_phase = 0;
+    for (int t = 0; t < g.H; t++) {
+        const int cur = t & 1, prv = cur ^ 1;
+        mbar_wait(&fullC[stg], ring_phase);
+        load_regs<NP>(ringC + ((size_t)stg * V3_COLS + gidx) * D + lane_off, c);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&emptyC[stg]);   // this warp holds its C values in registers
+        if (left_edge && t > 0) {
+#pragma unroll
+            for (int k = 0; k < NP; k++) pa[k] = (uint32_t)hq[k];
+            ma = (uint32_t)hq[NP];
+        } else {
+            load_regs<NP>(Xa + ((size_t)prv * (V3_COLS + 2) + gidx) * D + lane_off, pa);
+            ma = Ma[prv * (V3_COLS + 2) + gidx];
+        }
+        if (right_edge && t > 0) {
+#pragma unroll
+            for (int k = 0; k < NP; k++) pb[k] = (uint32_t)hq[k];
+            mb = (uint32_t)hq[NP];
+        } else {
+            load_regs<NP>(Xb + ((size_t)prv * (V3_COLS + 2) + gidx + 2) * D + lane_off, pb);
+            mb = Mb[prv * (V3_COLS + 2) + gidx + 2];
+        }
+        __syncwarp();
+        sgm_step<NP, G>(pa, ma, c, P1x2, P2x2, PADx2, lg);
+        if (!active) {
+#pragma unroll
+            for (int k = 0; k < NP; k++) pa[k] = 0;
+            ma = 0;
+        }
+        if (right_edge) {
+            unsigned long long* hp = Hptr(s + 1, cur, 0);
+#pragma unroll
+            for (int k = 0; k < NP; k++) halo_put(hp + k, pa[k], (uint32_t)(t + 1));
+            halo_put(hp + NP, ma, (uint32_t)(t + 1));
+        }
+        store_regs<NP>(Xa + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D + lane_off, pa);
+        if (lg == 0) Ma[cur * (V3_COLS + 2) + gidx + 1] = ma;
+        sgm_step<NP, G>(pb, mb, c, P1x2, P2x2, PADx2, lg);
+        if (!active) {
+#pragma unroll
+            for (int k = 0; k < NP; k++) pb[k] = 0;
+            mb = 0;
+        }
+        if (left_edge) {
+            unsigned long long* hp = Hptr(s - 1, cur, 1);
+#pragma unroll
+            for (int k = 0; k < NP; k++) halo_put(hp + k, pb[k], (uint32_t)(t + 1));
+            halo_put(hp + NP, mb, (uint32_t)(t + 1));
+        }
+        store_regs<NP>(Xb + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D + lane_off, pb);
+        if (lg == 0) Mb[cur * (V3_COLS + 2) + gidx + 1] = mb;
+        if (t + 1 < g.H) {
+            if (left_edge) halo_issue<NW>(Hptr(s, cur, 0), hq);
+            if (right_edge) halo_issue<NW>(Hptr(s, cur, 1), hq);
+        }
+#pragma unroll
+        for (int k = 0; k < NP; k++) acc[k] = __vminu2(__vadd2(pa[k], pb[k]), 0x7FFF7FFFu);
+        __syncwarp();
+        sgm_step<NP, G>(Pv, mv, c, P1x2, P2x2, PADx2, lg);
+#pragma unroll
+        for (int k = 0; k < NP; k++) acc[k] = __vminu2(__vadd2(acc[k], Pv[k]), 0x7FFF7FFFu);
+        if (active) store_regs<NP>(Sb + (size_t)t * rowstride, acc);
+        if (t + 1 < g.H) {
+            if (left_edge) halo_complete<NW>(Hptr(s, cur, 0), (uint32_t)(t + 1), err, hq);
+            if (right_edge) halo_complete<NW>(Hptr(s, cur, 1), (uint32_t)(t + 1), err, hq);
+        }
+        named_bar_sync(1, CF_CONS);   // the row's diagonal states are in shared memory
+        if (++stg == CF_NST) { stg = 0; ring_phase ^= 1; }
     }
 }
 
@@ -697,10 +993,10 @@ __device__ __forceinline__ void wta_pixel(const uint32_t (&Sr)[NP], int lg, cons
 
 // Horizontal chains: one group per output row. dir = +1 (L->R) accumulates into S;
 // dir = -1 (R->L) with WTA = true finishes S in registers and emits the raw disparity.
-template <int NP, int G, bool WTA>
-__global__ void __launch_bounds__(128) k_path_h(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int dir,
-                                                int accumulate, int16_t* __restrict__ dispraw, uint32_t* __restrict__ wta) {
-    constexpr int CPB = 128 / G;
+template <int NP, int G, bool WTA, int THREADS = 128>
+__global__ void __launch_bounds__(THREADS) k_path_h(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int dir,
+                                                    int accumulate, int16_t* __restrict__ dispraw, uint32_t* __restrict__ wta) {
+    constexpr int CPB = THREADS / G;
     __shared__ __align__(16) int16_t smS[WTA ? CPB * 2 * NP * G : 8];
     const int lane = threadIdx.x & 31, lg = lane & (G - 1);
     const int row = blockIdx.x * CPB + threadIdx.x / G;
@@ -760,16 +1056,18 @@ __global__ void __launch_bounds__(128) k_path_h(Geom g, const int16_t* __restric
 // group stages the next chunks of K steps of its row (K*D*2 contiguous bytes of C, and of S) with bulk async copies,
 // H_STAGES chunks deep, completion on a per-warp mbarrier. That keeps ~16 KB per warp in flight instead of the 2 KB a
 // one-step register prefetch gives, which is what the single-chain-per-row parallelism needs to reach HBM speed.
-constexpr int H_STAGES = 3;
+constexpr int H_STAGES_MAX = 4;
+constexpr int H_STAGES_DEFAULT = 3, H_WARPS_DEFAULT = 4, HB_THREADS_DEFAULT = 128;
 
 template <int NP, bool WTA>
 __global__ void __launch_bounds__(128) k_path_h2(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int dir, int accumulate,
-                                                 int K, int16_t* __restrict__ dispraw, uint32_t* __restrict__ wta) {
-    constexpr int G = 8, ROWS = 4, NWARP = 4;
+                                                 int K, int H_STAGES, int16_t* __restrict__ dispraw, uint32_t* __restrict__ wta) {
+    constexpr int G = 8, ROWS = 4, NWARP_MAX = 4;
     extern __shared__ __align__(128) uint8_t hsm[];
-    __shared__ __align__(8) uint64_t full[NWARP][H_STAGES];
-    __shared__ __align__(16) int16_t smS[WTA ? NWARP * ROWS * 2 * NP * G : 8];
+    __shared__ __align__(8) uint64_t full[NWARP_MAX][H_STAGES_MAX];
+    __shared__ __align__(16) int16_t smS[WTA ? NWARP_MAX * ROWS * 2 * NP * G : 8];
     const int D = g.D;
+    const int NWARP = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gidx = lane / G, lg = lane & (G - 1);
     const int row = (blockIdx.x * NWARP + warp) * ROWS + gidx;
     bool active = row < g.H;
@@ -798,10 +1096,9 @@ __global__ void __launch_bounds__(128) k_path_h2(Geom g, const int16_t* __restri
         if (dir > 0) { xlo = c * K; n = min(K, g.W1 - xlo); }
         else { const int xhi = g.W1 - 1 - c * K; xlo = max(xhi - K + 1, 0); n = xhi - xlo + 1; }
     };
-    auto issue = [&](int c) {   // lanes with lg == 0: one per row
+    auto issue = [&](int c, int st) {   // lanes with lg == 0: one per row; st = c mod H_STAGES
         int xlo, n;
         chunk_range(c, xlo, n);
-        const int st = c % H_STAGES;
         uint8_t* base = ring + (size_t)st * stage_bytes + (size_t)gidx * K * D * 2;
         const uint32_t bytes = (uint32_t)n * D * 2;
         mbar_expect_tx(&full[warp][st], accumulate ? 2 * bytes : bytes);
@@ -814,17 +1111,18 @@ __global__ void __launch_bounds__(128) k_path_h2(Geom g, const int16_t* __restri
     }
     __syncwarp();
     if (lg == 0)
-        for (int c = 0; c < H_STAGES && c < nchunks; c++) issue(c);
+        for (int c = 0; c < H_STAGES && c < nchunks; c++) issue(c, c);
     uint32_t P[NP], c_[NP], s_[NP], L[NP], m = 0;
 #pragma unroll
     for (int k = 0; k < NP; k++) { P[k] = 0; s_[k] = 0; }
     int16_t* sm = smS + (warp * ROWS + gidx) * 2 * NP * G;
     int x = dir > 0 ? 0 : g.W1 - 1;
+    int st = 0;
+    uint32_t ring_phase = 0;
     for (int c = 0; c < nchunks; c++) {
         int xlo, n;
         chunk_range(c, xlo, n);
-        const int st = c % H_STAGES;
-        mbar_wait(&full[warp][st], (uint32_t)((c / H_STAGES) & 1));
+        mbar_wait(&full[warp][st], ring_phase);
         const uint8_t* base = ring + (size_t)st * stage_bytes + (size_t)gidx * K * D * 2;
         for (int j = 0; j < n; j++) {
             const int jm = x - xlo;   // position of this step inside the staged run
@@ -847,7 +1145,8 @@ __global__ void __launch_bounds__(128) k_path_h2(Geom g, const int16_t* __restri
             x += dir;
         }
         __syncwarp();   // every lane is done reading this stage
-        if (lg == 0 && c + H_STAGES < nchunks) issue(c + H_STAGES);
+        if (lg == 0 && c + H_STAGES < nchunks) issue(c + H_STAGES, st);
+        if (++st == H_STAGES) { st = 0; ring_phase ^= 1; }
     }
 }
 
@@ -924,27 +1223,35 @@ int launch_path_h(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int1
                   int16_t* dispraw, uint32_t* wta) {
     constexpr int G = 8;
     static const bool legacy = getenv("SDR_PATH_H_LEGACY") != nullptr;   // A/B switch: register-prefetch version
-    const int K = std::max(1, 512 / g.D);                                 // steps per staged chunk: about 1 KB per row
-    const size_t smem = (size_t)4 * H_STAGES * 2 * 4 * K * g.D * 2;       // [warp][stage][C|S][row][K][D]
+    // tuning knobs (defaults chosen on a B200 at 1280x720x128, batch 8)
+    static const int env_k = getenv("SDR_H_K") ? atoi(getenv("SDR_H_K")) : 0;
+    static const int env_st = getenv("SDR_H_STAGES") ? atoi(getenv("SDR_H_STAGES")) : 0;
+    static const int env_w = getenv("SDR_H_WARPS") ? atoi(getenv("SDR_H_WARPS")) : 0;
+    static const int env_bt = getenv("SDR_HB_THREADS") ? atoi(getenv("SDR_HB_THREADS")) : 0;
+    const int K = env_k > 0 ? env_k : std::max(1, 512 / g.D);            // steps per staged chunk: about 1 KB per row
+    const int nst = env_st >= 2 && env_st <= H_STAGES_MAX ? env_st : H_STAGES_DEFAULT;
+    const int nwarp = env_w == 1 || env_w == 2 || env_w == 4 ? env_w : H_WARPS_DEFAULT;
+    const size_t smem = (size_t)nwarp * nst * 2 * 4 * K * g.D * 2;       // [warp][stage][C|S][row][K][D]
     // measured (1280x720x128, batch 8): L->R 1.12 -> 1.01 ms with the ring; the R->L + WTA kernel is bound by its own
     // dependent arithmetic and loses with the extra shared-memory hop (0.94 -> 1.52 ms), so it keeps the register prefetch
     if (!legacy && !wta_on && smem <= ctx->smem_optin) {
-        dim3 grid(div_up(g.H, 16), 1, batch);
-        if (wta_on) {
-            SDR_CUDA(ctx, cudaFuncSetAttribute(k_path_h2<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_path_h2<NP, true><<<grid, 128, smem, ctx->stream>>>(g, C, S, dir, acc, K, dispraw, wta);
-        } else {
-            SDR_CUDA(ctx, cudaFuncSetAttribute(k_path_h2<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_path_h2<NP, false><<<grid, 128, smem, ctx->stream>>>(g, C, S, dir, acc, K, dispraw, wta);
-        }
+        dim3 grid(div_up(g.H, 4 * nwarp), 1, batch);
+        SDR_CUDA(ctx, cudaFuncSetAttribute(k_path_h2<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_path_h2<NP, false><<<grid, 32 * nwarp, smem, ctx->stream>>>(g, C, S, dir, acc, K, nst, dispraw, wta);
         SDR_LAUNCHED(ctx);
         return SDR_OK;
     }
-    dim3 grid(div_up(g.H, 128 / G), 1, batch);
-    if (wta_on)
-        k_path_h<NP, G, true><<<grid, 128, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
-    else
-        k_path_h<NP, G, false><<<grid, 128, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
+    const int threads = env_bt == 32 || env_bt == 64 ? env_bt : HB_THREADS_DEFAULT;
+    dim3 grid(div_up(g.H, threads / G), 1, batch);
+    if (wta_on) {
+        if (threads == 32) k_path_h<NP, G, true, 32><<<grid, 32, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
+        else if (threads == 64) k_path_h<NP, G, true, 64><<<grid, 64, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
+        else k_path_h<NP, G, true, 128><<<grid, 128, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
+    } else {
+        if (threads == 32) k_path_h<NP, G, false, 32><<<grid, 32, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
+        else if (threads == 64) k_path_h<NP, G, false, 64><<<grid, 64, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
+        else k_path_h<NP, G, false, 128><<<grid, 128, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
+    }
     SDR_LAUNCHED(ctx);
     return SDR_OK;
 }
@@ -960,8 +1267,11 @@ int launch_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int
     constexpr int MINB = NP <= 8 ? 2 : 1;
     auto kern = acc ? k_path_v3<NP, MINB, true> : k_path_v3<NP, MINB, false>;
     const int nstrips = div_up(g.W1, V3_COLS);
+    static const int env_stages = getenv("SDR_V3_STAGES") ? atoi(getenv("SDR_V3_STAGES")) : 0;   // tuning knob
+    int nst = acc ? 3 : V3_STAGES_DEFAULT;
+    if (env_stages >= 2 && env_stages <= V3_STAGES_MAX) nst = acc ? std::min(env_stages, 3) : env_stages;
     const size_t smem = (size_t)4 * (V3_COLS + 2) * g.D * sizeof(int16_t) + (size_t)4 * (V3_COLS + 2) * sizeof(uint32_t) +
-                        (size_t)(acc ? 2 * 3 : V3_STAGES_MAX) * V3_COLS * g.D * sizeof(int16_t);
+                        (size_t)(acc ? 2 * nst : nst) * V3_COLS * g.D * sizeof(int16_t);
     if (smem > ctx->smem_optin) return -1;
     SDR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -984,12 +1294,61 @@ int launch_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int
         Geom gg = g;
         unsigned long long* halo = sc.halo.as<unsigned long long>();
         int* err = sc.err.as<int>();
-        void* args[] = {(void*)&gg, (void*)&C, (void*)&S, (void*)&diry, (void*)&b0, (void*)&halo, (void*)&err};
+        void* args[] = {(void*)&gg, (void*)&C, (void*)&S, (void*)&diry, (void*)&b0, (void*)&halo, (void*)&err, (void*)&nst};
         SDR_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3(nstrips, F, 1), dim3(256, 1, 1), args, smem, ctx->stream));
         ctx->launches++;
     }
     SDR_CUDA(ctx, cudaMemcpyAsync(sc.host_err.p, sc.err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     return SDR_OK;
+}
+
+// Fused cost + top-down sweep. Returns SDR_OK, an error, or -1 when this configuration is not covered (caller runs
+// k_cost followed by k_path_v3 / k_path_v instead).
+template <int NP, int SW2>
+int launch_cost_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int4* PL, const uint8_t* PR, int16_t* C, int16_t* S, V3Scratch& sc) {
+    auto kern = k_cost_path_v3<NP, SW2>;
+    const int nstrips = div_up(g.W1, V3_COLS);
+    const CfLayout lay = cf_layout(g.D, SW2, g.SH2);
+    if (lay.total > ctx->smem_optin) return -1;
+    SDR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+    int per_sm = 0;
+    SDR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CF_PROD + CF_CONS, lay.total));
+    const int cap = per_sm * ctx->sm_count;
+    if (cap < nstrips) return -1;
+    const int fpl = std::min(batch, cap / nstrips);
+    int rc;
+    const size_t halo_bytes = (size_t)nstrips * 4 * 8 * (NP + 1) * sizeof(unsigned long long);   // per frame
+    if ((rc = sc.halo.reserve(ctx, halo_bytes * fpl))) return rc;
+    if (!sc.err.p) {
+        if ((rc = sc.err.reserve(ctx, sizeof(int)))) return rc;
+        if ((rc = sc.host_err.reserve(ctx, sizeof(int)))) return rc;
+        *(int*)sc.host_err.p = 0;
+        SDR_CUDA(ctx, cudaMemsetAsync(sc.err.p, 0, sizeof(int), ctx->stream));
+    }
+    for (int b0 = 0; b0 < batch; b0 += fpl) {
+        const int F = std::min(fpl, batch - b0);
+        SDR_CUDA(ctx, cudaMemsetAsync(sc.halo.p, 0, halo_bytes * F, ctx->stream));
+        Geom gg = g;
+        unsigned long long* halo = sc.halo.as<unsigned long long>();
+        int* err = sc.err.as<int>();
+        void* args[] = {(void*)&gg, (void*)&PL, (void*)&PR, (void*)&C, (void*)&S, (void*)&b0, (void*)&halo, (void*)&err};
+        SDR_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3(nstrips, F, 1), dim3(CF_PROD + CF_CONS, 1, 1), args, lay.total,
+                                                  ctx->stream));
+        ctx->launches++;
+    }
+    SDR_CUDA(ctx, cudaMemcpyAsync(sc.host_err.p, sc.err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return SDR_OK;
+}
+
+int launch_cost_path_fused(sdr_ctx* ctx, const Geom& g, int batch, const int4* PL, const uint8_t* PR, int16_t* C, int16_t* S, V3Scratch& sc) {
+    if (g.nseg != 1 || g.SW2 != g.SH2 || g.seg[0].src_start != 0 || g.crows != g.H) return -1;
+    const int np = g.D / 16;
+    if (g.D % 16) return -1;
+    if (np == 8 && g.SW2 == 2) return launch_cost_path_v3<8, 2>(ctx, g, batch, PL, PR, C, S, sc);
+    if (np == 8 && g.SW2 == 1) return launch_cost_path_v3<8, 1>(ctx, g, batch, PL, PR, C, S, sc);
+    if (np == 4 && g.SW2 == 2) return launch_cost_path_v3<4, 2>(ctx, g, batch, PL, PR, C, S, sc);
+    if (np == 4 && g.SW2 == 1) return launch_cost_path_v3<4, 1>(ctx, g, batch, PL, PR, C, S, sc);
+    return -1;
 }
 
 #define NP_SWITCH(np, CALL)                                                              \
@@ -1025,6 +1384,7 @@ struct sdr_sgbm {
     SpeckleScratch speckle;
     V3Scratch v3;
     bool use_fused_sweep = true;
+    bool use_cost_fusion = true;               // cost volume + top-down sweep in one kernel (k_cost_path_v3)
     int stripe_first = 0, stripe_count = -1;   // MODE_SGBM_3WAY: subset of the four stripes to match (-1 = all)
     bool skip_post = false;                    // stop after the raw matcher output (median / speckle run elsewhere)
     DevBuf post_in;
@@ -1062,6 +1422,7 @@ extern "C" int sdr_sgbm_create(sdr_ctx* ctx, const sdr_sgbm_params* params, sdr_
     m->ctx = ctx;
     m->p = *params;
     m->use_fused_sweep = getenv("SDR_DISABLE_FUSED_SWEEP") == nullptr;   // A/B switch for the cooperative sweep
+    m->use_cost_fusion = getenv("SDR_DISABLE_COST_FUSION") == nullptr;   // A/B switch for the fused cost + sweep kernel
     *out = m;
     return SDR_OK;
 }
@@ -1166,7 +1527,23 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
                                                                          m->PL.as<int4>(), m->PR.as<uint8_t>());
         SDR_LAUNCHED(ctx);
         m->timer.mark(st, "prefilter");
-        {
+        const int16_t* C = m->C.as<int16_t>();
+        int16_t* S = m->S.as<int16_t>();
+        const int np = path_cfg(g.D).NP;
+        // a previous fused sweep that timed out on its neighbour flags poisons the handle
+        if (m->v3.host_err.p && *(volatile int*)m->v3.host_err.p)
+            return SDR_FAIL(ctx, SDR_ECUDA, "fused path sweep timed out waiting for a neighbouring strip");
+        // MODE_SGBM / MODE_HH: cost volume and top-down sweep in one kernel when the configuration is covered
+        bool cost_done = false;
+        if (m->p.mode != SDR_MODE_SGBM_3WAY && m->use_fused_sweep && m->use_cost_fusion) {
+            rc = launch_cost_path_fused(ctx, g, batch, m->PL.as<int4>(), m->PR.as<uint8_t>(), m->C.as<int16_t>(), S, m->v3);
+            if (rc > 0) return rc;
+            if (rc == SDR_OK) {
+                cost_done = true;
+                m->timer.mark(st, "cost_path_v_fused");
+            }
+        }
+        if (!cost_done) {
             const int n = 2 * g.SH2 + 1, DQ = g.D / 8;
             const int nthr = (256 / DQ) * DQ, XG = nthr / DQ;
             const int items = div_up(COST_TXH, XG);
@@ -1189,21 +1566,15 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
             SDR_LAUNCHED(ctx);
             m->timer.mark(st, "cost");
         }
-        const int16_t* C = m->C.as<int16_t>();
-        int16_t* S = m->S.as<int16_t>();
-        const int np = path_cfg(g.D).NP;
         // direction list: {dirx, diry}; the first one initialises S
         if (m->p.mode == SDR_MODE_SGBM_3WAY) {
             NP_SWITCH(np, rc = launch_path_v<NPc>(ctx, g, batch, C, S, 0, +1, 0));
             if (rc) return rc;
             m->timer.mark(st, "path_v");
         } else {
-            // a previous fused sweep that timed out on its neighbour flags poisons the handle
-            if (m->v3.host_err.p && *(volatile int*)m->v3.host_err.p)
-                return SDR_FAIL(ctx, SDR_ECUDA, "fused path sweep timed out waiting for a neighbouring strip");
             const int npass = m->p.mode == SDR_MODE_HH ? 2 : 1;
             bool fused = m->use_fused_sweep;
-            for (int pass = 0; pass < npass && fused; pass++) {
+            for (int pass = cost_done ? 1 : 0; pass < npass && fused; pass++) {
                 NP_SWITCH(np, rc = launch_path_v3<NPc>(ctx, g, batch, C, S, pass == 0 ? +1 : -1, pass, m->v3));
                 if (rc == -1) { fused = false; break; }   // grid cannot be co-resident: separate launches per direction
                 if (rc) return rc;
@@ -1212,7 +1583,7 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
             if (!fused) {
                 const int dirs[6][2] = {{0, +1}, {+1, +1}, {-1, +1}, {0, -1}, {+1, -1}, {-1, -1}};
                 const int nd = m->p.mode == SDR_MODE_HH ? 6 : 3;
-                for (int i = 0; i < nd; i++) {
+                for (int i = cost_done ? 3 : 0; i < nd; i++) {
                     NP_SWITCH(np, rc = launch_path_v<NPc>(ctx, g, batch, C, S, dirs[i][0], dirs[i][1], i > 0));
                     if (rc) return rc;
                     m->timer.mark(st, i == 0 ? "path_v0" : i == 1 ? "path_v1" : i == 2 ? "path_v2" : i == 3 ? "path_v3" : i == 4 ? "path_v4" : "path_v5");

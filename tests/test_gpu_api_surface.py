@@ -26,10 +26,12 @@ def test_caller_stream_timers_and_launch_count(orc):
         e1.record(s)
     s.synchronize()                                   # the library ran on the caller's stream: torch events bracket it
     assert np.array_equal(O.cpu().numpy(), orc.sgbm_compute(l, r, orc.make_params(*args)))
-    assert c.kernel_launches - n0 >= 8
     st = dict(m.stage_times())
-    for k in ("prefilter", "cost", "path_v_fused_down", "path_h_fwd", "path_h_bwd_wta", "lrcheck", "median3", "speckle"):
+    # cost volume + top-down sweep run as one kernel where the configuration is covered, else as two
+    assert ("cost_path_v_fused" in st) or ("cost" in st and "path_v_fused_down" in st), st
+    for k in ("prefilter", "path_h_fwd", "path_h_bwd_wta", "lrcheck", "median3", "speckle"):
         assert k in st and st[k] > 0, k
+    assert c.kernel_launches - n0 >= 7
     assert e0.elapsed_time(e1) >= 0.9 * sum(st.values())
     m.close(); c.close()
 
