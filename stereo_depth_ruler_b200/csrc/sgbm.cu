@@ -635,15 +635,15 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
 
 // ---- fused cost + top-down sweep ---------------------------------------------------------------------------------
 // One CTA = one 32-column strip of one frame, 12 warps in two roles:
-//   warps 8-11 (producer, 128 threads): BT pixel cost -> vertical running box sum -> horizontal box sum for the strip's
+//   first warps (producer, CF_PROD threads): BT pixel cost -> vertical running box sum -> horizontal box sum for the strip's
 //       32 columns (+2*SW2 halo columns), one image row after the other, into a ring of C row tiles in shared memory;
 //       every finished tile is also written to the C volume in HBM (one TMA bulk store) for the horizontal kernels;
-//   warps 0-7 (consumer, 256 threads): the three top-down paths of k_path_v3 reading C from that ring.
+//   last 8 warps (consumer, 256 threads): the three top-down paths of k_path_v3 reading C from that ring.
 // The sweep alone leaves ~60 % of the issue slots idle (it waits for its neighbours' halos every row) and the cost
 // kernel alone is issue-bound: in one kernel the producer fills those slots, and the sweep's read of C from HBM
 // (one volume pass) disappears. Registers are split with setmaxnreg (producer 64, consumer 88 per thread).
+constexpr int CF_PROD_DEFAULT = 256;
 constexpr int CF_NST = 3;          // C row tiles in flight between producer and consumer
-constexpr int CF_PROD = 128;       // producer threads
 constexpr int CF_CONS = 256;       // consumer threads (32 columns x 8 lanes)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -677,10 +677,10 @@ __host__ __device__ inline CfLayout cf_layout(int D, int SW2, int SH2) {
     return L;
 }
 
-template <int NP, int SW2>
+template <int NP, int SW2, int CF_PROD>
 __global__ void __launch_bounds__(CF_PROD + CF_CONS, 2)
 k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ PR, int16_t* __restrict__ C, int16_t* __restrict__ S, int b0,
-               unsigned long long* halo, int* err) {
+               unsigned long long* halo, int* err, int dbg) {
     constexpr int G = 8, NW = NP + 1, D = 16 * NP, DQ = D / 8;
     constexpr int XG = CF_PROD / DQ;            // producer column groups
     constexpr int CPT = V3_COLS / XG;           // consecutive output columns per producer thread
@@ -710,10 +710,14 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
     __syncthreads();
     const uint32_t tile_bytes = (uint32_t)(min(V3_COLS, g.W1 - x0) * D * 2);
 
-    if (threadIdx.x >= CF_CONS) {
+    // Producer warps come first: the SM's warp arbiter favours the higher warp slots, which gives the latency-critical
+    // consumer chain priority while the producer's independent arithmetic fills the remaining issue slots.
+    if (threadIdx.x < CF_PROD) {
         // =============================== producer: cost rows ===============================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
-        const int tid = threadIdx.x - CF_CONS;
+        // register split (per thread): 128 producers 64 / consumers 88 (launch 80); 256 producers 48 / consumers 80 (launch 64)
+        if constexpr (CF_PROD == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;\n");
+        const int tid = threadIdx.x;
         const int q = tid % DQ, xg = tid / DQ;
         uint8_t* stage = cfsm + lay.off_stage;
         uint8_t* ring8 = cfsm + lay.off_ring8;                 // [n][CW][D] u8
@@ -745,7 +749,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             bulk_g2s(st, PL + ((size_t)b * g.H + rc) * g.W + lo + g.minX1, pl_bytes, &fullIn[i & 1]);
             bulk_g2s(st + CW * 16, PR + (((size_t)b * g.H + rc) * (g.Wp >> 4) + cs) * PR_CHUNK, pr_bytes, &fullIn[i & 1]);
         };
-        if (tid == 0) {
+        if (tid == 0 && !(dbg & 64)) {
             issue_in(0);
             if (NV > 1) issue_in(1);
         }
@@ -753,12 +757,12 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
         uint32_t cphase = 0;
         for (int i = 0; i < NV; i++) {
             const uint8_t* st = stage + (size_t)(i & 1) * lay.stage_bytes;
-            mbar_wait(&fullIn[i & 1], (uint32_t)((i >> 1) & 1));
+            if (!(dbg & 64)) mbar_wait(&fullIn[i & 1], (uint32_t)((i >> 1) & 1));
             const int4* pls = (const int4*)st;
             const uint8_t* prs = st + CW * 16;
 #pragma unroll
             for (int k = 0; k < ITEMS; k++) {
-                if (k < CPT || xg < NX) {
+                if ((k < CPT || xg < NX) && !(dbg & 2)) {
                     const int h = k < CPT ? CPT * xg + k : V3_COLS + xg;
                     const int o0 = (int)(tab[k] & 0xFFFFu), ix = (int)((tab[k] >> 16) & 0x7FFFu);
                     const int o1 = o0 + ((int)tab[k] < 0 ? PR_CHUNK - 12 : 4);
@@ -787,7 +791,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
                 if (tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(CF_NST - 1) : "memory");
             }
             named_bar_sync(2, CF_PROD);   // Vs complete; every producer thread is done with this input stage
-            if (tid == 0 && i + 2 < NV) issue_in(i + 2);
+            if (tid == 0 && i + 2 < NV && !(dbg & 64)) issue_in(i + 2);
             if (y >= 0) {
                 if (y >= CF_NST) mbar_wait(&emptyC[cst], cphase ^ 1);   // consumers released the slot (use number y/NST - 1)
                 // horizontal box sum: window of CPT + NX columns = own columns (registers) + NX right neighbours (Vs)
@@ -815,11 +819,13 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
                     }
                     *(uint4*)(ct + (size_t)(CPT * xg + k) * D + 8 * q) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
+                if (!(dbg & 16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
                 named_bar_sync(3, CF_PROD);   // tile complete (and every read of Vs is done)
                 if (tid == 0) {
+                    if (!(dbg & 8)) {
                     bulk_s2g(C + (((size_t)b * g.crows + y) * g.W1 + x0) * D, ct, tile_bytes);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
                     mbar_arrive(&fullC[cst]);
                 }
                 if (++cst == CF_NST) { cst = 0; cphase ^= 1; }
@@ -830,8 +836,10 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
     }
 
     // =============================== consumer: the three top-down paths ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;\n");
-    const int gidx = threadIdx.x / G, lg = threadIdx.x & (G - 1);
+    if constexpr (CF_PROD == 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;\n");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 80;\n");
+    const int ct = threadIdx.x - CF_PROD;
+    const int gidx = ct / G, lg = ct & (G - 1);
     const int x = x0 + gidx;
     const bool active = x < g.W1;
     const int xl = min(x, g.W1 - 1);
@@ -845,7 +853,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
     };
     int16_t* Sb = S + (size_t)b * g.H * g.W1 * D + (size_t)xl * D + lane_off;
     const size_t rowstride = (size_t)g.W1 * D;
-    const bool left_edge = gidx == 0 && s > 0, right_edge = gidx == V3_COLS - 1 && s + 1 < nstrips;
+    const bool left_edge = gidx == 0 && s > 0 && !(dbg & 1), right_edge = gidx == V3_COLS - 1 && s + 1 < nstrips && !(dbg & 1);
     // the +P2 bias of OpenCV's C is folded out of the stored volume, exactly as in k_cost / k_path_v3
     uint32_t Pv[NP], pa[NP], pb[NP], c[NP], acc[NP];
     uint32_t mv = 0, ma = 0, mb = 0;
@@ -879,7 +887,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             mb = Mb[prv * (V3_COLS + 2) + gidx + 2];
         }
         __syncwarp();
-        sgm_step<NP, G>(pa, ma, c, P1x2, P2x2, PADx2, lg);
+        if (!(dbg & 4)) sgm_step<NP, G>(pa, ma, c, P1x2, P2x2, PADx2, lg);
         if (!active) {
 #pragma unroll
             for (int k = 0; k < NP; k++) pa[k] = 0;
@@ -893,7 +901,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
         }
         store_regs<NP>(Xa + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D + lane_off, pa);
         if (lg == 0) Ma[cur * (V3_COLS + 2) + gidx + 1] = ma;
-        sgm_step<NP, G>(pb, mb, c, P1x2, P2x2, PADx2, lg);
+        if (!(dbg & 4)) sgm_step<NP, G>(pb, mb, c, P1x2, P2x2, PADx2, lg);
         if (!active) {
 #pragma unroll
             for (int k = 0; k < NP; k++) pb[k] = 0;
@@ -914,10 +922,10 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
 #pragma unroll
         for (int k = 0; k < NP; k++) acc[k] = __vminu2(__vadd2(pa[k], pb[k]), 0x7FFF7FFFu);
         __syncwarp();
-        sgm_step<NP, G>(Pv, mv, c, P1x2, P2x2, PADx2, lg);
+        if (!(dbg & 4)) sgm_step<NP, G>(Pv, mv, c, P1x2, P2x2, PADx2, lg);
 #pragma unroll
         for (int k = 0; k < NP; k++) acc[k] = __vminu2(__vadd2(acc[k], Pv[k]), 0x7FFF7FFFu);
-        if (active) store_regs<NP>(Sb + (size_t)t * rowstride, acc);
+        if (active && !(dbg & 32)) store_regs<NP>(Sb + (size_t)t * rowstride, acc);
         if (t + 1 < g.H) {
             if (left_edge) halo_complete<NW>(Hptr(s, cur, 0), (uint32_t)(t + 1), err, hq);
             if (right_edge) halo_complete<NW>(Hptr(s, cur, 1), (uint32_t)(t + 1), err, hq);
@@ -1057,7 +1065,7 @@ __global__ void __launch_bounds__(THREADS) k_path_h(Geom g, const int16_t* __res
 // H_STAGES chunks deep, completion on a per-warp mbarrier. That keeps ~16 KB per warp in flight instead of the 2 KB a
 // one-step register prefetch gives, which is what the single-chain-per-row parallelism needs to reach HBM speed.
 constexpr int H_STAGES_MAX = 4;
-constexpr int H_STAGES_DEFAULT = 3, H_WARPS_DEFAULT = 4, HB_THREADS_DEFAULT = 128;
+constexpr int H_STAGES_DEFAULT = 2, H_WARPS_DEFAULT = 2, HB_THREADS_DEFAULT = 32;   // B200 sweep at 1280x720x128, batch 8 (tools/tune_env.py)
 
 template <int NP, bool WTA>
 __global__ void __launch_bounds__(128) k_path_h2(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int dir, int accumulate,
@@ -1304,9 +1312,9 @@ int launch_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int
 
 // Fused cost + top-down sweep. Returns SDR_OK, an error, or -1 when this configuration is not covered (caller runs
 // k_cost followed by k_path_v3 / k_path_v instead).
-template <int NP, int SW2>
+template <int NP, int SW2, int CF_PROD>
 int launch_cost_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int4* PL, const uint8_t* PR, int16_t* C, int16_t* S, V3Scratch& sc) {
-    auto kern = k_cost_path_v3<NP, SW2>;
+    auto kern = k_cost_path_v3<NP, SW2, CF_PROD>;
     const int nstrips = div_up(g.W1, V3_COLS);
     const CfLayout lay = cf_layout(g.D, SW2, g.SH2);
     if (lay.total > ctx->smem_optin) return -1;
@@ -1331,7 +1339,9 @@ int launch_cost_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int4* PL, 
         Geom gg = g;
         unsigned long long* halo = sc.halo.as<unsigned long long>();
         int* err = sc.err.as<int>();
-        void* args[] = {(void*)&gg, (void*)&PL, (void*)&PR, (void*)&C, (void*)&S, (void*)&b0, (void*)&halo, (void*)&err};
+        static const int dbg_env = getenv("SDR_CF_DEBUG") ? atoi(getenv("SDR_CF_DEBUG")) : 0;   // experiments only (1: no halo exchange, wrong results)
+        int dbg = dbg_env;
+        void* args[] = {(void*)&gg, (void*)&PL, (void*)&PR, (void*)&C, (void*)&S, (void*)&b0, (void*)&halo, (void*)&err, (void*)&dbg};
         SDR_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3(nstrips, F, 1), dim3(CF_PROD + CF_CONS, 1, 1), args, lay.total,
                                                   ctx->stream));
         ctx->launches++;
@@ -1344,10 +1354,14 @@ int launch_cost_path_fused(sdr_ctx* ctx, const Geom& g, int batch, const int4* P
     if (g.nseg != 1 || g.SW2 != g.SH2 || g.seg[0].src_start != 0 || g.crows != g.H) return -1;
     const int np = g.D / 16;
     if (g.D % 16) return -1;
-    if (np == 8 && g.SW2 == 2) return launch_cost_path_v3<8, 2>(ctx, g, batch, PL, PR, C, S, sc);
-    if (np == 8 && g.SW2 == 1) return launch_cost_path_v3<8, 1>(ctx, g, batch, PL, PR, C, S, sc);
-    if (np == 4 && g.SW2 == 2) return launch_cost_path_v3<4, 2>(ctx, g, batch, PL, PR, C, S, sc);
-    if (np == 4 && g.SW2 == 1) return launch_cost_path_v3<4, 1>(ctx, g, batch, PL, PR, C, S, sc);
+    static const int env_prod = getenv("SDR_CF_PROD") ? atoi(getenv("SDR_CF_PROD")) : 0;   // tuning knob: producer threads (128 | 256)
+    const int prod = env_prod == 128 || env_prod == 256 ? env_prod : CF_PROD_DEFAULT;
+#define CF_CASE(NPV, SWV)                                                                                                  \
+    if (np == NPV && g.SW2 == SWV)                                                                                         \
+        return prod == 128 ? launch_cost_path_v3<NPV, SWV, 128>(ctx, g, batch, PL, PR, C, S, sc)                          \
+                           : launch_cost_path_v3<NPV, SWV, 256>(ctx, g, batch, PL, PR, C, S, sc);
+    CF_CASE(8, 2) CF_CASE(8, 1) CF_CASE(4, 2) CF_CASE(4, 1)
+#undef CF_CASE
     return -1;
 }
 
