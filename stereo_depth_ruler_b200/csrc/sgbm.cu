@@ -680,7 +680,7 @@ __host__ __device__ inline CfLayout cf_layout(int D, int SW2, int SH2) {
 template <int NP, int SW2, int CF_PROD>
 __global__ void __launch_bounds__(CF_PROD + CF_CONS, 2)
 k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ PR, int16_t* __restrict__ C, int16_t* __restrict__ S, int b0,
-               unsigned long long* halo, int* err, int dbg) {
+               unsigned long long* halo, int* err) {
     constexpr int G = 8, NW = NP + 1, D = 16 * NP, DQ = D / 8;
     constexpr int XG = CF_PROD / DQ;            // producer column groups
     constexpr int CPT = V3_COLS / XG;           // consecutive output columns per producer thread
@@ -749,7 +749,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             bulk_g2s(st, PL + ((size_t)b * g.H + rc) * g.W + lo + g.minX1, pl_bytes, &fullIn[i & 1]);
             bulk_g2s(st + CW * 16, PR + (((size_t)b * g.H + rc) * (g.Wp >> 4) + cs) * PR_CHUNK, pr_bytes, &fullIn[i & 1]);
         };
-        if (tid == 0 && !(dbg & 64)) {
+        if (tid == 0) {
             issue_in(0);
             if (NV > 1) issue_in(1);
         }
@@ -757,12 +757,12 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
         uint32_t cphase = 0;
         for (int i = 0; i < NV; i++) {
             const uint8_t* st = stage + (size_t)(i & 1) * lay.stage_bytes;
-            if (!(dbg & 64)) mbar_wait(&fullIn[i & 1], (uint32_t)((i >> 1) & 1));
+            mbar_wait(&fullIn[i & 1], (uint32_t)((i >> 1) & 1));
             const int4* pls = (const int4*)st;
             const uint8_t* prs = st + CW * 16;
 #pragma unroll
             for (int k = 0; k < ITEMS; k++) {
-                if ((k < CPT || xg < NX) && !(dbg & 2)) {
+                if (k < CPT || xg < NX) {
                     const int h = k < CPT ? CPT * xg + k : V3_COLS + xg;
                     const int o0 = (int)(tab[k] & 0xFFFFu), ix = (int)((tab[k] >> 16) & 0x7FFFu);
                     const int o1 = o0 + ((int)tab[k] < 0 ? PR_CHUNK - 12 : 4);
@@ -791,7 +791,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
                 if (tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(CF_NST - 1) : "memory");
             }
             named_bar_sync(2, CF_PROD);   // Vs complete; every producer thread is done with this input stage
-            if (tid == 0 && i + 2 < NV && !(dbg & 64)) issue_in(i + 2);
+            if (tid == 0 && i + 2 < NV) issue_in(i + 2);
             if (y >= 0) {
                 if (y >= CF_NST) mbar_wait(&emptyC[cst], cphase ^ 1);   // consumers released the slot (use number y/NST - 1)
                 // horizontal box sum: window of CPT + NX columns = own columns (registers) + NX right neighbours (Vs)
@@ -819,13 +819,11 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
                     }
                     *(uint4*)(ct + (size_t)(CPT * xg + k) * D + 8 * q) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
                 }
-                if (!(dbg & 16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
                 named_bar_sync(3, CF_PROD);   // tile complete (and every read of Vs is done)
                 if (tid == 0) {
-                    if (!(dbg & 8)) {
                     bulk_s2g(C + (((size_t)b * g.crows + y) * g.W1 + x0) * D, ct, tile_bytes);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
                     mbar_arrive(&fullC[cst]);
                 }
                 if (++cst == CF_NST) { cst = 0; cphase ^= 1; }
@@ -853,7 +851,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
     };
     int16_t* Sb = S + (size_t)b * g.H * g.W1 * D + (size_t)xl * D + lane_off;
     const size_t rowstride = (size_t)g.W1 * D;
-    const bool left_edge = gidx == 0 && s > 0 && !(dbg & 1), right_edge = gidx == V3_COLS - 1 && s + 1 < nstrips && !(dbg & 1);
+    const bool left_edge = gidx == 0 && s > 0, right_edge = gidx == V3_COLS - 1 && s + 1 < nstrips;
     // the +P2 bias of OpenCV's C is folded out of the stored volume, exactly as in k_cost / k_path_v3
     uint32_t Pv[NP], pa[NP], pb[NP], c[NP], acc[NP];
     uint32_t mv = 0, ma = 0, mb = 0;
@@ -887,7 +885,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             mb = Mb[prv * (V3_COLS + 2) + gidx + 2];
         }
         __syncwarp();
-        if (!(dbg & 4)) sgm_step<NP, G>(pa, ma, c, P1x2, P2x2, PADx2, lg);
+        sgm_step<NP, G>(pa, ma, c, P1x2, P2x2, PADx2, lg);
         if (!active) {
 #pragma unroll
             for (int k = 0; k < NP; k++) pa[k] = 0;
@@ -901,7 +899,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
         }
         store_regs<NP>(Xa + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D + lane_off, pa);
         if (lg == 0) Ma[cur * (V3_COLS + 2) + gidx + 1] = ma;
-        if (!(dbg & 4)) sgm_step<NP, G>(pb, mb, c, P1x2, P2x2, PADx2, lg);
+        sgm_step<NP, G>(pb, mb, c, P1x2, P2x2, PADx2, lg);
         if (!active) {
 #pragma unroll
             for (int k = 0; k < NP; k++) pb[k] = 0;
@@ -922,10 +920,10 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
 #pragma unroll
         for (int k = 0; k < NP; k++) acc[k] = __vminu2(__vadd2(pa[k], pb[k]), 0x7FFF7FFFu);
         __syncwarp();
-        if (!(dbg & 4)) sgm_step<NP, G>(Pv, mv, c, P1x2, P2x2, PADx2, lg);
+        sgm_step<NP, G>(Pv, mv, c, P1x2, P2x2, PADx2, lg);
 #pragma unroll
         for (int k = 0; k < NP; k++) acc[k] = __vminu2(__vadd2(acc[k], Pv[k]), 0x7FFF7FFFu);
-        if (active && !(dbg & 32)) store_regs<NP>(Sb + (size_t)t * rowstride, acc);
+        if (active) store_regs<NP>(Sb + (size_t)t * rowstride, acc);
         if (t + 1 < g.H) {
             if (left_edge) halo_complete<NW>(Hptr(s, cur, 0), (uint32_t)(t + 1), err, hq);
             if (right_edge) halo_complete<NW>(Hptr(s, cur, 1), (uint32_t)(t + 1), err, hq);
@@ -1065,7 +1063,8 @@ __global__ void __launch_bounds__(THREADS) k_path_h(Geom g, const int16_t* __res
 // H_STAGES chunks deep, completion on a per-warp mbarrier. That keeps ~16 KB per warp in flight instead of the 2 KB a
 // one-step register prefetch gives, which is what the single-chain-per-row parallelism needs to reach HBM speed.
 constexpr int H_STAGES_MAX = 4;
-constexpr int H_STAGES_DEFAULT = 2, H_WARPS_DEFAULT = 2, HB_THREADS_DEFAULT = 32;   // B200 sweep at 1280x720x128, batch 8 (tools/tune_env.py)
+constexpr int H_STAGES_DEFAULT = 2, H_WARPS_DEFAULT = 2, HB_THREADS_DEFAULT = 32;
+constexpr bool HB_RING_DEFAULT = false;   // R->L + WTA through the TMA ring: 0.99 ms vs 0.93 ms with the register prefetch   // B200 sweep at 1280x720x128, batch 8 (tools/tune_env.py)
 
 template <int NP, bool WTA>
 __global__ void __launch_bounds__(128) k_path_h2(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int dir, int accumulate,
@@ -1242,14 +1241,20 @@ int launch_path_h(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int1
     const size_t smem = (size_t)nwarp * nst * 2 * 4 * K * g.D * 2;       // [warp][stage][C|S][row][K][D]
     // measured (1280x720x128, batch 8): L->R 1.12 -> 1.01 ms with the ring; the R->L + WTA kernel is bound by its own
     // dependent arithmetic and loses with the extra shared-memory hop (0.94 -> 1.52 ms), so it keeps the register prefetch
-    if (!legacy && !wta_on && smem <= ctx->smem_optin) {
+    static const bool wta_ring = getenv("SDR_HB_RING") ? atoi(getenv("SDR_HB_RING")) != 0 : HB_RING_DEFAULT;
+    if (!legacy && (!wta_on || wta_ring) && smem <= ctx->smem_optin) {
         dim3 grid(div_up(g.H, 4 * nwarp), 1, batch);
-        SDR_CUDA(ctx, cudaFuncSetAttribute(k_path_h2<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_path_h2<NP, false><<<grid, 32 * nwarp, smem, ctx->stream>>>(g, C, S, dir, acc, K, nst, dispraw, wta);
+        if (wta_on) {
+            SDR_CUDA(ctx, cudaFuncSetAttribute(k_path_h2<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_path_h2<NP, true><<<grid, 32 * nwarp, smem, ctx->stream>>>(g, C, S, dir, acc, K, nst, dispraw, wta);
+        } else {
+            SDR_CUDA(ctx, cudaFuncSetAttribute(k_path_h2<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_path_h2<NP, false><<<grid, 32 * nwarp, smem, ctx->stream>>>(g, C, S, dir, acc, K, nst, dispraw, wta);
+        }
         SDR_LAUNCHED(ctx);
         return SDR_OK;
     }
-    const int threads = env_bt == 32 || env_bt == 64 ? env_bt : HB_THREADS_DEFAULT;
+    const int threads = env_bt == 32 || env_bt == 64 || env_bt == 128 ? env_bt : HB_THREADS_DEFAULT;
     dim3 grid(div_up(g.H, threads / G), 1, batch);
     if (wta_on) {
         if (threads == 32) k_path_h<NP, G, true, 32><<<grid, 32, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
@@ -1339,9 +1344,7 @@ int launch_cost_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int4* PL, 
         Geom gg = g;
         unsigned long long* halo = sc.halo.as<unsigned long long>();
         int* err = sc.err.as<int>();
-        static const int dbg_env = getenv("SDR_CF_DEBUG") ? atoi(getenv("SDR_CF_DEBUG")) : 0;   // experiments only (1: no halo exchange, wrong results)
-        int dbg = dbg_env;
-        void* args[] = {(void*)&gg, (void*)&PL, (void*)&PR, (void*)&C, (void*)&S, (void*)&b0, (void*)&halo, (void*)&err, (void*)&dbg};
+        void* args[] = {(void*)&gg, (void*)&PL, (void*)&PR, (void*)&C, (void*)&S, (void*)&b0, (void*)&halo, (void*)&err};
         SDR_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3(nstrips, F, 1), dim3(CF_PROD + CF_CONS, 1, 1), args, lay.total,
                                                   ctx->stream));
         ctx->launches++;
