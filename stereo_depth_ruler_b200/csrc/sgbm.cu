@@ -152,7 +152,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "SDR_MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"   // suspend-time hint: sleep in hardware until the phase completes
         "@p bra SDR_MBAR_DONE;\n"
         "bra SDR_MBAR_WAIT;\n"
         "SDR_MBAR_DONE:\n"
@@ -356,6 +356,31 @@ __device__ __forceinline__ void store_regs(int16_t* p, const uint32_t (&r)[NP]) 
     }
 }
 
+// Shared-memory copy of one column's D path costs held by G = 8 lanes x NP registers, laid out so that every 128-bit
+// access of a quarter-warp covers 128 contiguous bytes: register quad q of lane lg sits at int16 offset (q*8 + lg)*8.
+// (The natural layout -- lane lg's 2*NP values contiguous -- makes lanes lg and lg+4 hit the same banks when NP = 8.)
+template <int NP>
+__device__ __forceinline__ void load_col_sm(const int16_t* col, int lg, uint32_t (&r)[NP]) {
+    if constexpr (NP % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < NP / 4; q++) {
+            const uint4 v = *(const uint4*)(col + (q * 8 + lg) * 8);
+            r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+        }
+    } else {
+        load_regs<NP>(col + lg * 2 * NP, r);
+    }
+}
+template <int NP>
+__device__ __forceinline__ void store_col_sm(int16_t* col, int lg, const uint32_t (&r)[NP]) {
+    if constexpr (NP % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < NP / 4; q++) *(uint4*)(col + (q * 8 + lg) * 8) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+    } else {
+        store_regs<NP>(col + lg * 2 * NP, r);
+    }
+}
+
 // One path step, in place: on entry P = L of the previous pixel on the path and m = its minimum (packed in both halves);
 // on exit P = L of this pixel and m = its minimum.
 //   L[d] = C[d] + min( min(P[d], min(P[d-1], P[d+1]) + P1) - m, P2 )
@@ -469,14 +494,14 @@ constexpr int V3_SPIN_LIMIT = 1 << 22;
 // separate flag is needed: the reader polls the word until the sequence matches (single-copy-atomic 8-byte accesses).
 __device__ __forceinline__ void halo_put(unsigned long long* p, uint32_t data, uint32_t seq) {
     const unsigned long long v = ((unsigned long long)seq << 32) | data;
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // Halo reads: all words of a lane are requested back to back (one L2 round trip), the sequence numbers are checked
 // later (halo_ready), and only a stale word triggers the bounded re-poll.
 template <int NW>
 __device__ __forceinline__ void halo_issue(const unsigned long long* p, unsigned long long (&v)[NW]) {
 #pragma unroll
-    for (int k = 0; k < NW; k++) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v[k]) : "l"(p + k) : "memory");
+    for (int k = 0; k < NW; k++) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v[k]) : "l"(p + k) : "memory");
 }
 template <int NW>
 __device__ __forceinline__ void halo_complete(const unsigned long long* p, uint32_t seq, int* err, unsigned long long (&v)[NW]) {
@@ -489,6 +514,7 @@ __device__ __forceinline__ void halo_complete(const unsigned long long* p, uint3
         ++spins;
         if ((spins & 63) == 0 && *(volatile int*)err) break;
         if (spins > V3_SPIN_LIMIT) { atomicExch(err, 1); break; }   // never hang the GPU on a broken protocol
+        __nanosleep(40);   // leave the issue slots to the warps this one is waiting for
         halo_issue<NW>(p, v);
     }
 }
@@ -566,7 +592,7 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
             for (int k = 0; k < NP; k++) pa[k] = (uint32_t)hq[k];
             ma = (uint32_t)hq[NP];
         } else {
-            load_regs<NP>(Xa + ((size_t)prv * (V3_COLS + 2) + gidx) * D + lane_off, pa);
+            load_col_sm<NP>(Xa + ((size_t)prv * (V3_COLS + 2) + gidx) * D, lg, pa);
             ma = Ma[prv * (V3_COLS + 2) + gidx];
         }
         if (right_edge && t > 0) {
@@ -574,7 +600,7 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
             for (int k = 0; k < NP; k++) pb[k] = (uint32_t)hq[k];
             mb = (uint32_t)hq[NP];
         } else {
-            load_regs<NP>(Xb + ((size_t)prv * (V3_COLS + 2) + gidx + 2) * D + lane_off, pb);
+            load_col_sm<NP>(Xb + ((size_t)prv * (V3_COLS + 2) + gidx + 2) * D, lg, pb);
             mb = Mb[prv * (V3_COLS + 2) + gidx + 2];
         }
         __syncwarp();
@@ -590,7 +616,7 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
             for (int k = 0; k < NP; k++) halo_put(hp + k, pa[k], (uint32_t)(t + 1));
             halo_put(hp + NP, ma, (uint32_t)(t + 1));
         }
-        store_regs<NP>(Xa + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D + lane_off, pa);
+        store_col_sm<NP>(Xa + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D, lg, pa);
         if (lg == 0) Ma[cur * (V3_COLS + 2) + gidx + 1] = ma;
         sgm_step<NP, G>(pb, mb, c, P1x2, P2x2, PADx2, lg);
         if (!active) {
@@ -604,7 +630,7 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
             for (int k = 0; k < NP; k++) halo_put(hp + k, pb[k], (uint32_t)(t + 1));
             halo_put(hp + NP, mb, (uint32_t)(t + 1));
         }
-        store_regs<NP>(Xb + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D + lane_off, pb);
+        store_col_sm<NP>(Xb + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D, lg, pb);
         if (lg == 0) Mb[cur * (V3_COLS + 2) + gidx + 1] = mb;
         // request the neighbour's state of THIS row now (it publishes early in its row); it is consumed next row, so the
         // L2 round trip overlaps the vertical path below
@@ -873,7 +899,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             for (int k = 0; k < NP; k++) pa[k] = (uint32_t)hq[k];
             ma = (uint32_t)hq[NP];
         } else {
-            load_regs<NP>(Xa + ((size_t)prv * (V3_COLS + 2) + gidx) * D + lane_off, pa);
+            load_col_sm<NP>(Xa + ((size_t)prv * (V3_COLS + 2) + gidx) * D, lg, pa);
             ma = Ma[prv * (V3_COLS + 2) + gidx];
         }
         if (right_edge && t > 0) {
@@ -881,7 +907,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             for (int k = 0; k < NP; k++) pb[k] = (uint32_t)hq[k];
             mb = (uint32_t)hq[NP];
         } else {
-            load_regs<NP>(Xb + ((size_t)prv * (V3_COLS + 2) + gidx + 2) * D + lane_off, pb);
+            load_col_sm<NP>(Xb + ((size_t)prv * (V3_COLS + 2) + gidx + 2) * D, lg, pb);
             mb = Mb[prv * (V3_COLS + 2) + gidx + 2];
         }
         __syncwarp();
@@ -897,7 +923,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             for (int k = 0; k < NP; k++) halo_put(hp + k, pa[k], (uint32_t)(t + 1));
             halo_put(hp + NP, ma, (uint32_t)(t + 1));
         }
-        store_regs<NP>(Xa + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D + lane_off, pa);
+        store_col_sm<NP>(Xa + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D, lg, pa);
         if (lg == 0) Ma[cur * (V3_COLS + 2) + gidx + 1] = ma;
         sgm_step<NP, G>(pb, mb, c, P1x2, P2x2, PADx2, lg);
         if (!active) {
@@ -911,7 +937,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             for (int k = 0; k < NP; k++) halo_put(hp + k, pb[k], (uint32_t)(t + 1));
             halo_put(hp + NP, mb, (uint32_t)(t + 1));
         }
-        store_regs<NP>(Xb + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D + lane_off, pb);
+        store_col_sm<NP>(Xb + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D, lg, pb);
         if (lg == 0) Mb[cur * (V3_COLS + 2) + gidx + 1] = mb;
         if (t + 1 < g.H) {
             if (left_edge) halo_issue<NW>(Hptr(s, cur, 0), hq);

@@ -87,13 +87,19 @@ __global__ void k_vox_reset(VoxParams* vp0) {
     vp->min_disp_key = 0x7FFFFFFF;
 }
 
+constexpr int VOX_PPT = 8;   // pixels per thread in the reduction kernels: 8x fewer same-address atomics per frame
+
 __global__ void __launch_bounds__(256) k_vox_mindisp(Source s, VoxParams* vp0) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, fr = blockIdx.y;
+    const int fr = blockIdx.y;
     VoxParams* vp = vp0 + fr;
     int key = 0x7FFFFFFF;
-    if (i < s.W * s.H) {
-        const int y = i / s.W, x = i - y * s.W;
-        key = fkey((float)((const int16_t*)(s.disp + (size_t)fr * s.dframe + (size_t)y * s.dstep))[x] * 0.0625f);
+#pragma unroll
+    for (int k = 0; k < VOX_PPT; k++) {
+        const int i = (blockIdx.x * VOX_PPT + k) * blockDim.x + threadIdx.x;
+        if (i < s.W * s.H) {
+            const int y = i / s.W, x = i - y * s.W;
+            key = min(key, fkey((float)((const int16_t*)(s.disp + (size_t)fr * s.dframe + (size_t)y * s.dstep))[x] * 0.0625f));
+        }
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
@@ -107,16 +113,24 @@ __global__ void __launch_bounds__(256) k_vox_mindisp(Source s, VoxParams* vp0) {
 }
 
 __global__ void __launch_bounds__(256) k_vox_bbox(Source s, VoxParams* vp0) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, fr = blockIdx.y;
+    const int fr = blockIdx.y;
     VoxParams* vp = vp0 + fr;
     int mn[3] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF}, mx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
     unsigned ok = 0;
-    if (i < s.W * s.H) {
-        float p[3];
-        if (fetch_point(s, vp, fr, i, p[0], p[1], p[2])) {
-            ok = 1;
+#pragma unroll 2
+    for (int k = 0; k < VOX_PPT; k++) {
+        const int i = (blockIdx.x * VOX_PPT + k) * blockDim.x + threadIdx.x;
+        if (i < s.W * s.H) {
+            float p[3];
+            if (fetch_point(s, vp, fr, i, p[0], p[1], p[2])) {
+                ok++;
 #pragma unroll
-            for (int c = 0; c < 3; c++) mn[c] = mx[c] = fkey(p[c]);
+                for (int c = 0; c < 3; c++) {
+                    const int key = fkey(p[c]);
+                    mn[c] = min(mn[c], key);
+                    mx[c] = max(mx[c], key);
+                }
+            }
         }
     }
 #pragma unroll
@@ -392,15 +406,41 @@ __global__ void __launch_bounds__(256) k_vox_reduce(Source s, VoxParams* vp0, co
                                                     float* __restrict__ oxyz, uint8_t* __restrict__ orgb, uint32_t* __restrict__ oidx,
                                                     uint32_t* __restrict__ ocnt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, fr = blockIdx.y;
-    if (i >= n) return;
     VoxParams* vp = vp0 + fr;
     keys += (size_t)fr * n; vals += (size_t)fr * n; slot += (size_t)fr * n;
     oxyz += (size_t)fr * n * 3; orgb += (size_t)fr * n * 3; oidx += (size_t)fr * n; ocnt += (size_t)fr * n;
-    const uint32_t key = keys[i];
+    // every thread fetches the point at its own sorted position (parallel, coalesced key/val reads); the run heads then
+    // add their run in sorted order (= ascending point index) out of shared memory, exactly the order of the sequential sum
+    __shared__ float pxyz[256][3];
+    __shared__ float prgb[256][3];
+    __shared__ uint32_t pkey[256];
+    const uint32_t key = i < n ? keys[i] : 0xFFFFFFFFu;
+    {
+        float X = 0.f, Y = 0.f, Z = 0.f, R = 0.f, G = 0.f, B = 0.f;
+        if (key != 0xFFFFFFFFu) {
+            const int pt = (int)vals[i];
+            fetch_point(s, vp, fr, pt, X, Y, Z);
+            if (s.bgr) {
+                const int y = pt / s.W, x = pt - y * s.W;
+                const uint8_t* c = s.bgr + (size_t)fr * s.cframe + (size_t)y * s.cstep + (size_t)x * 3;
+                R = (float)c[2]; G = (float)c[1]; B = (float)c[0];
+            }
+        }
+        pxyz[threadIdx.x][0] = X; pxyz[threadIdx.x][1] = Y; pxyz[threadIdx.x][2] = Z;
+        prgb[threadIdx.x][0] = R; prgb[threadIdx.x][1] = G; prgb[threadIdx.x][2] = B;
+        pkey[threadIdx.x] = key;
+    }
+    __syncthreads();
     if (key == 0xFFFFFFFFu || (i > 0 && keys[i - 1] == key)) return;
     float sx = 0.f, sy = 0.f, sz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
     int cnt = 0;
-    for (int j = i; j < n && keys[j] == key; j++) {
+    int j = i;
+    for (int t = threadIdx.x; t < 256 && j < n && pkey[t] == key; t++, j++) {   // the part of the run inside this block
+        sx = __fadd_rn(sx, pxyz[t][0]); sy = __fadd_rn(sy, pxyz[t][1]); sz = __fadd_rn(sz, pxyz[t][2]);
+        sr = __fadd_rn(sr, prgb[t][0]); sg = __fadd_rn(sg, prgb[t][1]); sb = __fadd_rn(sb, prgb[t][2]);
+        cnt++;
+    }
+    for (; j < n && keys[j] == key; j++) {   // a run that continues past the block's last position
         const int pt = (int)vals[j];
         float X, Y, Z;
         fetch_point(s, vp, fr, pt, X, Y, Z);
@@ -533,13 +573,14 @@ int sdr_cloud_enqueue(sdr_cloud* c, int frames, const uint8_t* points, size_t ps
     s.z_max = opt->z_max;
     VoxParams* vp = c->params.as<VoxParams>();
     const dim3 g256(div_up(n, 256), frames);
+    const dim3 gppt(div_up(n, 256 * VOX_PPT), frames);   // reduction kernels: VOX_PPT pixels per thread
     k_vox_reset<<<frames, 1, 0, st>>>(vp);
     SDR_LAUNCHED(ctx);
     if (s.from_disp && s.handle_missing) {
-        k_vox_mindisp<<<g256, 256, 0, st>>>(s, vp);
+        k_vox_mindisp<<<gppt, 256, 0, st>>>(s, vp);
         SDR_LAUNCHED(ctx);
     }
-    k_vox_bbox<<<g256, 256, 0, st>>>(s, vp);
+    k_vox_bbox<<<gppt, 256, 0, st>>>(s, vp);
     SDR_LAUNCHED(ctx);
     k_vox_params<<<frames, 1, 0, st>>>(vp, opt->leaf[0], opt->leaf[1], opt->leaf[2]);
     SDR_LAUNCHED(ctx);

@@ -148,3 +148,43 @@ def test_post_filters_standalone(ctx, orc, golden):
     # speckle filtering is idempotent
     y1 = capi.filter_speckles(ctx, y, -16, 50, 16)
     assert np.array_equal(capi.filter_speckles(ctx, y1, -16, 50, 16), y1)
+
+
+FUSED = [(300, 70, 128, 5, 0), (290, 45, 128, 3, 0), (333, 40, 128, 5, 1), (197, 50, 64, 3, 0), (161, 37, 64, 5, 1),
+         (161, 2, 128, 5, 0), (164, 9, 64, 5, 0)]
+
+
+@pytest.mark.parametrize("W,H,D,bs,mode", FUSED)
+def test_fused_cost_sweep_kernel(ctx, orc, W, H, D, bs, mode, monkeypatch):
+    """The configurations the fused cost + top-down sweep kernel covers (D = 64 / 128, blockSize 3 / 5, MODE_SGBM and the
+    first pass of MODE_HH), ragged strip widths and fewer rows than the box window: bit-exact against the oracle incl.
+    the C and S volumes, identical to the two-kernel path, and the stage timer shows which path ran."""
+    from stereo_depth_ruler_b200 import capi, synth
+    args = (0, D, bs, 8 * bs * bs, 32 * bs * bs, 1, 63, 12, 50, 2, mode)
+    B = 3
+    pairs = [synth.stereo_pair(W, H, D, 20 + s) for s in range(B)]
+    po = orc.make_params(*args)
+    refs = [orc.sgbm_compute(l, r, po) for l, r in pairs]
+    outs = {}
+    for fused in (True, False):
+        if fused:
+            monkeypatch.delenv("SDR_DISABLE_COST_FUSION", raising=False)
+        else:
+            monkeypatch.setenv("SDR_DISABLE_COST_FUSION", "1")
+        m = capi.Sgbm(ctx, capi.make_params(*args))          # the switch is read when the handle is created
+        m.set_profiling(True)
+        got = m.compute_batch(np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs]), np.empty((B, H, W), np.int16))
+        names = [k for k, _ in m.stage_times()]
+        assert ("cost_path_v_fused" in names) == fused, names
+        for i in range(B):
+            assert np.array_equal(got[i], refs[i]), (fused, i)
+        # the debug view reads frame 0 of the last call: run the first pair alone
+        m.compute(*pairs[0])
+        W1 = W - D
+        outs[fused] = (m.debug_read(0, (H, W1, D)).copy(), m.debug_read(1, (H, W1, D)).copy())
+        m.close()
+    assert np.array_equal(outs[True][0], outs[False][0]) and np.array_equal(outs[True][1], outs[False][1])
+    if mode == 0:
+        raw, Cv, Sv, Sp = orc.sgbm_match(pairs[0][0], pairs[0][1], po, want_volumes=True)
+        assert np.array_equal(outs[True][0].astype(np.int32) + args[4], Cv)
+        assert np.array_equal(outs[True][1], Sp)
