@@ -44,10 +44,24 @@ __device__ __forceinline__ int uf_find(const int* parent, int i) {
     }
 }
 
+// find with path halving: every visited node is re-pointed at its grandparent. Racing with the atomicMin links is benign:
+// a node only ever points at a smaller index of its own component, and a link lost to such a store is re-established by
+// the linker's own loop (it goes on to unite the old parent with its target).
+__device__ __forceinline__ int uf_find_halving(int* parent, int i) {
+    int c = i;
+    while (true) {
+        const int n = __ldcg(parent + c);
+        if (n == c) return c;
+        const int nn = __ldcg(parent + n);
+        if (nn != n) parent[c] = nn;
+        c = nn;
+    }
+}
+
 __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
     while (true) {
-        a = uf_find(parent, a);
-        b = uf_find(parent, b);
+        a = uf_find_halving(parent, a);
+        b = uf_find_halving(parent, b);
         if (a == b) return;
         if (a < b) { const int t = a; a = b; b = t; }
         const int old = atomicMin(parent + a, b);

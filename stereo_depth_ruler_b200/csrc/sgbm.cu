@@ -481,6 +481,9 @@ constexpr int V3_COLS = 32;
 constexpr int V3_STAGES_MAX = 6;       // rows of C in flight per CTA (TMA ring); 3 when S is staged too (keeps 2 CTAs/SM)
 constexpr int V3_STAGES_DEFAULT = 6;
 constexpr int V3_SPIN_LIMIT = 1 << 22;
+#ifndef SDR_HALO_SLEEP_NS
+#define SDR_HALO_SLEEP_NS 40   // back-off between two polls of a neighbour's halo words
+#endif
 
 // Halo words carry their own sequence number (row + 1) in the upper half of one 64-bit store, so no fence and no
 // separate flag is needed: the reader polls the word until the sequence matches (single-copy-atomic 8-byte accesses).
@@ -506,7 +509,7 @@ __device__ __forceinline__ void halo_complete(const unsigned long long* p, uint3
         ++spins;
         if ((spins & 63) == 0 && *(volatile int*)err) break;
         if (spins > V3_SPIN_LIMIT) { atomicExch(err, 1); break; }   // never hang the GPU on a broken protocol
-        __nanosleep(40);   // leave the issue slots to the warps this one is waiting for
+        if (SDR_HALO_SLEEP_NS > 0) __nanosleep(SDR_HALO_SLEEP_NS);   // leave the issue slots to the warps this one is waiting for
         halo_issue<NW>(p, v);
     }
 }
@@ -655,13 +658,16 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
 // One CTA = one 32-column strip of one frame, 12 warps in two roles:
 //   first warps (producer, CF_PROD threads): BT pixel cost -> vertical running box sum -> horizontal box sum for the strip's
 //       32 columns (+2*SW2 halo columns), one image row after the other, into a ring of C row tiles in shared memory;
-//       (the consumers also write the tile to the C volume in HBM, which the horizontal kernels read);
+//       every finished tile is also written to the C volume in HBM (one TMA bulk store) for the horizontal kernels;
 //   last 8 warps (consumer, 256 threads): the three top-down paths of k_path_v3 reading C from that ring.
 // The sweep alone leaves ~60 % of the issue slots idle (it waits for its neighbours' halos every row) and the cost
 // kernel alone is issue-bound: in one kernel the producer fills those slots, and the sweep's read of C from HBM
 // (one volume pass) disappears. Registers are split with setmaxnreg (producer 64, consumer 88 per thread).
-constexpr int CF_PROD_DEFAULT = 256;
-constexpr int CF_NST = 3;          // C row tiles in flight between producer and consumer
+constexpr int CF_PROD_DEFAULT = 128;
+#ifndef SDR_CF_NST
+#define SDR_CF_NST 3
+#endif
+constexpr int CF_NST = SDR_CF_NST;          // C row tiles in flight between producer and consumer
 constexpr int CF_CONS = 256;       // consumer threads (32 columns x 8 lanes)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -670,6 +676,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+
 struct CfLayout {   // shared-memory carve-up (bytes), computed identically on host and device
     int cw, nchunks_max, stage_bytes;
     size_t off_ma, off_ring_c, off_stage, off_ring8, off_vs, total;
@@ -686,7 +696,7 @@ __host__ __device__ inline CfLayout cf_layout(int D, int SW2, int SH2) {
     L.off_stage = o;   o += (size_t)2 * L.stage_bytes;
     L.off_ring8 = o;   o += (size_t)(2 * SH2 + 1) * L.cw * D;
     o = (o + 15) & ~(size_t)15;
-    L.off_vs = o;      o += (size_t)2 * L.cw * D * 2;   // two buffers (alternating rows): one producer barrier per row
+    L.off_vs = o;      o += (size_t)L.cw * D * 2;
     L.total = o;
     return L;
 }
@@ -716,12 +726,13 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
     for (int i = threadIdx.x; i < (int)(lay.off_ring_c / 4); i += blockDim.x) ((uint32_t*)cfsm)[i] = 0;
     for (int i = threadIdx.x; i < (int)((lay.off_vs - lay.off_ring8) / 4); i += blockDim.x) ((uint32_t*)(cfsm + lay.off_ring8))[i] = 0;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < CF_NST; i++) { mbar_init(&fullC[i], CF_PROD); mbar_init(&emptyC[i], CF_CONS / 32); }
+        for (int i = 0; i < CF_NST; i++) { mbar_init(&fullC[i], 1); mbar_init(&emptyC[i], CF_CONS / 32); }
         mbar_init(&fullIn[0], 1);
         mbar_init(&fullIn[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    const uint32_t tile_bytes = (uint32_t)(min(V3_COLS, g.W1 - x0) * D * 2);
 
     // Producer warps come first: the SM's warp arbiter favours the higher warp slots, which gives the latency-critical
     // consumer chain priority while the producer's independent arithmetic fills the remaining issue slots.
@@ -731,15 +742,10 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
         if constexpr (CF_PROD == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;\n");
         const int tid = threadIdx.x;
-        // t16: position of the thread's 16-byte slice inside a column of the shared-memory tiles; q: the disparity octet it
-        // computes. Octets are dealt so that lane lg of a consumer column group finds its register quad qq at slice
-        // qq*8 + lg (load_col_sm): every 128-bit access of a quarter-warp, producer or consumer, is 128 contiguous bytes.
-        constexpr int OPL = NP / 4;   // octets per consumer lane
-        const int t16 = tid % DQ, xg = tid / DQ;
-        const int q = (t16 & 7) * OPL + (t16 >> 3);
+        const int q = tid % DQ, xg = tid / DQ;
         uint8_t* stage = cfsm + lay.off_stage;
         uint8_t* ring8 = cfsm + lay.off_ring8;                 // [n][CW][D] u8
-        uint16_t* Vs0 = (uint16_t*)(cfsm + lay.off_vs);        // [2][CW][D] u16
+        uint16_t* Vs = (uint16_t*)(cfsm + lay.off_vs);         // [CW][D] u16
         const int lo = max(x0 - SW2, 0), hi = min(x0 - SW2 + CW, g.W1);
         const int j0_min = (g.W - 1 - (hi - 1 + g.minX1)) + g.minD, j0_max = (g.W - 1 - (lo + g.minX1)) + g.minD + 8 * (DQ - 1);
         const int cs = max(j0_min - 3, 0) >> 4, nchunks = ((j0_max + 7) >> 4) - cs + 1;
@@ -786,7 +792,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
                     const int o1 = o0 + ((int)tab[k] < 0 ? PR_CHUNK - 12 : 4);
                     uint32_t n0, n1;
                     bt_item(pls[ix], prs, o0, o1, n0, n1);
-                    uint2* rp = (uint2*)(ring8 + ((size_t)slot * CW + h) * D + 8 * t16);
+                    uint2* rp = (uint2*)(ring8 + ((size_t)slot * CW + h) * D + 8 * q);
                     const uint2 old = *rp;
                     *rp = make_uint2(n0, n1);
                     // V += new - old per 16-bit half: new (bytes, zero-extended) minus old (bytes, zero-extended)
@@ -798,14 +804,15 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             }
             slot = slot + 1 == n ? 0 : slot + 1;
             const int y = i - 2 * g.SH2;          // output row finished by this virtual row
-            uint16_t* Vs = Vs0 + (size_t)(y & 1) * CW * D;
             if (y >= 0) {
 #pragma unroll
                 for (int k = 0; k < ITEMS; k++)
                     if (k < CPT || xg < NX) {
                         const int h = k < CPT ? CPT * xg + k : V3_COLS + xg;
-                        *(uint4*)(Vs + (size_t)h * D + 8 * t16) = make_uint4(V[k][0], V[k][1], V[k][2], V[k][3]);
+                        *(uint4*)(Vs + (size_t)h * D + 8 * q) = make_uint4(V[k][0], V[k][1], V[k][2], V[k][3]);
                     }
+                // the bulk store that last read ring slot cst must be done reading before the slot is rewritten
+                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(CF_NST - 1) : "memory");
             }
             named_bar_sync(2, CF_PROD);   // Vs complete; every producer thread is done with this input stage
             if (tid == 0 && i + 2 < NV) issue_in(i + 2);
@@ -817,7 +824,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
                 for (int k = 0; k < CPT; k++) { w[k][0] = V[k][0]; w[k][1] = V[k][1]; w[k][2] = V[k][2]; w[k][3] = V[k][3]; }
 #pragma unroll
                 for (int j = 0; j < NX; j++) {
-                    const uint4 v = *(const uint4*)(Vs + (size_t)(CPT * xg + CPT + j) * D + 8 * t16);
+                    const uint4 v = *(const uint4*)(Vs + (size_t)(CPT * xg + CPT + j) * D + 8 * q);
                     w[CPT + j][0] = v.x; w[CPT + j][1] = v.y; w[CPT + j][2] = v.z; w[CPT + j][3] = v.w;
                 }
                 uint32_t acc[4];
@@ -834,12 +841,19 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
 #pragma unroll
                         for (int r = 0; r < 4; r++) acc[r] = __vsub2(__vadd2(acc[r], w[k + NX][r]), w[k - 1][r]);
                     }
-                    *(uint4*)(ct + (size_t)(CPT * xg + k) * D + 8 * t16) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+                    *(uint4*)(ct + (size_t)(CPT * xg + k) * D + 8 * q) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
                 }
-                mbar_arrive(&fullC[cst]);   // release: this thread's part of the tile is written
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
+                named_bar_sync(3, CF_PROD);   // tile complete (and every read of Vs is done)
+                if (tid == 0) {
+                    bulk_s2g(C + (((size_t)b * g.crows + y) * g.W1 + x0) * D, ct, tile_bytes);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    mbar_arrive(&fullC[cst]);
+                }
                 if (++cst == CF_NST) { cst = 0; cphase ^= 1; }
             }
         }
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         return;
     }
 
@@ -860,7 +874,6 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
         return halo + ((((size_t)f * nstrips + strip) * 2 + buf) * 2 + which) * HW + (size_t)lg * NW;
     };
     int16_t* Sb = S + (size_t)b * g.H * g.W1 * D + (size_t)xl * D + lane_off;
-    int16_t* Cb = C + (size_t)b * g.crows * g.W1 * D + (size_t)xl * D + lane_off;
     const size_t rowstride = (size_t)g.W1 * D;
     const bool left_edge = gidx == 0 && s > 0, right_edge = gidx == V3_COLS - 1 && s + 1 < nstrips;
     // the +P2 bias of OpenCV's C is folded out of the stored volume, exactly as in k_cost / k_path_v3
@@ -876,10 +889,9 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
     for (int t = 0; t < g.H; t++) {
         const int cur = t & 1, prv = cur ^ 1;
         mbar_wait(&fullC[stg], ring_phase);
-        load_col_sm<NP>(ringC + ((size_t)stg * V3_COLS + gidx) * D, lg, c);
+        load_regs<NP>(ringC + ((size_t)stg * V3_COLS + gidx) * D + lane_off, c);
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(&emptyC[stg]);   // this warp holds its C values in registers
-        if (active) store_regs<NP>(Cb + (size_t)t * rowstride, c);   // the horizontal kernels read C from the volume
         if (left_edge && t > 0) {
 #pragma unroll
             for (int k = 0; k < NP; k++) pa[k] = (uint32_t)hq[k];
@@ -1335,7 +1347,11 @@ int launch_cost_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int4* PL, 
     SDR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CF_PROD + CF_CONS, lay.total));
     const int cap = per_sm * ctx->sm_count;
     if (cap < nstrips) return -1;
-    const int fpl = std::min(batch, cap / nstrips);
+    // frames per cooperative launch: all that fit by default; fewer (SDR_CF_FPL) leaves part of every SM to the kernels of
+    // other handles / streams, which the fused kernel otherwise shuts out (it takes the whole register file at 2 CTAs/SM)
+    static const int env_fpl = getenv("SDR_CF_FPL") ? atoi(getenv("SDR_CF_FPL")) : 0;
+    int fpl = std::min(batch, cap / nstrips);
+    if (env_fpl > 0) fpl = std::min(fpl, env_fpl);
     int rc;
     const size_t halo_bytes = (size_t)nstrips * 4 * 8 * (NP + 1) * sizeof(unsigned long long);   // per frame
     if ((rc = sc.halo.reserve(ctx, halo_bytes * fpl))) return rc;
