@@ -297,15 +297,15 @@ def run_ours(args):
     # algorithmic bytes per frame of each SGBM kernel (DESIGN.md "Kernels"): distinct bytes it must read + write
     algo = {"prefilter": 2 * img + (16 + 25) * img, "cost": (16 + 25) * img + vol, "path_v_fused_down": 2 * vol,
             "cost_path_v_fused": (16 + 25) * img + 2 * vol, "path_v_fused_up": 3 * vol, "path_v0": 2 * vol, "path_v1": 3 * vol, "path_v2": 3 * vol, "path_h_fwd": 3 * vol,
-            "path_h_bwd_wta": 2 * vol + 6 * img, "lrcheck": 8 * img, "median3": 4 * img, "speckle": 24 * img}
+            "path_h_bwd_wta": 2 * vol + 6 * img, "path_h_both_wta": 5 * vol + 6 * img, "lrcheck": 8 * img, "median3": 4 * img, "speckle": 24 * img}
     # DRAM bytes per launch at 8 frames per launch from the committed `ncu --set full` capture of this build
     # (profiles/r1b_ncu_sgbm_kernels.txt: dram__bytes_read.sum + dram__bytes_write.sum); scaled to the batch in use.
-    ncu_traffic_b8 = {"cost_path_v_fused": 0.292325e9 + 3.342508e9, "path_h_fwd": 3.397468e9 + 1.659015e9,
-                      "path_h_bwd_wta": 3.397687e9 + 0.043536e9, "prefilter": 0.031252e9 + 0.248703e9,
+    ncu_traffic_b8 = {"cost_path_v_fused": 0.292538e9 + 3.339035e9, "path_h_fwd": 3.397419e9 + 1.659663e9,
+                      "path_h_bwd_wta": 3.397855e9 + 0.045961e9, "prefilter": 0.031247e9 + 0.250350e9,
                       "cost": 0.314232e9 + 1.644994e9, "path_v_fused_down": 1.699093e9 + 1.653423e9}
     # SM-side utilisation of the same captures (the fused kernel is bound by instruction issue / the integer pipe and
     # shared memory, not by HBM): smsp__issue_active and sm__inst_executed_pipe_alu, percent of peak
-    ncu_sm_b8 = {"cost_path_v_fused": (54.0, 51.3), "path_h_fwd": (30.2, 32.0), "path_h_bwd_wta": (47.3, 46.6), "prefilter": (85.5, 65.2)}
+    ncu_sm_b8 = {"cost_path_v_fused": (56.6, 56.5), "path_h_fwd": (30.0, 31.9), "path_h_bwd_wta": (47.2, 46.5), "prefilter": (85.6, 65.1)}
     dom = max(acc, key=acc.get)
     peaks = {}
     try:

@@ -1082,12 +1082,112 @@ __global__ void __launch_bounds__(THREADS) k_path_h(Geom g, const int16_t* __res
     }
 }
 
+// Both horizontal paths of a row in ONE launch: two adjacent 8-lane groups of a warp run the L->R and the R->L chain of
+// the same row at the same time and meet in the middle. In the first half of its walk a chain adds its L into S (read-
+// modify-write, as k_path_h<.., false>); in the second half the other chain has already been there, so S + L is the final
+// sum and the chain runs WTA / uniqueness / sub-pixel on it (as k_path_h<.., true>). Same five volume passes as the two
+// separate kernels, but twice as many chains in flight (the step is a long dependent chain: the kernels are bound by the
+// number of chains, not by issue or HBM), the WTA work is spread over both chains, and one launch less.
+// The two chains of a row advance in lock step (one __syncwarp per step), which orders "partner stored S[x]" before
+// "this chain loads S[x]" at the two or three pixels around the meeting point where the one-step-ahead prefetch of S
+// would be stale.
+template <int NP>
+__device__ __forceinline__ void load_regs_l2(const int16_t* p, uint32_t (&r)[NP]) {
+    if constexpr (NP % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < NP / 4; i++) {
+            const uint4 v = __ldcg((const uint4*)p + i);
+            r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        }
+    } else if constexpr (NP % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < NP / 2; i++) {
+            const uint2 v = __ldcg((const uint2*)p + i);
+            r[2 * i] = v.x; r[2 * i + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) r[i] = __ldcg((const unsigned int*)p + i);
+    }
+}
+
+template <int NP, int G, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_path_hh(Geom g, const int16_t* __restrict__ C, int16_t* S, int16_t* __restrict__ dispraw,
+                                                     uint32_t* __restrict__ wta) {
+    constexpr int CPB = THREADS / G;   // chains per block, two per row
+    static_assert(G == 8 && CPB % 2 == 0, "the two chains of a row must sit in one warp");
+    __shared__ __align__(16) int16_t smS[CPB * 2 * NP * G];
+    const int lane = threadIdx.x & 31, lg = lane & (G - 1);
+    const int chain = blockIdx.x * CPB + threadIdx.x / G;
+    const int row = chain >> 1, dir = (chain & 1) ? -1 : +1;
+    bool active = row < g.H;
+    int y = min(row, g.H - 1);
+    const int b = blockIdx.z;
+    const int D = g.D, W1 = g.W1;
+    int si = -1;
+    for (int i = 0; i < g.nseg; i++)
+        if (y >= g.seg[i].dst_start && y < g.seg[i].src_end) si = i;
+    if (si < 0) {   // row outside the selected stripes: run on a valid row, write nothing
+        si = 0;
+        y = g.seg[0].dst_start;
+        active = false;
+    }
+    const Seg sg = g.seg[si];
+    const uint32_t P1x2 = pack16(g.P1, g.P1), P2x2 = pack16(g.P2, g.P2);
+    const int pad = 32767 - g.P1;
+    const uint32_t PADx2 = pack16(pad, pad);
+    uint32_t P[NP], c[NP], s[NP], L[NP], cn[NP], sn[NP], m = 0;
+#pragma unroll
+    for (int k = 0; k < NP; k++) P[k] = 0;
+    const size_t lane_off = (size_t)lg * 2 * NP;
+    const int16_t* Cb = C + (((size_t)b * g.crows + sg.crow0 + (y - sg.src_start)) * W1) * D + lane_off;
+    int16_t* Sb = S + (((size_t)b * g.H + y) * W1) * D + lane_off;
+    const int h1 = (W1 + 1) / 2;    // L->R accumulates x < h1, R->L accumulates x >= h1; each finishes the other's pixels
+    const int wta_from = W1 / 2;    // first step at which a chain of the warp is past its accumulating half
+    int x = dir > 0 ? 0 : W1 - 1;
+    load_regs<NP>(Cb + (size_t)x * D, cn);
+    load_regs_l2<NP>(Sb + (size_t)x * D, sn);
+    int16_t* sm = smS + (threadIdx.x / G) * 2 * NP * G;
+    for (int step = 0; step < W1; step++) {
+#pragma unroll
+        for (int k = 0; k < NP; k++) { c[k] = cn[k]; s[k] = sn[k]; }
+        const int xn = x + dir;
+        if (step + 1 < W1) {
+            load_regs<NP>(Cb + (size_t)xn * D, cn);
+            load_regs_l2<NP>(Sb + (size_t)xn * D, sn);
+        }
+        sgm_step<NP, G>(P, m, c, P1x2, P2x2, PADx2, lg);
+        const bool acc_half = dir > 0 ? x < h1 : x >= h1;
+        if (acc_half) {
+#pragma unroll
+            for (int k = 0; k < NP; k++) L[k] = __vminu2(__vadd2(s[k], P[k]), 0x7FFF7FFFu);
+            if (active) store_regs<NP>(Sb + (size_t)x * D, L);
+        }
+        __syncwarp();   // the partner's store of this step (and of every earlier step) is visible from here on
+        if (step >= wta_from) {   // uniform over the warp: every lane takes part in the shuffles of wta_pixel
+            // the partner added its L to this pixel 2*step - (W1 - 1) steps ago: 0 or 1 means after the prefetch was issued
+            if (!acc_half && 2 * step - (W1 - 1) < 2) load_regs_l2<NP>(Sb + (size_t)x * D, s);
+#pragma unroll
+            for (int k = 0; k < NP; k++) L[k] = __vminu2(__vadd2(s[k], P[k]), 0x7FFF7FFFu);
+            int dv;
+            uint32_t wv;
+            wta_pixel<NP, G>(L, lg, g, sm, dv, wv);
+            if (active && !acc_half && lg == 0) {
+                dispraw[((size_t)b * g.H + y) * g.W + x + g.minX1] = (int16_t)dv;
+                wta[((size_t)b * g.H + y) * W1 + x] = wv;
+            }
+        }
+        x = xn;
+    }
+}
+
 // Horizontal chains with a TMA-fed shared-memory ring (default): a warp owns 4 rows (8 lanes each); lane 0 of every row
 // group stages the next chunks of K steps of its row (K*D*2 contiguous bytes of C, and of S) with bulk async copies,
 // H_STAGES chunks deep, completion on a per-warp mbarrier. That keeps ~16 KB per warp in flight instead of the 2 KB a
 // one-step register prefetch gives, which is what the single-chain-per-row parallelism needs to reach HBM speed.
 constexpr int H_STAGES_MAX = 4;
 constexpr int H_STAGES_DEFAULT = 2, H_WARPS_DEFAULT = 2, HB_THREADS_DEFAULT = 32;
+constexpr bool PATH_HH_DEFAULT = false;
 constexpr bool HB_RING_DEFAULT = false;   // R->L + WTA through the TMA ring: 0.99 ms vs 0.93 ms with the register prefetch   // B200 sweep at 1280x720x128, batch 8 (tools/tune_env.py)
 
 template <int NP, bool WTA>
@@ -1288,6 +1388,15 @@ int launch_path_h(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int1
     return SDR_OK;
 }
 
+template <int NP>
+int launch_path_hh(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int16_t* S, int16_t* dispraw, uint32_t* wta) {
+    constexpr int G = 8, THREADS = 64;   // 2 warps = 4 rows x 2 directions per CTA
+    dim3 grid(div_up(2 * g.H, THREADS / G), 1, batch);
+    k_path_hh<NP, G, THREADS><<<grid, THREADS, 0, ctx->stream>>>(g, C, S, dispraw, wta);
+    SDR_LAUNCHED(ctx);
+    return SDR_OK;
+}
+
 struct V3Scratch {
     DevBuf halo, err;
     PinnedBuf host_err;
@@ -1424,7 +1533,8 @@ struct sdr_sgbm {
     SpeckleScratch speckle;
     V3Scratch v3;
     bool use_fused_sweep = true;
-    bool use_cost_fusion = true;               // cost volume + top-down sweep in one kernel (k_cost_path_v3)
+    bool use_cost_fusion = true;
+    bool use_hh = false;                       // both horizontal paths in one launch (k_path_hh)               // cost volume + top-down sweep in one kernel (k_cost_path_v3)
     int stripe_first = 0, stripe_count = -1;   // MODE_SGBM_3WAY: subset of the four stripes to match (-1 = all)
     bool skip_post = false;                    // stop after the raw matcher output (median / speckle run elsewhere)
     DevBuf post_in;
@@ -1462,6 +1572,7 @@ extern "C" int sdr_sgbm_create(sdr_ctx* ctx, const sdr_sgbm_params* params, sdr_
     m->ctx = ctx;
     m->p = *params;
     m->use_fused_sweep = getenv("SDR_DISABLE_FUSED_SWEEP") == nullptr;   // A/B switch for the cooperative sweep
+    m->use_hh = getenv("SDR_PATH_HH") ? atoi(getenv("SDR_PATH_HH")) != 0 : PATH_HH_DEFAULT;   // A/B switch: k_path_hh
     m->use_cost_fusion = getenv("SDR_DISABLE_COST_FUSION") == nullptr;   // A/B switch for the fused cost + sweep kernel
     *out = m;
     return SDR_OK;
@@ -1630,12 +1741,18 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
                 }
             }
         }
-        NP_SWITCH(np, rc = launch_path_h<NPc>(ctx, g, batch, C, S, +1, 1, false, nullptr, nullptr));
-        if (rc) return rc;
-        m->timer.mark(st, "path_h_fwd");
-        NP_SWITCH(np, rc = launch_path_h<NPc>(ctx, g, batch, C, S, -1, 1, true, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>()));
-        if (rc) return rc;
-        m->timer.mark(st, "path_h_bwd_wta");
+        if (m->use_hh) {   // both horizontal paths in one launch
+            NP_SWITCH(np, rc = launch_path_hh<NPc>(ctx, g, batch, C, S, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>()));
+            if (rc) return rc;
+            m->timer.mark(st, "path_h_both_wta");
+        } else {
+            NP_SWITCH(np, rc = launch_path_h<NPc>(ctx, g, batch, C, S, +1, 1, false, nullptr, nullptr));
+            if (rc) return rc;
+            m->timer.mark(st, "path_h_fwd");
+            NP_SWITCH(np, rc = launch_path_h<NPc>(ctx, g, batch, C, S, -1, 1, true, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>()));
+            if (rc) return rc;
+            m->timer.mark(st, "path_h_bwd_wta");
+        }
         const int ry0 = g.seg[0].dst_start, ry1 = g.seg[g.nseg - 1].src_end;   // output rows of the selected stripes
         k_lrcheck<<<dim3(ry1 - ry0, 1, batch), 256, (size_t)W * sizeof(uint32_t), st>>>(g, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>(),
                                                                                           m->matched.as<int16_t>(), (size_t)W * 2, img16, ry0);
