@@ -1390,9 +1390,13 @@ int launch_path_h(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int1
 
 template <int NP>
 int launch_path_hh(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int16_t* S, int16_t* dispraw, uint32_t* wta) {
-    constexpr int G = 8, THREADS = 64;   // 2 warps = 4 rows x 2 directions per CTA
-    dim3 grid(div_up(2 * g.H, THREADS / G), 1, batch);
-    k_path_hh<NP, G, THREADS><<<grid, THREADS, 0, ctx->stream>>>(g, C, S, dispraw, wta);
+    constexpr int G = 8;
+    static const int env_t = getenv("SDR_HH_THREADS") ? atoi(getenv("SDR_HH_THREADS")) : 0;   // tuning knob
+    const int threads = env_t == 32 || env_t == 64 || env_t == 128 ? env_t : 64;   // 64: 2 warps = 4 rows x 2 directions per CTA
+    dim3 grid(div_up(2 * g.H, threads / G), 1, batch);
+    if (threads == 32) k_path_hh<NP, G, 32><<<grid, 32, 0, ctx->stream>>>(g, C, S, dispraw, wta);
+    else if (threads == 128) k_path_hh<NP, G, 128><<<grid, 128, 0, ctx->stream>>>(g, C, S, dispraw, wta);
+    else k_path_hh<NP, G, 64><<<grid, 64, 0, ctx->stream>>>(g, C, S, dispraw, wta);
     SDR_LAUNCHED(ctx);
     return SDR_OK;
 }

@@ -188,3 +188,27 @@ def test_fused_cost_sweep_kernel(ctx, orc, W, H, D, bs, mode, monkeypatch):
         raw, Cv, Sv, Sp = orc.sgbm_match(pairs[0][0], pairs[0][1], po, want_volumes=True)
         assert np.array_equal(outs[True][0].astype(np.int32) + args[4], Cv)
         assert np.array_equal(outs[True][1], Sp)
+
+
+@pytest.mark.parametrize("W,H,args", [(300, 41, (0, 128, 5, 600, 2400, 1, 63, 12, 50, 2, 0)), (203, 33, (0, 64, 3, 72, 288, 1, 63, 12, 0, 0, 1)),
+                                      (177, 50, (0, 80, 5, 600, 2400, 1, 63, 12, 200, 2, 2)), (97, 9, (-16, 48, 5, 600, 2400, 2, 63, 5, 0, 0, 0)),
+                                      (67, 3, (0, 64, 5, 600, 2400, 1, 63, 12, 0, 0, 2)), (68, 5, (0, 64, 5, 600, 2400, 1, 63, 12, 0, 0, 0))])
+def test_two_direction_horizontal_kernel(ctx, orc, W, H, args, monkeypatch):
+    """SDR_PATH_HH=1: both horizontal paths of a row in one launch, meeting in the middle (odd and even W1,
+    W1 = 3 and 4, every mode): same CV_16S map and raw matcher output as the oracle."""
+    from stereo_depth_ruler_b200 import capi, synth
+    monkeypatch.setenv("SDR_PATH_HH", "1")
+    l, r = synth.stereo_pair(W, H, args[1], 31)
+    po = orc.make_params(*args)
+    m = capi.Sgbm(ctx, capi.make_params(*args))       # the switch is read when the handle is created
+    m.set_profiling(True)
+    got = m.compute(l, r)
+    assert "path_h_both_wta" in [k for k, _ in m.stage_times()]
+    assert np.array_equal(got, orc.sgbm_compute(l, r, po))
+    assert np.array_equal(m.debug_read(2, (H, W)), orc.sgbm_match(l, r, po))
+    B = 3
+    pairs = [synth.stereo_pair(W, H, args[1], 40 + s) for s in range(B)]
+    out = m.compute_batch(np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs]), np.empty((B, H, W), np.int16))
+    for i in range(B):
+        assert np.array_equal(out[i], orc.sgbm_compute(pairs[i][0], pairs[i][1], po)), i
+    m.close()
