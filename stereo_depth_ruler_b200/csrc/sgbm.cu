@@ -160,7 +160,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-
 // BT cost of 8 consecutive disparities at one pixel (both channels) -> two u8x4 words. pl: the pixel's packed left
 // constants; pr: staged right-image chunks (16 B of each of the 24 plane-copies per chunk); o0 / o1: byte offsets of the
 // two aligned words inside the stage for plane 0, copy a (plane p adds 64 p).
