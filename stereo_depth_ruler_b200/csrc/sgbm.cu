@@ -13,6 +13,7 @@
 #include "sdr_internal.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 
@@ -1186,7 +1187,6 @@ __global__ void __launch_bounds__(THREADS) k_path_hh(Geom g, const int16_t* __re
 // one-step register prefetch gives, which is what the single-chain-per-row parallelism needs to reach HBM speed.
 constexpr int H_STAGES_MAX = 4;
 constexpr int H_STAGES_DEFAULT = 2, H_WARPS_DEFAULT = 2, HB_THREADS_DEFAULT = 32;
-constexpr bool PATH_HH_DEFAULT = false;
 constexpr bool HB_RING_DEFAULT = false;   // R->L + WTA through the TMA ring: 0.99 ms vs 0.93 ms with the register prefetch   // B200 sweep at 1280x720x128, batch 8 (tools/tune_env.py)
 
 template <int NP, bool WTA>
@@ -1529,6 +1529,7 @@ int launch_cost_path_fused(sdr_ctx* ctx, const Geom& g, int batch, const int4* P
 // ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
+static std::atomic<int> g_live_sgbm[64];   // matcher handles alive per device (chooses the horizontal kernel variant)
 struct sdr_sgbm {
     sdr_ctx* ctx = nullptr;
     sdr_sgbm_params p{};
@@ -1537,7 +1538,7 @@ struct sdr_sgbm {
     V3Scratch v3;
     bool use_fused_sweep = true;
     bool use_cost_fusion = true;
-    bool use_hh = false;                       // both horizontal paths in one launch (k_path_hh)               // cost volume + top-down sweep in one kernel (k_cost_path_v3)
+    int hh_mode = -1;                          // both horizontal paths in one launch (k_path_hh): 1 / 0 forced by SDR_PATH_HH, -1 = automatic               // cost volume + top-down sweep in one kernel (k_cost_path_v3)
     int stripe_first = 0, stripe_count = -1;   // MODE_SGBM_3WAY: subset of the four stripes to match (-1 = all)
     bool skip_post = false;                    // stop after the raw matcher output (median / speckle run elsewhere)
     DevBuf post_in;
@@ -1575,7 +1576,8 @@ extern "C" int sdr_sgbm_create(sdr_ctx* ctx, const sdr_sgbm_params* params, sdr_
     m->ctx = ctx;
     m->p = *params;
     m->use_fused_sweep = getenv("SDR_DISABLE_FUSED_SWEEP") == nullptr;   // A/B switch for the cooperative sweep
-    m->use_hh = getenv("SDR_PATH_HH") ? atoi(getenv("SDR_PATH_HH")) != 0 : PATH_HH_DEFAULT;   // A/B switch: k_path_hh
+    m->hh_mode = getenv("SDR_PATH_HH") ? (atoi(getenv("SDR_PATH_HH")) != 0 ? 1 : 0) : -1;
+    g_live_sgbm[ctx->device & 63].fetch_add(1);
     m->use_cost_fusion = getenv("SDR_DISABLE_COST_FUSION") == nullptr;   // A/B switch for the fused cost + sweep kernel
     *out = m;
     return SDR_OK;
@@ -1583,6 +1585,7 @@ extern "C" int sdr_sgbm_create(sdr_ctx* ctx, const sdr_sgbm_params* params, sdr_
 
 extern "C" void sdr_sgbm_destroy(sdr_sgbm* m) {
     if (!m) return;
+    g_live_sgbm[m->ctx->device & 63].fetch_sub(1);
     cudaSetDevice(m->ctx->device);
     for (DevBuf* b : {&m->inL, &m->inR, &m->PL, &m->PR, &m->C, &m->S, &m->dispraw, &m->wta, &m->matched, &m->out,
                       &m->speckle.parent, &m->speckle.count, &m->v3.halo, &m->v3.err, &m->post_in})
@@ -1744,7 +1747,10 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
                 }
             }
         }
-        if (m->use_hh) {   // both horizontal paths in one launch
+        // One matcher on this device (the reference's usage): the two-direction kernel is 4-13 % faster. Several handles in
+        // flight (frame-parallel throughput): the two separate kernels leave room for each other's work.
+        const bool use_hh = m->hh_mode >= 0 ? m->hh_mode == 1 : g_live_sgbm[ctx->device & 63].load() == 1;
+        if (use_hh) {   // both horizontal paths in one launch
             NP_SWITCH(np, rc = launch_path_hh<NPc>(ctx, g, batch, C, S, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>()));
             if (rc) return rc;
             m->timer.mark(st, "path_h_both_wta");

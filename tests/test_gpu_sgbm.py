@@ -54,9 +54,10 @@ def test_against_oracle(ctx, orc, W, H, args, kind):
     m.close()
 
 
-def test_cost_and_aggregate_volumes(ctx, orc):
+def test_cost_and_aggregate_volumes(ctx, orc, monkeypatch):
     """Stage-level parity: C volume and the 4-path aggregate S of MODE_SGBM."""
     from stereo_depth_ruler_b200 import capi, synth
+    monkeypatch.setenv("SDR_PATH_HH", "0")   # the separate L->R kernel leaves the 4-path aggregate in S
     W, H, D = 200, 60, 48
     l, r = synth.stereo_pair(W, H, D, 9)
     po = orc.make_params(0, D, 5, 600, 2400, 1, 63, 12, 0, 0, 0)
@@ -161,6 +162,7 @@ def test_fused_cost_sweep_kernel(ctx, orc, W, H, D, bs, mode, monkeypatch):
     the C and S volumes, identical to the two-kernel path, and the stage timer shows which path ran."""
     from stereo_depth_ruler_b200 import capi, synth
     args = (0, D, bs, 8 * bs * bs, 32 * bs * bs, 1, 63, 12, 50, 2, mode)
+    monkeypatch.setenv("SDR_PATH_HH", "0")   # the separate L->R kernel leaves the 4-path aggregate in S
     B = 3
     pairs = [synth.stereo_pair(W, H, D, 20 + s) for s in range(B)]
     po = orc.make_params(*args)
@@ -211,4 +213,21 @@ def test_two_direction_horizontal_kernel(ctx, orc, W, H, args, monkeypatch):
     out = m.compute_batch(np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs]), np.empty((B, H, W), np.int16))
     for i in range(B):
         assert np.array_equal(out[i], orc.sgbm_compute(pairs[i][0], pairs[i][1], po)), i
+    m.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_per_direction_fallback_kernels(ctx, orc, mode, monkeypatch):
+    """SDR_DISABLE_FUSED_SWEEP=1: the one-launch-per-direction path kernels (the fallback when a cooperative grid does not
+    fit on the device) give the same map."""
+    from stereo_depth_ruler_b200 import capi, synth
+    monkeypatch.setenv("SDR_DISABLE_FUSED_SWEEP", "1")
+    W, H, args = 230, 37, (0, 64, 5, 600, 2400, 1, 63, 12, 30, 2, mode)
+    l, r = synth.stereo_pair(W, H, args[1], 17)
+    m = capi.Sgbm(ctx, capi.make_params(*args))
+    m.set_profiling(True)
+    got = m.compute(l, r)
+    names = [k for k, _ in m.stage_times()]
+    assert "path_v0" in names and "cost_path_v_fused" not in names, names
+    assert np.array_equal(got, orc.sgbm_compute(l, r, orc.make_params(*args)))
     m.close()
