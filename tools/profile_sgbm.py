@@ -1,5 +1,6 @@
 """Small driver for ncu: a few batched SGBM computes on device-resident synthetic pairs (no other kernels)."""
 import os, sys
+os.environ.setdefault("SDR_PATH_HH", "0")   # profile the kernels the multi-handle benchmark runs (one handle alone would pick k_path_hh)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from stereo_depth_ruler_b200 import capi, synth
