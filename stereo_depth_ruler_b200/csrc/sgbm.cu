@@ -69,59 +69,79 @@ __device__ __forceinline__ void prefilt_px(const uint8_t* img, size_t pitch, int
     r = r0[x];
 }
 
+// One block = 128 positions of one row of one eye. Every pixel's (Sobel, raw) pair is computed once into shared memory
+// (134 pixels: the block's range plus the neighbours the half-sample intervals and the shifted copies reach).
+// LEFT: thread t writes pixel x0 + t. RIGHT: the block owns 128 consecutive indices i of the reversed planes and writes
+// each of the 24 plane-copies as 32 aligned words (copy `sft` holds plane[i + sft], assembled from the byte planes in
+// shared memory with a funnel shift) instead of 24 single bytes per pixel.
 __global__ void __launch_bounds__(128) k_prefilter(Geom g, const uint8_t* left, size_t lpitch, size_t lframe,
                                                    const uint8_t* right, size_t rpitch, size_t rframe, int4* PL,
                                                    uint8_t* PR) {
-    const int x = blockIdx.x * 128 + threadIdx.x;
-    const int y = blockIdx.y;
+    __shared__ int16_t sS[136], sR[136];               // (Sobel, raw) of pixels xs0 .. xs0 + 133 (0 outside the image)
+    __shared__ __align__(4) uint8_t pb[6][136];        // RIGHT: byte planes (v, lo, 255-hi) x 2 channels at j = I0 .. I0 + 130
+    const int t = threadIdx.x, y = blockIdx.y;
     const int b = blockIdx.z >> 1, eye = blockIdx.z & 1;
-    if (x >= g.W) return;
     const uint8_t* img = eye ? right + (size_t)b * rframe : left + (size_t)b * lframe;
     const size_t pitch = eye ? rpitch : lpitch;
-    int s[3], r[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        int xx = x + i - 1;
-        if (xx >= 0 && xx < g.W)
-            prefilt_px(img, pitch, g.W, g.H, xx, y, g.ftzero, s[i], r[i]);
-        else {
-            s[i] = 0;  // never used: the x > 0 / x < W-1 guards below skip missing neighbours
-            r[i] = 0;
-        }
+    const int W = g.W;
+    // pixel range needed, ascending x. LEFT: x0-1 .. x0+128. RIGHT: j = I0-1 .. I0+131  <=>  x = W-1-j
+    const int I0 = blockIdx.x * 128;
+    const int xs0 = eye ? (W - 1 - (I0 + 131)) - 1 : I0 - 1;
+    const int ns = eye ? 134 : 130;
+    for (int k = t; k < ns; k += 128) {
+        const int xx = xs0 + k;
+        int sv = 0, rv = 0;
+        if (xx >= 0 && xx < W) prefilt_px(img, pitch, W, g.H, xx, y, g.ftzero, sv, rv);
+        sS[k] = (int16_t)sv;
+        sR[k] = (int16_t)rv;
     }
-    int lo[2], hi[2], v[2];
-    v[0] = s[1];
-    v[1] = r[1];
-    {
-        int vl = x > 0 ? (s[1] + s[0]) / 2 : s[1];
-        int vr = x < g.W - 1 ? (s[1] + s[2]) / 2 : s[1];
-        lo[0] = min(min(vl, vr), s[1]);
-        hi[0] = max(max(vl, vr), s[1]);
-        vl = x > 0 ? (r[1] + r[0]) / 2 : r[1];
-        vr = x < g.W - 1 ? (r[1] + r[2]) / 2 : r[1];
-        lo[1] = min(min(vl, vr), r[1]);
-        hi[1] = max(max(vl, vr), r[1]);
-    }
+    __syncthreads();
+    auto planes = [&](int x, int (&v)[2], int (&lo)[2], int (&hi)[2]) {   // BT half-sample interval at pixel x (inside the image)
+        const int k = x - xs0;
+        const int s0 = sS[k - 1], s1 = sS[k], s2 = sS[k + 1], r0 = sR[k - 1], r1 = sR[k], r2 = sR[k + 1];
+        v[0] = s1; v[1] = r1;
+        int vl = x > 0 ? (s1 + s0) / 2 : s1, vr = x < W - 1 ? (s1 + s2) / 2 : s1;
+        lo[0] = min(min(vl, vr), s1); hi[0] = max(max(vl, vr), s1);
+        vl = x > 0 ? (r1 + r0) / 2 : r1; vr = x < W - 1 ? (r1 + r2) / 2 : r1;
+        lo[1] = min(min(vl, vr), r1); hi[1] = max(max(vl, vr), r1);
+    };
     if (eye == 0) {
-        int4 o;
-        o.x = (int)pack16(-v[0], v[0] - 255);
-        o.y = (int)pack16(-hi[0], lo[0] - 255);
-        o.z = (int)pack16(-v[1], v[1] - 255);
-        o.w = (int)pack16(-hi[1], lo[1] - 255);
-        PL[((size_t)b * g.H + y) * g.W + x] = o;
-    } else {
-        uint8_t* row = PR + ((size_t)b * g.H + y) * (g.Wp >> 4) * PR_CHUNK;   // chunk (i/16): 16 bytes of each of the 24 plane-copies
-        const int j = g.W - 1 - x;
+        const int x = I0 + t;
+        if (x < W) {
+            int v[2], lo[2], hi[2];
+            planes(x, v, lo, hi);
+            int4 o;
+            o.x = (int)pack16(-v[0], v[0] - 255);
+            o.y = (int)pack16(-hi[0], lo[0] - 255);
+            o.z = (int)pack16(-v[1], v[1] - 255);
+            o.w = (int)pack16(-hi[1], lo[1] - 255);
+            PL[((size_t)b * g.H + y) * W + x] = o;
+        }
+        return;
+    }
+    for (int k = t; k < 132; k += 128) {   // plane bytes at j = I0 + k (k < 131 used; 131 pads the last word)
+        const int x = W - 1 - (I0 + k);
+        int v[2] = {0, 0}, lo[2] = {0, 0}, hi[2] = {255, 255};
+        if (k < 131 && x >= 0 && x < W) planes(x, v, lo, hi);
 #pragma unroll
         for (int ch = 0; ch < 2; ch++) {
-            const uint8_t val[3] = {(uint8_t)v[ch], (uint8_t)lo[ch], (uint8_t)(255 - hi[ch])};
+            pb[ch * 3 + 0][k] = (uint8_t)v[ch];
+            pb[ch * 3 + 1][k] = (uint8_t)lo[ch];
+            pb[ch * 3 + 2][k] = (uint8_t)(255 - hi[ch]);
+        }
+    }
+    __syncthreads();
+    uint8_t* row = PR + ((size_t)b * g.H + y) * (g.Wp >> 4) * PR_CHUNK;   // chunk (i/16): 16 bytes of each of the 24 plane-copies
+    const int w = t & 31, i = I0 + 4 * w;
+    if (i < g.Wp) {
+        uint8_t* dst = row + (size_t)(i >> 4) * PR_CHUNK + (i & 15);
 #pragma unroll
-            for (int pl = 0; pl < 3; pl++)
-#pragma unroll
-                for (int sft = 0; sft < 4; sft++) {
-                    int i = j - sft;
-                    if (i >= 0) row[(size_t)(i >> 4) * PR_CHUNK + ((ch * 3 + pl) * 4 + sft) * 16 + (i & 15)] = val[pl];
-                }
+        for (int k = 0; k < 6; k++) {
+            const int pc = (t >> 5) * 6 + k;          // plane-copy index = plane * 4 + shift
+            const int pl = pc >> 2, sft = pc & 3;
+            const uint32_t* src = (const uint32_t*)pb[pl];
+            const uint32_t val = __funnelshift_r(src[w], src[w + 1], 8 * sft);   // bytes plane[4w + sft .. 4w + sft + 3]
+            *(uint32_t*)(dst + pc * 16) = val;
         }
     }
 }
