@@ -466,27 +466,29 @@ __global__ void __launch_bounds__(256) k_vox_reduce(Source s, VoxParams* vp0, co
 
 // PCL passthrough ("Leaf size is too small"): output = input cloud, organised, NaN where non-finite.
 __global__ void __launch_bounds__(256) k_vox_passthrough(Source s, const VoxParams* vp0, float* __restrict__ oxyz, uint8_t* __restrict__ orgb) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, fr = blockIdx.y;
+    const int fr = blockIdx.y;
     const VoxParams* vp = vp0 + fr;
-    if (i >= s.W * s.H || !vp->overflow) return;
+    if (!vp->overflow) return;   // the usual case: a small grid of blocks that leave at once
     oxyz += (size_t)fr * s.W * s.H * 3;
     orgb += (size_t)fr * s.W * s.H * 3;
     Source t = s;
     t.drop_invalid = 0;
     t.z_max = 0.f;
-    float X, Y, Z;
-    const bool fin = fetch_point(t, vp, fr, i, X, Y, Z);
     const float nan = __int_as_float(0x7FC00000);
-    oxyz[(size_t)i * 3] = fin ? X : nan;
-    oxyz[(size_t)i * 3 + 1] = fin ? Y : nan;
-    oxyz[(size_t)i * 3 + 2] = fin ? Z : nan;
-    uint8_t r = 0, g = 0, b = 0;
-    if (fin && s.bgr) {
-        const int y = i / s.W, x = i - y * s.W;
-        const uint8_t* c = s.bgr + (size_t)fr * s.cframe + (size_t)y * s.cstep + (size_t)x * 3;
-        r = c[2]; g = c[1]; b = c[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.W * s.H; i += gridDim.x * blockDim.x) {
+        float X, Y, Z;
+        const bool fin = fetch_point(t, vp, fr, i, X, Y, Z);
+        oxyz[(size_t)i * 3] = fin ? X : nan;
+        oxyz[(size_t)i * 3 + 1] = fin ? Y : nan;
+        oxyz[(size_t)i * 3 + 2] = fin ? Z : nan;
+        uint8_t r = 0, g = 0, b = 0;
+        if (fin && s.bgr) {
+            const int y = i / s.W, x = i - y * s.W;
+            const uint8_t* c = s.bgr + (size_t)fr * s.cframe + (size_t)y * s.cstep + (size_t)x * 3;
+            r = c[2]; g = c[1]; b = c[0];
+        }
+        orgb[(size_t)i * 3] = r; orgb[(size_t)i * 3 + 1] = g; orgb[(size_t)i * 3 + 2] = b;
     }
-    orgb[(size_t)i * 3] = r; orgb[(size_t)i * 3 + 1] = g; orgb[(size_t)i * 3 + 2] = b;
 }
 
 }  // namespace
@@ -604,7 +606,7 @@ int sdr_cloud_enqueue(sdr_cloud* c, int frames, const uint8_t* points, size_t ps
     k_vox_reduce<<<g256, 256, 0, st>>>(s, vp, c->keys[cur].as<uint32_t>(), c->vals[cur].as<uint32_t>(), c->flags.as<uint32_t>(), n,
                                        c->oxyz.as<float>(), c->orgb.as<uint8_t>(), c->oidx.as<uint32_t>(), c->ocnt.as<uint32_t>());
     SDR_LAUNCHED(ctx);
-    k_vox_passthrough<<<g256, 256, 0, st>>>(s, vp, c->oxyz.as<float>(), c->orgb.as<uint8_t>());
+    k_vox_passthrough<<<dim3(std::min(div_up(n, 256), 4 * ctx->sm_count), frames), 256, 0, st>>>(s, vp, c->oxyz.as<float>(), c->orgb.as<uint8_t>());
     SDR_LAUNCHED(ctx);
     SDR_CUDA(ctx, cudaMemcpyAsync(c->host_params.p, vp, F * sizeof(VoxParams), cudaMemcpyDeviceToHost, st));
     if (!c->done) SDR_CUDA(ctx, cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming | cudaEventBlockingSync));
