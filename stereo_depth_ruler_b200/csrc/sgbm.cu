@@ -688,7 +688,6 @@ constexpr int CF_PROD_DEFAULT = 128;
 #define SDR_CF_NST 3
 #endif
 constexpr int CF_NST = SDR_CF_NST;          // C row tiles in flight between producer and consumer
-constexpr int CF_CONS = 256;       // consumer threads (32 columns x 8 lanes)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -704,15 +703,15 @@ struct CfLayout {   // shared-memory carve-up (bytes), computed identically on h
     int cw, nchunks_max, stage_bytes;
     size_t off_ma, off_ring_c, off_stage, off_ring8, off_vs, total;
 };
-__host__ __device__ inline CfLayout cf_layout(int D, int SW2, int SH2) {
+__host__ __device__ inline CfLayout cf_layout(int D, int SW2, int SH2, int COLS) {
     CfLayout L;
-    L.cw = V3_COLS + 2 * SW2;
+    L.cw = COLS + 2 * SW2;
     L.nchunks_max = (L.cw + D + 32) / 16 + 1;
     L.stage_bytes = ((L.cw * 16 + L.nchunks_max * PR_CHUNK) + 127) & ~127;
-    size_t o = (size_t)4 * (V3_COLS + 2) * D * 2;          // Xa, Xb
-    L.off_ma = o;  o += (size_t)4 * (V3_COLS + 2) * 4;     // Ma, Mb
+    size_t o = (size_t)4 * (COLS + 2) * D * 2;          // Xa, Xb
+    L.off_ma = o;  o += (size_t)4 * (COLS + 2) * 4;     // Ma, Mb
     o = (o + 127) & ~(size_t)127;
-    L.off_ring_c = o;  o += (size_t)CF_NST * V3_COLS * D * 2;
+    L.off_ring_c = o;  o += (size_t)CF_NST * COLS * D * 2;
     L.off_stage = o;   o += (size_t)2 * L.stage_bytes;
     L.off_ring8 = o;   o += (size_t)(2 * SH2 + 1) * L.cw * D;
     o = (o + 15) & ~(size_t)15;
@@ -721,26 +720,27 @@ __host__ __device__ inline CfLayout cf_layout(int D, int SW2, int SH2) {
     return L;
 }
 
-template <int NP, int SW2, int CF_PROD>
-__global__ void __launch_bounds__(CF_PROD + CF_CONS, 2)
+template <int NP, int SW2, int CF_PROD, int COLS>
+__global__ void __launch_bounds__(CF_PROD + COLS * 8, COLS == 32 ? 2 : 1)
 k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ PR, int16_t* __restrict__ C, int16_t* __restrict__ S, int b0,
                unsigned long long* halo, int* err) {
     constexpr int G = 8, NW = NP + 1, D = 16 * NP, DQ = D / 8;
+    constexpr int CF_CONS = COLS * G;           // consumer threads (8 lanes per column)
     constexpr int XG = CF_PROD / DQ;            // producer column groups
-    constexpr int CPT = V3_COLS / XG;           // consecutive output columns per producer thread
+    constexpr int CPT = COLS / XG;           // consecutive output columns per producer thread
     constexpr int NX = 2 * SW2;                 // halo columns of the strip (box-sum window minus one)
-    constexpr int CW = V3_COLS + NX;
-    static_assert(CF_PROD % DQ == 0 && V3_COLS % XG == 0 && NX <= XG, "producer tiling");
+    constexpr int CW = COLS + NX;
+    static_assert(CF_PROD % DQ == 0 && COLS % XG == 0 && NX <= XG, "producer tiling");
     extern __shared__ __align__(128) uint8_t cfsm[];
     __shared__ __align__(8) uint64_t fullC[CF_NST], emptyC[CF_NST], fullIn[2];
-    const CfLayout lay = cf_layout(D, SW2, g.SH2);
+    const CfLayout lay = cf_layout(D, SW2, g.SH2, COLS);
     int16_t* Xa = (int16_t*)cfsm;
-    int16_t* Xb = Xa + 2 * (V3_COLS + 2) * D;
+    int16_t* Xb = Xa + 2 * (COLS + 2) * D;
     uint32_t* Ma = (uint32_t*)(cfsm + lay.off_ma);
-    uint32_t* Mb = Ma + 2 * (V3_COLS + 2);
+    uint32_t* Mb = Ma + 2 * (COLS + 2);
     int16_t* ringC = (int16_t*)(cfsm + lay.off_ring_c);
     const int s = blockIdx.x, nstrips = gridDim.x, f = blockIdx.y, b = b0 + f;
-    const int x0 = s * V3_COLS;
+    const int x0 = s * COLS;
     const int n = 2 * g.SH2 + 1;
     // ---- prologue (all threads): zero the diagonal states and the pixel-cost ring, set up the barriers
     for (int i = threadIdx.x; i < (int)(lay.off_ring_c / 4); i += blockDim.x) ((uint32_t*)cfsm)[i] = 0;
@@ -752,14 +752,14 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const uint32_t tile_bytes = (uint32_t)(min(V3_COLS, g.W1 - x0) * D * 2);
+    const uint32_t tile_bytes = (uint32_t)(min(COLS, g.W1 - x0) * D * 2);
 
     // Producer warps come first: the SM's warp arbiter favours the higher warp slots, which gives the latency-critical
     // consumer chain priority while the producer's independent arithmetic fills the remaining issue slots.
     if (threadIdx.x < CF_PROD) {
         // =============================== producer: cost rows ===============================
         // register split (per thread): 128 producers 64 / consumers 88 (launch 80); 256 producers 48 / consumers 80 (launch 64)
-        if constexpr (CF_PROD == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
+        if constexpr (2 * CF_PROD == COLS * 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;\n");
         const int tid = threadIdx.x;
         const int q = tid % DQ, xg = tid / DQ;
@@ -776,7 +776,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
         uint32_t V[ITEMS][4];
 #pragma unroll
         for (int k = 0; k < ITEMS; k++) {
-            const int h = k < CPT ? CPT * xg + k : V3_COLS + xg;
+            const int h = k < CPT ? CPT * xg + k : COLS + xg;
             const int xc = min(max(x0 - SW2 + h, 0), g.W1 - 1);
             const int ix = min(max(xc - lo, 0), CW - 1);
             const int j0 = (g.W - 1 - (xc + g.minX1)) + g.minD + 8 * q;
@@ -807,7 +807,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
 #pragma unroll
             for (int k = 0; k < ITEMS; k++) {
                 if (k < CPT || xg < NX) {
-                    const int h = k < CPT ? CPT * xg + k : V3_COLS + xg;
+                    const int h = k < CPT ? CPT * xg + k : COLS + xg;
                     const int o0 = (int)(tab[k] & 0xFFFFu), ix = (int)((tab[k] >> 16) & 0x7FFFu);
                     const int o1 = o0 + ((int)tab[k] < 0 ? PR_CHUNK - 12 : 4);
                     uint32_t n0, n1;
@@ -828,7 +828,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
 #pragma unroll
                 for (int k = 0; k < ITEMS; k++)
                     if (k < CPT || xg < NX) {
-                        const int h = k < CPT ? CPT * xg + k : V3_COLS + xg;
+                        const int h = k < CPT ? CPT * xg + k : COLS + xg;
                         *(uint4*)(Vs + (size_t)h * D + 8 * q) = make_uint4(V[k][0], V[k][1], V[k][2], V[k][3]);
                     }
                 // the bulk store that last read ring slot cst must be done reading before the slot is rewritten
@@ -854,7 +854,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
 #pragma unroll
                     for (int j = 1; j <= NX; j++) acc[r] = __vadd2(acc[r], w[j][r]);
                 }
-                int16_t* ct = ringC + (size_t)cst * V3_COLS * D;
+                int16_t* ct = ringC + (size_t)cst * COLS * D;
 #pragma unroll
                 for (int k = 0; k < CPT; k++) {
                     if (k > 0) {
@@ -878,7 +878,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
     }
 
     // =============================== consumer: the three top-down paths ===============================
-    if constexpr (CF_PROD == 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;\n");
+    if constexpr (2 * CF_PROD == COLS * 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;\n");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 80;\n");
     const int ct = threadIdx.x - CF_PROD;
     const int gidx = ct / G, lg = ct & (G - 1);
@@ -895,7 +895,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
     };
     int16_t* Sb = S + (size_t)b * g.H * g.W1 * D + (size_t)xl * D + lane_off;
     const size_t rowstride = (size_t)g.W1 * D;
-    const bool left_edge = gidx == 0 && s > 0, right_edge = gidx == V3_COLS - 1 && s + 1 < nstrips;
+    const bool left_edge = gidx == 0 && s > 0, right_edge = gidx == COLS - 1 && s + 1 < nstrips;
     // the +P2 bias of OpenCV's C is folded out of the stored volume, exactly as in k_cost / k_path_v3
     uint32_t Pv[NP], pa[NP], pb[NP], c[NP], acc[NP];
     uint32_t mv = 0, ma = 0, mb = 0;
@@ -909,7 +909,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
     for (int t = 0; t < g.H; t++) {
         const int cur = t & 1, prv = cur ^ 1;
         mbar_wait(&fullC[stg], ring_phase);
-        load_regs<NP>(ringC + ((size_t)stg * V3_COLS + gidx) * D + lane_off, c);
+        load_regs<NP>(ringC + ((size_t)stg * COLS + gidx) * D + lane_off, c);
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(&emptyC[stg]);   // this warp holds its C values in registers
         if (left_edge && t > 0) {
@@ -917,16 +917,16 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             for (int k = 0; k < NP; k++) pa[k] = (uint32_t)hq[k];
             ma = (uint32_t)hq[NP];
         } else {
-            load_col_sm<NP>(Xa + ((size_t)prv * (V3_COLS + 2) + gidx) * D, lg, pa);
-            ma = Ma[prv * (V3_COLS + 2) + gidx];
+            load_col_sm<NP>(Xa + ((size_t)prv * (COLS + 2) + gidx) * D, lg, pa);
+            ma = Ma[prv * (COLS + 2) + gidx];
         }
         if (right_edge && t > 0) {
 #pragma unroll
             for (int k = 0; k < NP; k++) pb[k] = (uint32_t)hq[k];
             mb = (uint32_t)hq[NP];
         } else {
-            load_col_sm<NP>(Xb + ((size_t)prv * (V3_COLS + 2) + gidx + 2) * D, lg, pb);
-            mb = Mb[prv * (V3_COLS + 2) + gidx + 2];
+            load_col_sm<NP>(Xb + ((size_t)prv * (COLS + 2) + gidx + 2) * D, lg, pb);
+            mb = Mb[prv * (COLS + 2) + gidx + 2];
         }
         __syncwarp();
         sgm_step<NP, G>(pa, ma, c, P1x2, P2x2, PADx2, lg);
@@ -941,8 +941,8 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             for (int k = 0; k < NP; k++) halo_put(hp + k, pa[k], (uint32_t)(t + 1));
             halo_put(hp + NP, ma, (uint32_t)(t + 1));
         }
-        store_col_sm<NP>(Xa + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D, lg, pa);
-        if (lg == 0) Ma[cur * (V3_COLS + 2) + gidx + 1] = ma;
+        store_col_sm<NP>(Xa + ((size_t)cur * (COLS + 2) + gidx + 1) * D, lg, pa);
+        if (lg == 0) Ma[cur * (COLS + 2) + gidx + 1] = ma;
         sgm_step<NP, G>(pb, mb, c, P1x2, P2x2, PADx2, lg);
         if (!active) {
 #pragma unroll
@@ -955,8 +955,8 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             for (int k = 0; k < NP; k++) halo_put(hp + k, pb[k], (uint32_t)(t + 1));
             halo_put(hp + NP, mb, (uint32_t)(t + 1));
         }
-        store_col_sm<NP>(Xb + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D, lg, pb);
-        if (lg == 0) Mb[cur * (V3_COLS + 2) + gidx + 1] = mb;
+        store_col_sm<NP>(Xb + ((size_t)cur * (COLS + 2) + gidx + 1) * D, lg, pb);
+        if (lg == 0) Mb[cur * (COLS + 2) + gidx + 1] = mb;
         if (t + 1 < g.H) {
             if (left_edge) halo_issue<NW>(Hptr(s, cur, 0), hq);
             if (right_edge) halo_issue<NW>(Hptr(s, cur, 1), hq);
@@ -1468,11 +1468,12 @@ int launch_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int
 
 // Fused cost + top-down sweep. Returns SDR_OK, an error, or -1 when this configuration is not covered (caller runs
 // k_cost followed by k_path_v3 / k_path_v instead).
-template <int NP, int SW2, int CF_PROD>
+template <int NP, int SW2, int CF_PROD, int COLS>
 int launch_cost_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int4* PL, const uint8_t* PR, int16_t* C, int16_t* S, V3Scratch& sc) {
-    auto kern = k_cost_path_v3<NP, SW2, CF_PROD>;
-    const int nstrips = div_up(g.W1, V3_COLS);
-    const CfLayout lay = cf_layout(g.D, SW2, g.SH2);
+    auto kern = k_cost_path_v3<NP, SW2, CF_PROD, COLS>;
+    constexpr int CF_CONS = COLS * 8;
+    const int nstrips = div_up(g.W1, COLS);
+    const CfLayout lay = cf_layout(g.D, SW2, g.SH2, COLS);
     if (lay.total > ctx->smem_optin) return -1;
     SDR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
     int per_sm = 0;
@@ -1514,10 +1515,22 @@ int launch_cost_path_fused(sdr_ctx* ctx, const Geom& g, int batch, const int4* P
     if (g.D % 16) return -1;
     static const int env_prod = getenv("SDR_CF_PROD") ? atoi(getenv("SDR_CF_PROD")) : 0;   // tuning knob: producer threads (128 | 256)
     const int prod = env_prod == 128 || env_prod == 256 ? env_prod : CF_PROD_DEFAULT;
+    // D = 128: 64-column strips, one CTA per SM (512 consumer + 256 producer threads): half as many strip borders to hand
+    // halos across, 2.06 -> 1.98 ms at 1280x720, batch 8. SDR_CF_COLS=32 selects the 32-column CTAs (two per SM).
+    static const int env_cols = getenv("SDR_CF_COLS") ? atoi(getenv("SDR_CF_COLS")) : 0;
+    // Only when the wider strips still fill the device (batch 8 at 1280 wide: 144 CTAs); small batches keep the 32-column
+    // CTAs, which give twice as many (a single 1280x720 frame: 1.4 ms against 2.0 ms).
+    const bool wide_fills = env_cols == 64 || (long long)div_up(g.W1, 64) * batch * 4 >= 3LL * ctx->sm_count;
+    if (env_cols != 32 && np == 8 && wide_fills) {
+        int rc64 = -1;
+        if (g.SW2 == 2) rc64 = launch_cost_path_v3<8, 2, 256, 64>(ctx, g, batch, PL, PR, C, S, sc);
+        else if (g.SW2 == 1) rc64 = launch_cost_path_v3<8, 1, 256, 64>(ctx, g, batch, PL, PR, C, S, sc);
+        if (rc64 != -1) return rc64;   // -1: does not fit this device, try the smaller CTAs
+    }
 #define CF_CASE(NPV, SWV)                                                                                                  \
     if (np == NPV && g.SW2 == SWV)                                                                                         \
-        return prod == 128 ? launch_cost_path_v3<NPV, SWV, 128>(ctx, g, batch, PL, PR, C, S, sc)                          \
-                           : launch_cost_path_v3<NPV, SWV, 256>(ctx, g, batch, PL, PR, C, S, sc);
+        return prod == 128 ? launch_cost_path_v3<NPV, SWV, 128, 32>(ctx, g, batch, PL, PR, C, S, sc)                      \
+                           : launch_cost_path_v3<NPV, SWV, 256, 32>(ctx, g, batch, PL, PR, C, S, sc);
     CF_CASE(8, 2) CF_CASE(8, 1) CF_CASE(4, 2) CF_CASE(4, 1)
 #undef CF_CASE
     return -1;
