@@ -299,13 +299,13 @@ def run_ours(args):
             "cost_path_v_fused": (16 + 25) * img + 2 * vol, "path_v_fused_up": 3 * vol, "path_v0": 2 * vol, "path_v1": 3 * vol, "path_v2": 3 * vol, "path_h_fwd": 3 * vol,
             "path_h_bwd_wta": 2 * vol + 6 * img, "path_h_both_wta": 5 * vol + 6 * img, "lrcheck": 8 * img, "median3": 4 * img, "speckle": 24 * img}
     # DRAM bytes per launch at 8 frames per launch from the committed `ncu --set full` capture of this build
-    # (profiles/r1c_ncu_sgbm_kernels.txt: dram__bytes_read.sum + dram__bytes_write.sum); scaled to the batch in use.
-    ncu_traffic_b8 = {"cost_path_v_fused": 0.292448e9 + 3.340143e9, "path_h_fwd": 3.397449e9 + 1.662190e9,
-                      "path_h_bwd_wta": 3.397774e9 + 0.043574e9, "prefilter": 0.028150e9 + 0.247177e9,
+    # (profiles/r1d_ncu_sgbm_kernels.txt: dram__bytes_read.sum + dram__bytes_write.sum); scaled to the batch in use.
+    ncu_traffic_b8 = {"cost_path_v_fused": 0.292766e9 + 3.342460e9, "path_h_fwd": 3.398017e9 + 1.659239e9,
+                      "path_h_bwd_wta": 3.397685e9 + 0.044063e9, "prefilter": 0.028159e9 + 0.247181e9,
                       "cost": 0.314232e9 + 1.644994e9, "path_v_fused_down": 1.699093e9 + 1.653423e9}
     # SM-side utilisation of the same captures (the fused kernel is bound by instruction issue / the integer pipe and
     # shared memory, not by HBM): smsp__issue_active and sm__inst_executed_pipe_alu, percent of peak
-    ncu_sm_b8 = {"cost_path_v_fused": (56.5, 56.8), "path_h_fwd": (30.0, 32.1), "path_h_bwd_wta": (47.3, 46.6), "prefilter": (87.0, 60.7)}
+    ncu_sm_b8 = {"cost_path_v_fused": (57.4, 57.8), "path_h_fwd": (30.1, 31.9), "path_h_bwd_wta": (47.1, 46.5), "prefilter": (86.6, 60.8)}
     dom = max(acc, key=acc.get)
     peaks = {}
     try:
@@ -318,7 +318,7 @@ def run_ours(args):
     core_bytes = (2 * vol + 4 * img) * B                   # compulsory 3.69 MB + one int16 volume round trip per frame
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (ncu_traffic_b8[dom] * B / 8.0) if dom in ncu_traffic_b8 else None,
-                "traffic_source": "profiles/r1c_ncu_sgbm_kernels.txt (ncu --set full, per launch at 8 frames, scaled to this batch)",
+                "traffic_source": "profiles/r1d_ncu_sgbm_kernels.txt (ncu --set full, per launch at 8 frames, scaled to this batch)",
                 "sm_issue_active_pct": ncu_sm_b8.get(dom, (None, None))[0], "sm_alu_pipe_pct": ncu_sm_b8.get(dom, (None, None))[1],
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
                 "algorithmic_bytes_per_launch": algo.get(dom, 2 * vol) * B, "kernel_ms": acc[dom],
@@ -327,8 +327,8 @@ def run_ours(args):
                               "ms_per_batch": sgbm_ms, "algorithmic_bytes": core_bytes},
                 "stage_ms_per_batch": {k: round(v, 4) for k, v in acc.items()},
                 "stage_hbm_frac": {k: round(algo[k] * B / (v * 1e-3) / 1e9 / peak, 3) for k, v in acc.items() if k in algo and v > 0},
-                "note": "the dominant kernel (cost volume + top-down sweep fused) is not HBM-bound: issue port 57 %, integer pipe A 57 %, "
-                        "shared memory 47 % busy (DESIGN.md 2a, 5); the HBM-bound kernels are path_h_fwd and path_h_bwd_wta (stage_hbm_frac)"}
+                "note": "the dominant kernel (cost volume + top-down sweep fused) is not HBM-bound: issue port 57 %, integer pipe A 58 %, "
+                        "shared memory 48 % busy (DESIGN.md 2a, 5); the HBM-bound kernels are path_h_fwd and path_h_bwd_wta (stage_hbm_frac)"}
 
     # ---- per-stage times of the whole pipeline (one extra profiled step) ----
     pipe.set_profiling(True)
