@@ -1373,7 +1373,8 @@ int launch_path_h(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int1
     static const int env_st = getenv("SDR_H_STAGES") ? atoi(getenv("SDR_H_STAGES")) : 0;
     static const int env_w = getenv("SDR_H_WARPS") ? atoi(getenv("SDR_H_WARPS")) : 0;
     static const int env_bt = getenv("SDR_HB_THREADS") ? atoi(getenv("SDR_HB_THREADS")) : 0;
-    const int K = env_k > 0 ? env_k : std::max(1, 512 / g.D);            // steps per staged chunk: about 1 KB per row
+    const int K = env_k > 0 ? env_k : std::max(1, 512 / g.D);            // steps per staged chunk: about 1 KB per row (512 B: L->R alone 0.88 -> 0.82 ms at
+                                                                          // batch 8, but slower with other handles in flight, at D = 256 and for one frame)
     const int nst = env_st >= 2 && env_st <= H_STAGES_MAX ? env_st : H_STAGES_DEFAULT;
     const int nwarp = env_w == 1 || env_w == 2 || env_w == 4 ? env_w : H_WARPS_DEFAULT;
     const size_t smem = (size_t)nwarp * nst * 2 * 4 * K * g.D * 2;       // [warp][stage][C|S][row][K][D]
