@@ -1510,7 +1510,8 @@ int launch_cost_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int4* PL, 
     return SDR_OK;
 }
 
-int launch_cost_path_fused(sdr_ctx* ctx, const Geom& g, int batch, const int4* PL, const uint8_t* PR, int16_t* C, int16_t* S, V3Scratch& sc) {
+int launch_cost_path_fused(sdr_ctx* ctx, const Geom& g, int batch, const int4* PL, const uint8_t* PR, int16_t* C, int16_t* S, V3Scratch& sc,
+                           int env_cols) {
     if (g.nseg != 1 || g.SW2 != g.SH2 || g.seg[0].src_start != 0 || g.crows != g.H) return -1;
     const int np = g.D / 16;
     if (g.D % 16) return -1;
@@ -1518,7 +1519,6 @@ int launch_cost_path_fused(sdr_ctx* ctx, const Geom& g, int batch, const int4* P
     const int prod = env_prod == 128 || env_prod == 256 ? env_prod : CF_PROD_DEFAULT;
     // D = 128: 64-column strips, one CTA per SM (512 consumer + 256 producer threads): half as many strip borders to hand
     // halos across, 2.06 -> 1.98 ms at 1280x720, batch 8. SDR_CF_COLS=32 selects the 32-column CTAs (two per SM).
-    static const int env_cols = getenv("SDR_CF_COLS") ? atoi(getenv("SDR_CF_COLS")) : 0;
     // Only when the wider strips still fill the device (batch 8 at 1280 wide: 144 CTAs); small batches keep the 32-column
     // CTAs, which give twice as many (a single 1280x720 frame: 1.4 ms against 2.0 ms).
     const bool wide_fills = env_cols == 64 || (long long)div_up(g.W1, 64) * batch * 4 >= 3LL * ctx->sm_count;
@@ -1572,6 +1572,7 @@ struct sdr_sgbm {
     V3Scratch v3;
     bool use_fused_sweep = true;
     bool use_cost_fusion = true;
+    int cf_cols = 0;                           // its strip width: 0 = automatic, 32 / 64 forced by SDR_CF_COLS
     int hh_mode = -1;                          // both horizontal paths in one launch (k_path_hh): 1 / 0 forced by SDR_PATH_HH, -1 = automatic               // cost volume + top-down sweep in one kernel (k_cost_path_v3)
     int stripe_first = 0, stripe_count = -1;   // MODE_SGBM_3WAY: subset of the four stripes to match (-1 = all)
     bool skip_post = false;                    // stop after the raw matcher output (median / speckle run elsewhere)
@@ -1612,6 +1613,7 @@ extern "C" int sdr_sgbm_create(sdr_ctx* ctx, const sdr_sgbm_params* params, sdr_
     m->use_fused_sweep = getenv("SDR_DISABLE_FUSED_SWEEP") == nullptr;   // A/B switch for the cooperative sweep
     m->hh_mode = getenv("SDR_PATH_HH") ? (atoi(getenv("SDR_PATH_HH")) != 0 ? 1 : 0) : -1;
     g_live_sgbm[ctx->device & 63].fetch_add(1);
+    m->cf_cols = getenv("SDR_CF_COLS") ? atoi(getenv("SDR_CF_COLS")) : 0;
     m->use_cost_fusion = getenv("SDR_DISABLE_COST_FUSION") == nullptr;   // A/B switch for the fused cost + sweep kernel
     *out = m;
     return SDR_OK;
@@ -1727,7 +1729,7 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
         // MODE_SGBM / MODE_HH: cost volume and top-down sweep in one kernel when the configuration is covered
         bool cost_done = false;
         if (m->p.mode != SDR_MODE_SGBM_3WAY && m->use_fused_sweep && m->use_cost_fusion) {
-            rc = launch_cost_path_fused(ctx, g, batch, m->PL.as<int4>(), m->PR.as<uint8_t>(), m->C.as<int16_t>(), S, m->v3);
+            rc = launch_cost_path_fused(ctx, g, batch, m->PL.as<int4>(), m->PR.as<uint8_t>(), m->C.as<int16_t>(), S, m->v3, m->cf_cols);
             if (rc > 0) return rc;
             if (rc == SDR_OK) {
                 cost_done = true;

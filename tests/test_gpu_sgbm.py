@@ -231,3 +231,41 @@ def test_per_direction_fallback_kernels(ctx, orc, mode, monkeypatch):
     assert "path_v0" in names and "cost_path_v_fused" not in names, names
     assert np.array_equal(got, orc.sgbm_compute(l, r, orc.make_params(*args)))
     m.close()
+
+
+@pytest.mark.parametrize("W,H,bs", [(300, 40, 5), (333, 23, 3), (257, 31, 5)])
+def test_fused_kernel_wide_strips_small(ctx, orc, W, H, bs, monkeypatch):
+    """SDR_CF_COLS=64: the 64-column-strip form of the fused kernel (one CTA per SM; what a batch of 8 at 1280 wide runs)
+    on ragged widths (last strip partial, a single strip + 1 column), against the oracle."""
+    from stereo_depth_ruler_b200 import capi, synth
+    monkeypatch.setenv("SDR_CF_COLS", "64")
+    args = (0, 128, bs, 8 * bs * bs, 32 * bs * bs, 1, 63, 12, 50, 2, 0)
+    pairs = [synth.stereo_pair(W, H, 128, 50 + s) for s in range(2)]
+    m = capi.Sgbm(ctx, capi.make_params(*args))
+    m.set_profiling(True)
+    out = m.compute_batch(np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs]), np.empty((2, H, W), np.int16))
+    assert "cost_path_v_fused" in [k for k, _ in m.stage_times()]
+    for i, (l, r) in enumerate(pairs):
+        assert np.array_equal(out[i], orc.sgbm_compute(l, r, orc.make_params(*args))), i
+    m.close()
+
+
+def test_headline_batch_of_8_equals_single_frames(ctx, golden):
+    """The benchmark's shape: 8 frames of 1280x720x128 in one call (fused kernel with 64-column strips, several handles'
+    worth of work per launch) give, frame by frame, the maps of one-frame calls (32-column strips); frame 0 is the cv2
+    golden map."""
+    import torch
+    from stereo_depth_ruler_b200 import capi, synth
+    B = 8
+    pairs = [synth.stereo_pair(1280, 720, 128, s) for s in range(B)]
+    m = capi.Sgbm(ctx, capi.make_params())
+    L = torch.from_numpy(np.stack([p[0] for p in pairs])).cuda()
+    R = torch.from_numpy(np.stack([p[1] for p in pairs])).cuda()
+    O = torch.empty((B, 720, 1280), dtype=torch.int16, device="cuda")
+    m.compute_batch(L, R, O)
+    ctx.synchronize()
+    out = O.cpu().numpy()
+    assert sha(out[0]) == str(golden["full_c1_sha"])
+    for i in range(1, B):
+        assert np.array_equal(out[i], m.compute(*pairs[i])), i
+    m.close()
