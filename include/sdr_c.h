@@ -134,6 +134,37 @@ SDR_API int sdr_sgbm_match_stripes(sdr_sgbm* m, const sdr_image* left, const sdr
 /* medianBlur(3) + filterSpeckles with the handle's parameters on an assembled raw map. */
 SDR_API int sdr_sgbm_postfilter(sdr_sgbm* m, const sdr_image* raw, sdr_image* disp);
 
+/* The same split, native and in one process, over several GPUs of one box (BASELINE config 5). devices[0] assembles the
+ * map and runs the median / speckle filters; every device matches a contiguous block of the stripes from just the input
+ * rows it needs (host frames: each device uploads its own overlapping row range; frames resident on devices[0]: the
+ * rows travel by cudaMemcpyPeerAsync over NVLink) and pushes its raw strip to devices[0] by a peer copy. No collective.
+ * Devices beyond the number of stripes (4 for MODE_SGBM_3WAY, 1 otherwise) idle; a device may be listed more than once.
+ * left / right: u8 1-ch in host / pinned memory, or dense in the memory of devices[0]; disp: int16, host or devices[0].
+ * With a device-resident disp the call is asynchronous: sdr_sgbm_split_synchronize waits for it. */
+typedef struct sdr_sgbm_split sdr_sgbm_split;
+typedef struct sdr_split_stats {
+    int n_parts, n_stripes;
+    int device[16], stripes[16], input_rows[16], peer_access[16];
+    int64_t input_bytes[16];  /* image bytes uploaded / peer-copied to part k (0: used in place) */
+    int64_t gather_bytes[16]; /* raw-strip bytes peer-copied from part k to devices[0] */
+    float ms;                 /* device time of the whole call, CUDA events on devices[0]'s stream */
+} sdr_split_stats;
+SDR_API int sdr_sgbm_split_create(const int* devices, int n_devices, const sdr_sgbm_params* params, sdr_sgbm_split** out);
+SDR_API void sdr_sgbm_split_destroy(sdr_sgbm_split* s);
+SDR_API int sdr_sgbm_split_compute(sdr_sgbm_split* s, const sdr_image* left, const sdr_image* right, sdr_image* disp);
+SDR_API int sdr_sgbm_split_synchronize(sdr_sgbm_split* s);
+SDR_API int sdr_sgbm_split_last_stats(sdr_sgbm_split* s, sdr_split_stats* out);
+SDR_API const char* sdr_sgbm_split_last_error(sdr_sgbm_split* s);
+
+/* Kernel-selection knobs of one matcher handle. No option changes a result (every kernel variant is bit-exact and tested);
+ * the library never reads the process environment. Options: "shared_device" (1: other matchers run on this device at the
+ * same time -- the throughput runners set it -- so the two horizontal passes stay separate kernels that leave room for
+ * each other; 0, the default and the reference's usage: one matcher, both passes in one launch), "path_hh" (-1 automatic,
+ * 0 / 1 force), "fused_sweep", "cost_fusion" (0 disables the cooperative sweep / the fused cost + sweep kernel),
+ * "cf_cols" (32 / 64), "cf_prod", "cf_fpl", "v3_stages", "h_legacy", "h_k", "h_stages", "h_warps", "hb_threads",
+ * "hb_ring", "hh_threads" (tile shapes, 0 = default). Unknown names return SDR_EINVAL. */
+SDR_API int sdr_sgbm_set_option(sdr_sgbm* m, const char* name, int value);
+
 /* Per-kernel device times (ms) of the last compute, measured with CUDA events on the ctx stream.
  * Enable first; names[i] point to static strings. Returns the number of stages written (<= cap). */
 SDR_API int sdr_sgbm_set_profiling(sdr_sgbm* m, int enabled);
@@ -221,6 +252,8 @@ SDR_API void sdr_pipeline_destroy(sdr_pipeline* p);
  * (valid until the next run). */
 SDR_API int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sdr_image* disp, sdr_image* points,
                              sdr_image* left_rect, sdr_cloud_view* views);
+/* sdr_sgbm_set_option on the pipeline's matcher. */
+SDR_API int sdr_pipeline_set_sgbm_option(sdr_pipeline* p, const char* name, int value);
 /* Per-stage device times (ms) of the last run (CUDA events on the ctx stream); enable first. */
 SDR_API int sdr_pipeline_set_profiling(sdr_pipeline* p, int enabled);
 SDR_API int sdr_pipeline_stage_times(sdr_pipeline* p, int cap, const char** names, float* ms);
@@ -230,6 +263,11 @@ SDR_API int sdr_pipeline_cloud_download(sdr_pipeline* p, int i, float* xyz, uint
  * queued back to back and waited for once. */
 SDR_API int sdr_pipeline_clouds_download(sdr_pipeline* p, int n, float* const* xyz, uint8_t* const* rgb, uint32_t* const* idx,
                                          uint32_t* const* cnt);
+/* The same clouds packed back to back, as they sit on the device: ONE copy per array (any may be NULL) and one wait.
+ * offsets[n + 1] (optional) receives the first point of every frame's cloud; frame i owns points [offsets[i], offsets[i+1]).
+ * Buffers must hold offsets[n] points (sum of views[i].n of the run); idx / cnt are undefined for passthrough frames. */
+SDR_API int sdr_pipeline_clouds_download_packed(sdr_pipeline* p, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt,
+                                                int64_t* offsets);
 
 /* ---- frame-parallel stream over the GPUs of one box (BASELINE config 4; the video loop of stereo_displayer.cpp:145-198
  *      with frames sharded by index, no collective: frames share no state) ----
@@ -241,15 +279,37 @@ SDR_API int sdr_pipeline_clouds_download(sdr_pipeline* p, int n, float* const* x
  * (valid during the call) and the cloud view (device pointers, valid during the call). */
 typedef int (*sdr_frame_source)(void* user, int64_t index, sdr_image* sbs);
 typedef void (*sdr_frame_sink)(void* user, int64_t index, int device, const sdr_image* disp, const sdr_cloud_view* cloud);
+/* The frame's filtered cloud in pinned HOST memory (valid during the call): n points, xyz f32[n][3], rgb u8[n][3]. */
+typedef void (*sdr_cloud_sink)(void* user, int64_t index, int device, int64_t n, const float* xyz, const uint8_t* rgb);
 typedef struct sdr_stream_stats {
     int64_t frames;        /* frames processed */
     double seconds;        /* wall time of the whole run */
     double frames_per_s;
     int64_t per_device[16];
+    uint64_t kernel_launches; /* this library's kernels launched by the run */
+    int64_t h2d_bytes, d2h_bytes; /* bytes copied host->device (frames) and device->host (maps, clouds) by the run */
 } sdr_stream_stats;
 SDR_API int sdr_stream_run(const int* devices, int n_devices, int handles_per_device, const sdr_calibration* calib,
                            const sdr_pipeline_options* opt, int64_t n_frames, sdr_frame_source source, sdr_frame_sink sink, void* user,
                            sdr_stream_stats* stats);
+/* The persistent form: contexts, pipelines, device scratch and pinned result buffers are created once (create) and reused
+ * by every process() call; one process() at a time. download_clouds != 0: every batch's clouds are also copied to pinned
+ * host memory (packed, one copy per array) and handed to cloud_sink. */
+typedef struct sdr_stream sdr_stream;
+SDR_API int sdr_stream_create(const int* devices, int n_devices, int handles_per_device, const sdr_calibration* calib,
+                              const sdr_pipeline_options* opt, int download_clouds, sdr_stream** out);
+SDR_API void sdr_stream_destroy(sdr_stream* s);
+SDR_API int sdr_stream_process(sdr_stream* s, int64_t n_frames, sdr_frame_source source, sdr_frame_sink sink, sdr_cloud_sink cloud_sink,
+                               void* user, sdr_stream_stats* stats);
+/* process() over a pool of SBS frames at a constant stride, frame i of the stream = pool frame (i mod n_pool), no callback
+ * into the host language (BASELINE config 4: 64 unique pairs cycled to 4096); results land in the workers' pinned
+ * buffers and are dropped. mem: sdr_mem of the pool. */
+SDR_API int sdr_stream_process_pool(sdr_stream* s, int64_t n_frames, const void* pool_base, int64_t n_pool, size_t frame_stride,
+                                    size_t step_bytes, int mem, sdr_stream_stats* stats);
+/* Binds the calling thread (and the threads it creates later) to the CPUs of the NUMA node `device` is attached to, so that
+ * pinned buffers allocated afterwards and the copies that use them stay on the GPU's socket. Returns the node, or -1 when the
+ * topology is not visible (nothing changes then). The stream workers do this themselves. */
+SDR_API int sdr_bind_host_to_device(int device);
 
 #ifdef __cplusplus
 }

@@ -74,13 +74,17 @@ SYMBOLS = [
     "sdr_rectifier_create", "sdr_rectifier_destroy", "sdr_rectifier_get_maps", "sdr_rectify",
     "sdr_remap_with_maps", "sdr_bgr2gray",
     "sdr_sgbm_create", "sdr_sgbm_destroy", "sdr_sgbm_compute", "sdr_sgbm_compute_batch",
-    "sdr_sgbm_set_profiling", "sdr_sgbm_stage_times", "sdr_sgbm_debug_read",
+    "sdr_sgbm_set_profiling", "sdr_sgbm_stage_times", "sdr_sgbm_debug_read", "sdr_sgbm_set_option",
+    "sdr_pipeline_set_sgbm_option", "sdr_sgbm_split_create", "sdr_sgbm_split_destroy", "sdr_sgbm_split_compute",
+    "sdr_sgbm_split_synchronize", "sdr_sgbm_split_last_stats", "sdr_sgbm_split_last_error",
     "sdr_sgbm_stripe_rows", "sdr_sgbm_match_stripes", "sdr_sgbm_postfilter",
     "sdr_median3_16s", "sdr_filter_speckles", "sdr_disp_to_float", "sdr_reproject_to_3d",
     "sdr_cloud_create", "sdr_cloud_destroy", "sdr_voxelgrid", "sdr_depth_cloud", "sdr_cloud_download",
     "sdr_pipeline_create", "sdr_pipeline_destroy", "sdr_pipeline_run", "sdr_pipeline_stage_times",
-    "sdr_pipeline_cloud_download", "sdr_pipeline_clouds_download", "sdr_pipeline_set_profiling",
+    "sdr_pipeline_cloud_download", "sdr_pipeline_clouds_download", "sdr_pipeline_clouds_download_packed",
+    "sdr_pipeline_set_profiling",
     "sdr_measure_distance", "sdr_depth_coverage", "sdr_cloud_save_pcd_binary", "sdr_stream_run",
+    "sdr_stream_create", "sdr_stream_destroy", "sdr_stream_process", "sdr_stream_process_pool", "sdr_bind_host_to_device",
 ]
 
 _lib = None
@@ -103,7 +107,7 @@ def lib():
         L.sdr_kernel_launches.argtypes = [C.c_void_p]
         L.sdr_destroy.argtypes = [C.c_void_p]
         L.sdr_destroy.restype = None
-        for n in ("sdr_rectifier_destroy", "sdr_sgbm_destroy", "sdr_cloud_destroy", "sdr_pipeline_destroy"):
+        for n in ("sdr_rectifier_destroy", "sdr_sgbm_destroy", "sdr_cloud_destroy", "sdr_pipeline_destroy", "sdr_stream_destroy", "sdr_sgbm_split_destroy"):
             if hasattr(L, n):
                 getattr(L, n).argtypes = [C.c_void_p]
                 getattr(L, n).restype = None
@@ -257,6 +261,11 @@ class Sgbm:
         self.ctx.check(lib().sdr_sgbm_postfilter(self._h, C.byref(ri), C.byref(oi)))
         return out
 
+    def set_option(self, name, value):
+        """Kernel-selection knob (sdr_sgbm_set_option); results never depend on it."""
+        self.ctx.check(lib().sdr_sgbm_set_option(self._h, name.encode(), int(value)))
+        return self
+
     def set_profiling(self, on=True):
         lib().sdr_sgbm_set_profiling(self._h, int(on))
 
@@ -274,6 +283,62 @@ class Sgbm:
     def close(self):
         if self._h:
             lib().sdr_sgbm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SplitStats(C.Structure):
+    _fields_ = [("n_parts", C.c_int), ("n_stripes", C.c_int), ("device", C.c_int * 16), ("stripes", C.c_int * 16),
+                ("input_rows", C.c_int * 16), ("peer_access", C.c_int * 16), ("input_bytes", C.c_int64 * 16),
+                ("gather_bytes", C.c_int64 * 16), ("ms", C.c_float)]
+
+
+class SgbmSplit:
+    """One oversize frame split by stripes over several GPUs in one process (sdr_sgbm_split_*; BASELINE config 5)."""
+
+    def __init__(self, devices, params):
+        self.params = params
+        self._h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        rc = lib().sdr_sgbm_split_create(devs, len(devices), C.byref(params), C.byref(self._h))
+        if rc != SDR_OK:
+            raise SdrError(rc, "sdr_sgbm_split_create(%r) failed" % (list(devices),))
+        lib().sdr_sgbm_split_last_error.restype = C.c_char_p
+        lib().sdr_sgbm_split_last_error.argtypes = [C.c_void_p]
+
+    def compute(self, left, right, out=None):
+        li, _ = as_image(left, 1); ri, _ = as_image(right, 1)
+        if out is None:
+            out = _empty_like_kind(left, tuple(left.shape), np.int16, "int16")
+        oi, _ = as_image(out, 1)
+        rc = lib().sdr_sgbm_split_compute(self._h, C.byref(li), C.byref(ri), C.byref(oi))
+        if rc != SDR_OK:
+            raise SdrError(rc, (lib().sdr_sgbm_split_last_error(self._h) or b"").decode())
+        return out
+
+    def synchronize(self):
+        rc = lib().sdr_sgbm_split_synchronize(self._h)
+        if rc != SDR_OK:
+            raise SdrError(rc, "sdr_sgbm_split_synchronize failed")
+
+    def stats(self):
+        st = SplitStats()
+        rc = lib().sdr_sgbm_split_last_stats(self._h, C.byref(st))
+        if rc != SDR_OK:
+            raise SdrError(rc, "sdr_sgbm_split_last_stats failed")
+        n = st.n_parts
+        return dict(ms=float(st.ms), n_parts=n, n_stripes=st.n_stripes, device=list(st.device[:n]), stripes=list(st.stripes[:n]),
+                    input_rows=list(st.input_rows[:n]), peer_access=list(st.peer_access[:n]), input_bytes=list(st.input_bytes[:n]),
+                    gather_bytes=list(st.gather_bytes[:n]))
+
+    def close(self):
+        if self._h:
+            lib().sdr_sgbm_split_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -516,6 +581,20 @@ class Pipeline:
             nb += int(v.n) * per_pt + (0 if v.passthrough else int(v.n) * per_vox)
         return nb
 
+    def set_sgbm_option(self, name, value):
+        self.ctx.check(lib().sdr_pipeline_set_sgbm_option(self._h, name.encode(), int(value)))
+        return self
+
+    def clouds_to_host_packed(self, n, xyz, rgb, idx=None, cnt=None):
+        """All n clouds of the last run, packed back to back, into caller buffers (ideally pinned; flat arrays big enough for
+        the sum of the cloud sizes): one device->host copy per array and one wait. Returns (offsets[n+1], bytes copied)."""
+        off = (C.c_int64 * (n + 1))()
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)   # noqa: E731
+        self.ctx.check(lib().sdr_pipeline_clouds_download_packed(self._h, ptr(xyz), ptr(rgb), ptr(idx), ptr(cnt), off))
+        total = int(off[n])
+        per = (12 if xyz is not None else 0) + (3 if rgb is not None else 0) + (4 if idx is not None else 0) + (4 if cnt is not None else 0)
+        return np.array(off[:], np.int64), total * per
+
     def set_profiling(self, on=True):
         lib().sdr_pipeline_set_profiling(self._h, int(on))
 
@@ -538,11 +617,86 @@ class Pipeline:
 
 
 class StreamStats(C.Structure):
-    _fields_ = [("frames", C.c_int64), ("seconds", C.c_double), ("frames_per_s", C.c_double), ("per_device", C.c_int64 * 16)]
+    _fields_ = [("frames", C.c_int64), ("seconds", C.c_double), ("frames_per_s", C.c_double), ("per_device", C.c_int64 * 16),
+                ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
+def bind_host_to_device(device):
+    """Bind this thread (and threads / pinned allocations made later) to the GPU's NUMA node; -1 if the topology is hidden."""
+    return int(lib().sdr_bind_host_to_device(int(device)))
+
+
+class Stream:
+    """Persistent frame-parallel runner (sdr_stream_*): native worker threads, one per (device, handle)."""
+
+    def __init__(self, devices, handles_per_device, calib, sgbm_params, voxel_opt, handle_missing=True, batch=8, download_clouds=True):
+        self.opt = PipelineOptions(sgbm_params, voxel_opt, int(bool(handle_missing)), int(batch), 0)
+        self._h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        rc = lib().sdr_stream_create(devs, len(devices), int(handles_per_device), C.byref(calib), C.byref(self.opt),
+                                     int(bool(download_clouds)), C.byref(self._h))
+        if rc != SDR_OK:
+            raise SdrError(rc, "sdr_stream_create failed")
+
+    def process_pool(self, n_frames, pool, mem=None):
+        """pool: [P][H][2W][3] uint8, numpy (host / pinned) or torch cuda tensor; frame i of the stream = pool[i mod P]."""
+        if _is_torch(pool):
+            ptr, stride, step = pool.data_ptr(), pool.stride(0), pool.stride(1)
+            mem = MEM_DEVICE if mem is None else mem
+        else:
+            ptr, stride, step = pool.ctypes.data, pool.strides[0], pool.strides[1]
+            mem = MEM_PINNED if mem is None else mem
+        st = StreamStats()
+        rc = lib().sdr_stream_process_pool(self._h, C.c_int64(n_frames), C.c_void_p(ptr), C.c_int64(len(pool)), C.c_size_t(stride),
+                                           C.c_size_t(step), int(mem), C.byref(st))
+        if rc != SDR_OK:
+            raise SdrError(rc, "sdr_stream_process_pool failed")
+        return st
+
+    def process(self, n_frames, frames, on_result=None, on_cloud=None):
+        """frames: list of SBS numpy arrays (cycled). on_result(index, device, disp, n_cloud_points) / on_cloud(index, device,
+        xyz, rgb) are called from worker threads with views that are valid during the call."""
+        imgs = [as_image(f, 3)[0] for f in frames]
+
+        def src(_u, i, out):
+            out[0] = imgs[i % len(imgs)]
+            return SDR_OK
+
+        def snk(_u, i, dev, disp, cloud):
+            d = disp[0]
+            arr = np.ctypeslib.as_array(C.cast(d.data, C.POINTER(C.c_int16)), shape=(d.rows, d.cols))
+            on_result(int(i), int(dev), arr, int(cloud[0].n))
+
+        def csnk(_u, i, dev, n, xyz, rgb):
+            n = int(n)
+            x = np.ctypeslib.as_array(xyz, shape=(n, 3)) if n else np.empty((0, 3), np.float32)
+            c = np.ctypeslib.as_array(rgb, shape=(n, 3)) if n else np.empty((0, 3), np.uint8)
+            on_cloud(int(i), int(dev), x, c)
+
+        cb_src = FRAME_SOURCE(src)
+        cb_snk = FRAME_SINK(snk) if on_result is not None else C.cast(None, FRAME_SINK)
+        cb_c = CLOUD_SINK(csnk) if on_cloud is not None else C.cast(None, CLOUD_SINK)
+        st = StreamStats()
+        rc = lib().sdr_stream_process(self._h, C.c_int64(n_frames), cb_src, cb_snk, cb_c, None, C.byref(st))
+        if rc != SDR_OK:
+            raise SdrError(rc, "sdr_stream_process failed")
+        return st
+
+    def close(self):
+        if self._h:
+            lib().sdr_stream_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 FRAME_SOURCE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.POINTER(Image))
 FRAME_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int, C.POINTER(Image), C.POINTER(CloudView))
+CLOUD_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_uint8))
 
 
 def stream_run(devices, handles_per_device, calib, sgbm_params, voxel_opt, frames, n_frames=None, handle_missing=True, batch=4,

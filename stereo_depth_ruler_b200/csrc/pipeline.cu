@@ -17,6 +17,42 @@ struct sdr_pipeline {
     StageTimer timer;
 };
 
+static int check_size(sdr_ctx* ctx, const sdr_image* im, int W, int H, const char* what) {
+    if (im->cols != W || im->rows != H)
+        return SDR_FAIL(ctx, SDR_ESIZE, "pipeline: %s must be %dx%d (the calibration size), got %dx%d", what, W, H, im->cols, im->rows);
+    return SDR_OK;
+}
+
+// n caller frames <-> a dense device block [n][rows][row_bytes]. One cudaMemcpyAsync for the whole batch when the caller's
+// frames are dense (step == row_bytes) and consecutive in memory (slices of one staging block), one per frame when they
+// are only dense, a pitched copy per frame otherwise (ROI views).
+static int copy_frames(sdr_ctx* ctx, bool to_device, uint8_t* dev, size_t dev_frame, size_t row_bytes, const sdr_image* im, int n, int rows) {
+    cudaStream_t st = ctx->stream;
+    const size_t frame = row_bytes * rows;
+    bool dense = dev_frame == frame, consecutive = true;
+    for (int i = 0; i < n; i++) {
+        dense = dense && im[i].step_bytes == row_bytes;
+        consecutive = consecutive && (const uint8_t*)im[i].data == (const uint8_t*)im[0].data + (size_t)i * frame;
+    }
+    if (dense && consecutive) {
+        if (to_device) SDR_CUDA(ctx, cudaMemcpyAsync(dev, im[0].data, frame * n, cudaMemcpyDefault, st));
+        else SDR_CUDA(ctx, cudaMemcpyAsync(im[0].data, dev, frame * n, cudaMemcpyDefault, st));
+        return SDR_OK;
+    }
+    for (int i = 0; i < n; i++) {
+        uint8_t* d = dev + (size_t)i * dev_frame;
+        if (im[i].step_bytes == row_bytes) {
+            if (to_device) SDR_CUDA(ctx, cudaMemcpyAsync(d, im[i].data, frame, cudaMemcpyDefault, st));
+            else SDR_CUDA(ctx, cudaMemcpyAsync(im[i].data, d, frame, cudaMemcpyDefault, st));
+        } else if (to_device) {
+            SDR_CUDA(ctx, cudaMemcpy2DAsync(d, row_bytes, im[i].data, im[i].step_bytes, row_bytes, rows, cudaMemcpyDefault, st));
+        } else {
+            SDR_CUDA(ctx, cudaMemcpy2DAsync(im[i].data, im[i].step_bytes, d, row_bytes, row_bytes, rows, cudaMemcpyDefault, st));
+        }
+    }
+    return SDR_OK;
+}
+
 extern "C" int sdr_pipeline_create(sdr_ctx* ctx, const sdr_calibration* calib, const sdr_pipeline_options* opt, sdr_pipeline** out) {
     if (!ctx || !calib || !opt || !out) return SDR_EINVAL;
     if (opt->batch < 1) return SDR_FAIL(ctx, SDR_EINVAL, "pipeline: batch must be >= 1");
@@ -60,6 +96,14 @@ extern "C" int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sd
         if (sbs[i].cols != 2 * W || sbs[i].rows != H)
             return SDR_FAIL(ctx, SDR_ESIZE, "pipeline: SBS frame must be %dx%d, got %dx%d", 2 * W, H, sbs[i].cols, sbs[i].rows);
     }
+    // every caller-owned output is checked before anything is queued: exactly W x H (a smaller Mat, e.g. the half-resolution
+    // map of the reference's live path, would be overrun by the copies below)
+    for (int i = 0; i < n; i++) {
+        if (disp && ((rc = sdr_check_image(ctx, &disp[i], 1, 2, "disp")) || (rc = check_size(ctx, &disp[i], W, H, "disp")))) return rc;
+        if (points && ((rc = sdr_check_image(ctx, &points[i], 3, 4, "points")) || (rc = check_size(ctx, &points[i], W, H, "points")))) return rc;
+        if (left_rect && ((rc = sdr_check_image(ctx, &left_rect[i], 3, 1, "left_rect")) || (rc = check_size(ctx, &left_rect[i], W, H, "left_rect"))))
+            return rc;
+    }
     p->timer.begin(st);
     // 1. frames to the device (used in place when they are already there at a constant stride)
     const size_t sbs_row = (size_t)2 * W * 3, sbs_frame_c = sbs_row * H;
@@ -74,9 +118,7 @@ extern "C" int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sd
         S0 = (const uint8_t*)sbs[0].data; sstep = sbs[0].step_bytes;
     } else {
         if ((rc = p->sbs.reserve(ctx, sbs_frame_c * n))) return rc;
-        for (int i = 0; i < n; i++)
-            SDR_CUDA(ctx, cudaMemcpy2DAsync(p->sbs.as<uint8_t>() + (size_t)i * sbs_frame_c, sbs_row, sbs[i].data, sbs[i].step_bytes, sbs_row, H,
-                                            cudaMemcpyDefault, st));
+        if ((rc = copy_frames(ctx, true, p->sbs.as<uint8_t>(), sbs_frame_c, sbs_row, sbs, n, H))) return rc;
         S0 = p->sbs.as<uint8_t>(); sstep = sbs_row; sframe = sbs_frame_c;
     }
     p->timer.mark(st, "h2d");
@@ -116,24 +158,10 @@ extern "C" int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sd
             return rc;
         p->timer.mark(st, "voxelgrid");
     }
-    // 5. outputs
-    for (int i = 0; i < n; i++) {
-        if (disp) {
-            if ((rc = sdr_check_image(ctx, &disp[i], 1, 2, "disp")) ) return rc;
-            SDR_CUDA(ctx, cudaMemcpy2DAsync(disp[i].data, disp[i].step_bytes, p->disp.as<uint8_t>() + (size_t)i * gray_frame * 2, (size_t)W * 2,
-                                            (size_t)W * 2, H, cudaMemcpyDefault, st));
-        }
-        if (points) {
-            if ((rc = sdr_check_image(ctx, &points[i], 3, 4, "points"))) return rc;
-            SDR_CUDA(ctx, cudaMemcpy2DAsync(points[i].data, points[i].step_bytes, p->points.as<uint8_t>() + (size_t)i * W * H * 12, (size_t)W * 12,
-                                            (size_t)W * 12, H, cudaMemcpyDefault, st));
-        }
-        if (left_rect) {
-            if ((rc = sdr_check_image(ctx, &left_rect[i], 3, 1, "left_rect"))) return rc;
-            SDR_CUDA(ctx, cudaMemcpy2DAsync(left_rect[i].data, left_rect[i].step_bytes, p->rectL.as<uint8_t>() + (size_t)i * bgr_frame, (size_t)W * 3,
-                                            (size_t)W * 3, H, cudaMemcpyDefault, st));
-        }
-    }
+    // 5. outputs (one copy per output kind when the caller's frames are dense and consecutive, e.g. slices of one pinned block)
+    if (disp && (rc = copy_frames(ctx, false, p->disp.as<uint8_t>(), gray_frame * 2, (size_t)W * 2, disp, n, H))) return rc;
+    if (points && (rc = copy_frames(ctx, false, p->points.as<uint8_t>(), (size_t)W * H * 12, (size_t)W * 12, points, n, H))) return rc;
+    if (left_rect && (rc = copy_frames(ctx, false, p->rectL.as<uint8_t>(), bgr_frame, (size_t)W * 3, left_rect, n, H))) return rc;
     p->timer.mark(st, "d2h");
     int status = SDR_OK;
     if (views) {
@@ -142,7 +170,13 @@ extern "C" int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sd
         else if (rc) return rc;
     }
     SDR_CUDA(ctx, sdr_wait(ctx));
+    if ((rc = sdr_sgbm_take_sweep_error(p->sgbm))) return rc;   // a sweep of THIS run gave up on a halo: its maps are garbage
     return status;
+}
+
+extern "C" int sdr_pipeline_set_sgbm_option(sdr_pipeline* p, const char* name, int value) {
+    if (!p || !p->sgbm) return SDR_EINVAL;
+    return sdr_sgbm_set_option(p->sgbm, name, value);
 }
 
 extern "C" int sdr_pipeline_set_profiling(sdr_pipeline* p, int enabled) {
@@ -175,4 +209,10 @@ extern "C" int sdr_pipeline_clouds_download(sdr_pipeline* p, int n, float* const
     }
     SDR_CUDA(ctx, sdr_wait(ctx));   // one host wait for the whole batch
     return SDR_OK;
+}
+
+extern "C" int sdr_pipeline_clouds_download_packed(sdr_pipeline* p, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt, int64_t* offsets) {
+    if (!p || !p->cloud) return SDR_EINVAL;
+    SDR_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    return sdr_cloud_download_packed(p->cloud, xyz, rgb, idx, cnt, offsets, true);
 }

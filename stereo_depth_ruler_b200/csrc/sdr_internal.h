@@ -111,4 +111,7 @@ int sdr_cloud_enqueue(sdr_cloud* c, int frames, const uint8_t* points, size_t ps
                       const sdr_voxel_options* opt);
 int sdr_cloud_finish(sdr_cloud* c, sdr_cloud_view* views);
 int sdr_cloud_download_frame(sdr_cloud* c, int f, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt, bool wait);
+int sdr_cloud_download_packed(sdr_cloud* c, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt, int64_t* offsets, bool wait);
 StageTimer* sdr_sgbm_timer(sdr_sgbm* m);
+// after a host wait on the ctx stream: SDR_ECUDA (once) if a cooperative sweep of the finished work timed out on a halo
+int sdr_sgbm_take_sweep_error(sdr_sgbm* m);

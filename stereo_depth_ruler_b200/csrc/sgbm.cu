@@ -16,6 +16,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -26,6 +27,7 @@ struct Seg {
 struct Geom {
     int W, H, D, minD, W1, minX1, maxX1;
     int nseg, crows;
+    int hrow0, hrows;   // output rows of the selected stripes [hrow0, hrow0 + hrows): what the horizontal kernels cover
     Seg seg[4];
     int SW2, SH2, P1, P2, ftzero, uq, d12, three_way;
     uint32_t uq_magic;  // ceil(2^32 / (100 - uq)): exact n / (100 - uq) for n < 2^32 / 100 by one __umulhi
@@ -76,10 +78,10 @@ __device__ __forceinline__ void prefilt_px(const uint8_t* img, size_t pitch, int
 // shared memory with a funnel shift) instead of 24 single bytes per pixel.
 __global__ void __launch_bounds__(128) k_prefilter(Geom g, const uint8_t* left, size_t lpitch, size_t lframe,
                                                    const uint8_t* right, size_t rpitch, size_t rframe, int4* PL,
-                                                   uint8_t* PR) {
+                                                   uint8_t* PR, int y0) {
     __shared__ int16_t sS[136], sR[136];               // (Sobel, raw) of pixels xs0 .. xs0 + 133 (0 outside the image)
     __shared__ __align__(4) uint8_t pb[6][136];        // RIGHT: byte planes (v, lo, 255-hi) x 2 channels at j = I0 .. I0 + 130
-    const int t = threadIdx.x, y = blockIdx.y;
+    const int t = threadIdx.x, y = y0 + blockIdx.y;
     const int b = blockIdx.z >> 1, eye = blockIdx.z & 1;
     const uint8_t* img = eye ? right + (size_t)b * rframe : left + (size_t)b * lframe;
     const size_t pitch = eye ? rpitch : lpitch;
@@ -1049,9 +1051,9 @@ __global__ void __launch_bounds__(THREADS) k_path_h(Geom g, const int16_t* __res
     constexpr int CPB = THREADS / G;
     __shared__ __align__(16) int16_t smS[WTA ? CPB * 2 * NP * G : 8];
     const int lane = threadIdx.x & 31, lg = lane & (G - 1);
-    const int row = blockIdx.x * CPB + threadIdx.x / G;
-    bool active = row < g.H;
-    int y = min(row, g.H - 1);
+    const int row = g.hrow0 + blockIdx.x * CPB + threadIdx.x / G;
+    bool active = row < g.hrow0 + g.hrows;
+    int y = min(row, g.hrow0 + g.hrows - 1);
     const int b = blockIdx.z;
     const int D = g.D;
     int si = -1;
@@ -1139,9 +1141,9 @@ __global__ void __launch_bounds__(THREADS) k_path_hh(Geom g, const int16_t* __re
     __shared__ __align__(16) int16_t smS[CPB * 2 * NP * G];
     const int lane = threadIdx.x & 31, lg = lane & (G - 1);
     const int chain = blockIdx.x * CPB + threadIdx.x / G;
-    const int row = chain >> 1, dir = (chain & 1) ? -1 : +1;
-    bool active = row < g.H;
-    int y = min(row, g.H - 1);
+    const int row = g.hrow0 + (chain >> 1), dir = (chain & 1) ? -1 : +1;
+    bool active = row < g.hrow0 + g.hrows;
+    int y = min(row, g.hrow0 + g.hrows - 1);
     const int b = blockIdx.z;
     const int D = g.D, W1 = g.W1;
     int si = -1;
@@ -1219,9 +1221,9 @@ __global__ void __launch_bounds__(128) k_path_h2(Geom g, const int16_t* __restri
     const int D = g.D;
     const int NWARP = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gidx = lane / G, lg = lane & (G - 1);
-    const int row = (blockIdx.x * NWARP + warp) * ROWS + gidx;
-    bool active = row < g.H;
-    int y = min(row, g.H - 1);
+    const int row = g.hrow0 + (blockIdx.x * NWARP + warp) * ROWS + gidx;
+    bool active = row < g.hrow0 + g.hrows;
+    int y = min(row, g.hrow0 + g.hrows - 1);
     const int b = blockIdx.z;
     int si = -1;
     for (int i = 0; i < g.nseg; i++)
@@ -1347,6 +1349,22 @@ __global__ void __launch_bounds__(256) k_lrcheck(Geom g, const int16_t* __restri
     }
 }
 
+// Kernel-selection knobs of a matcher handle (sdr_sgbm_set_option). None of them changes a result: every variant is
+// bit-exact (tests/test_gpu_sgbm.py runs them against the oracle); they exist for A/B measurements and for callers that
+// know how many matchers share the device. 0 = the built-in default unless stated otherwise.
+struct SgbmTune {
+    int fused_sweep = 1;    // cooperative down/diagonal sweep (k_path_v3); 0: one launch per direction (k_path_v)
+    int cost_fusion = 1;    // cost volume inside the sweep kernel (k_cost_path_v3)
+    int path_hh = -1;       // both horizontal paths in one launch (k_path_hh): 1 / 0, -1 = automatic (on for a lone matcher)
+    int shared_device = 0;  // 1: other matchers run on this device at the same time (what "automatic" looks at)
+    int cf_cols = 0;        // strip width of the fused kernel: 32 / 64
+    int cf_prod = 0;        // its producer threads: 128 / 256
+    int cf_fpl = 0;         // frames per cooperative launch
+    int v3_stages = 0;      // TMA ring depth of k_path_v3
+    int h_legacy = 0;       // register-prefetch k_path_h instead of the TMA-ring k_path_h2 for L->R
+    int h_k = 0, h_stages = 0, h_warps = 0, hb_threads = 0, hb_ring = -1, hh_threads = 0;
+};
+
 // ---- dispatch over (NP, G): D = 2*G*NP ----------------------------------------------------
 struct PathCfg {
     int NP, G;
@@ -1364,15 +1382,12 @@ int launch_path_v(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int1
     return SDR_OK;
 }
 template <int NP>
-int launch_path_h(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int16_t* S, int dir, int acc, bool wta_on,
+int launch_path_h(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, const int16_t* C, int16_t* S, int dir, int acc, bool wta_on,
                   int16_t* dispraw, uint32_t* wta) {
     constexpr int G = 8;
-    static const bool legacy = getenv("SDR_PATH_H_LEGACY") != nullptr;   // A/B switch: register-prefetch version
+    const bool legacy = tn.h_legacy != 0;   // A/B switch: register-prefetch version
     // tuning knobs (defaults chosen on a B200 at 1280x720x128, batch 8)
-    static const int env_k = getenv("SDR_H_K") ? atoi(getenv("SDR_H_K")) : 0;
-    static const int env_st = getenv("SDR_H_STAGES") ? atoi(getenv("SDR_H_STAGES")) : 0;
-    static const int env_w = getenv("SDR_H_WARPS") ? atoi(getenv("SDR_H_WARPS")) : 0;
-    static const int env_bt = getenv("SDR_HB_THREADS") ? atoi(getenv("SDR_HB_THREADS")) : 0;
+    const int env_k = tn.h_k, env_st = tn.h_stages, env_w = tn.h_warps, env_bt = tn.hb_threads;
     const int K = env_k > 0 ? env_k : std::max(1, 512 / g.D);            // steps per staged chunk: about 1 KB per row (512 B: L->R alone 0.88 -> 0.82 ms at
                                                                           // batch 8, but slower with other handles in flight, at D = 256 and for one frame)
     const int nst = env_st >= 2 && env_st <= H_STAGES_MAX ? env_st : H_STAGES_DEFAULT;
@@ -1380,9 +1395,9 @@ int launch_path_h(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int1
     const size_t smem = (size_t)nwarp * nst * 2 * 4 * K * g.D * 2;       // [warp][stage][C|S][row][K][D]
     // measured (1280x720x128, batch 8): L->R 1.12 -> 1.01 ms with the ring; the R->L + WTA kernel is bound by its own
     // dependent arithmetic and loses with the extra shared-memory hop (0.94 -> 1.52 ms), so it keeps the register prefetch
-    static const bool wta_ring = getenv("SDR_HB_RING") ? atoi(getenv("SDR_HB_RING")) != 0 : HB_RING_DEFAULT;
+    const bool wta_ring = tn.hb_ring >= 0 ? tn.hb_ring != 0 : HB_RING_DEFAULT;
     if (!legacy && (!wta_on || wta_ring) && smem <= ctx->smem_optin) {
-        dim3 grid(div_up(g.H, 4 * nwarp), 1, batch);
+        dim3 grid(div_up(g.hrows, 4 * nwarp), 1, batch);
         if (wta_on) {
             SDR_CUDA(ctx, cudaFuncSetAttribute(k_path_h2<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_path_h2<NP, true><<<grid, 32 * nwarp, smem, ctx->stream>>>(g, C, S, dir, acc, K, nst, dispraw, wta);
@@ -1394,7 +1409,7 @@ int launch_path_h(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int1
         return SDR_OK;
     }
     const int threads = env_bt == 32 || env_bt == 64 || env_bt == 128 ? env_bt : HB_THREADS_DEFAULT;
-    dim3 grid(div_up(g.H, threads / G), 1, batch);
+    dim3 grid(div_up(g.hrows, threads / G), 1, batch);
     if (wta_on) {
         if (threads == 32) k_path_h<NP, G, true, 32><<<grid, 32, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
         else if (threads == 64) k_path_h<NP, G, true, 64><<<grid, 64, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
@@ -1409,11 +1424,11 @@ int launch_path_h(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int1
 }
 
 template <int NP>
-int launch_path_hh(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int16_t* S, int16_t* dispraw, uint32_t* wta) {
+int launch_path_hh(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, const int16_t* C, int16_t* S, int16_t* dispraw, uint32_t* wta) {
     constexpr int G = 8;
-    static const int env_t = getenv("SDR_HH_THREADS") ? atoi(getenv("SDR_HH_THREADS")) : 0;   // tuning knob
+    const int env_t = tn.hh_threads;   // tuning knob
     const int threads = env_t == 32 || env_t == 64 || env_t == 128 ? env_t : 64;   // 64: 2 warps = 4 rows x 2 directions per CTA
-    dim3 grid(div_up(2 * g.H, threads / G), 1, batch);
+    dim3 grid(div_up(2 * g.hrows, threads / G), 1, batch);
     if (threads == 32) k_path_hh<NP, G, 32><<<grid, 32, 0, ctx->stream>>>(g, C, S, dispraw, wta);
     else if (threads == 128) k_path_hh<NP, G, 128><<<grid, 128, 0, ctx->stream>>>(g, C, S, dispraw, wta);
     else k_path_hh<NP, G, 64><<<grid, 64, 0, ctx->stream>>>(g, C, S, dispraw, wta);
@@ -1428,11 +1443,11 @@ struct V3Scratch {
 
 // Returns SDR_OK, an error, or -1 when the cooperative grid cannot be co-resident (caller falls back).
 template <int NP>
-int launch_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int16_t* S, int diry, int acc, V3Scratch& sc) {
+int launch_path_v3(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, const int16_t* C, int16_t* S, int diry, int acc, V3Scratch& sc) {
     constexpr int MINB = NP <= 8 ? 2 : 1;
     auto kern = acc ? k_path_v3<NP, MINB, true> : k_path_v3<NP, MINB, false>;
     const int nstrips = div_up(g.W1, V3_COLS);
-    static const int env_stages = getenv("SDR_V3_STAGES") ? atoi(getenv("SDR_V3_STAGES")) : 0;   // tuning knob
+    const int env_stages = tn.v3_stages;   // tuning knob
     int nst = acc ? 3 : V3_STAGES_DEFAULT;
     if (env_stages >= 2 && env_stages <= V3_STAGES_MAX) nst = acc ? std::min(env_stages, 3) : env_stages;
     const size_t smem = (size_t)4 * (V3_COLS + 2) * g.D * sizeof(int16_t) + (size_t)4 * (V3_COLS + 2) * sizeof(uint32_t) +
@@ -1470,7 +1485,7 @@ int launch_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int
 // Fused cost + top-down sweep. Returns SDR_OK, an error, or -1 when this configuration is not covered (caller runs
 // k_cost followed by k_path_v3 / k_path_v instead).
 template <int NP, int SW2, int CF_PROD, int COLS>
-int launch_cost_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int4* PL, const uint8_t* PR, int16_t* C, int16_t* S, V3Scratch& sc) {
+int launch_cost_path_v3(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, const int4* PL, const uint8_t* PR, int16_t* C, int16_t* S, V3Scratch& sc) {
     auto kern = k_cost_path_v3<NP, SW2, CF_PROD, COLS>;
     constexpr int CF_CONS = COLS * 8;
     const int nstrips = div_up(g.W1, COLS);
@@ -1483,7 +1498,7 @@ int launch_cost_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int4* PL, 
     if (cap < nstrips) return -1;
     // frames per cooperative launch: all that fit by default; fewer (SDR_CF_FPL) leaves part of every SM to the kernels of
     // other handles / streams, which the fused kernel otherwise shuts out (it takes the whole register file at 2 CTAs/SM)
-    static const int env_fpl = getenv("SDR_CF_FPL") ? atoi(getenv("SDR_CF_FPL")) : 0;
+    const int env_fpl = tn.cf_fpl;
     int fpl = std::min(batch, cap / nstrips);
     if (env_fpl > 0) fpl = std::min(fpl, env_fpl);
     int rc;
@@ -1510,12 +1525,13 @@ int launch_cost_path_v3(sdr_ctx* ctx, const Geom& g, int batch, const int4* PL, 
     return SDR_OK;
 }
 
-int launch_cost_path_fused(sdr_ctx* ctx, const Geom& g, int batch, const int4* PL, const uint8_t* PR, int16_t* C, int16_t* S, V3Scratch& sc,
-                           int env_cols) {
+int launch_cost_path_fused(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, const int4* PL, const uint8_t* PR, int16_t* C, int16_t* S,
+                           V3Scratch& sc) {
+    const int env_cols = tn.cf_cols;
     if (g.nseg != 1 || g.SW2 != g.SH2 || g.seg[0].src_start != 0 || g.crows != g.H) return -1;
     const int np = g.D / 16;
     if (g.D % 16) return -1;
-    static const int env_prod = getenv("SDR_CF_PROD") ? atoi(getenv("SDR_CF_PROD")) : 0;   // tuning knob: producer threads (128 | 256)
+    const int env_prod = tn.cf_prod;   // tuning knob: producer threads (128 | 256)
     const int prod = env_prod == 128 || env_prod == 256 ? env_prod : CF_PROD_DEFAULT;
     // D = 128: 64-column strips, one CTA per SM (512 consumer + 256 producer threads): half as many strip borders to hand
     // halos across, 2.06 -> 1.98 ms at 1280x720, batch 8. SDR_CF_COLS=32 selects the 32-column CTAs (two per SM).
@@ -1524,14 +1540,14 @@ int launch_cost_path_fused(sdr_ctx* ctx, const Geom& g, int batch, const int4* P
     const bool wide_fills = env_cols == 64 || (long long)div_up(g.W1, 64) * batch * 4 >= 3LL * ctx->sm_count;
     if (env_cols != 32 && np == 8 && wide_fills) {
         int rc64 = -1;
-        if (g.SW2 == 2) rc64 = launch_cost_path_v3<8, 2, 256, 64>(ctx, g, batch, PL, PR, C, S, sc);
-        else if (g.SW2 == 1) rc64 = launch_cost_path_v3<8, 1, 256, 64>(ctx, g, batch, PL, PR, C, S, sc);
+        if (g.SW2 == 2) rc64 = launch_cost_path_v3<8, 2, 256, 64>(ctx, tn, g, batch, PL, PR, C, S, sc);
+        else if (g.SW2 == 1) rc64 = launch_cost_path_v3<8, 1, 256, 64>(ctx, tn, g, batch, PL, PR, C, S, sc);
         if (rc64 != -1) return rc64;   // -1: does not fit this device, try the smaller CTAs
     }
 #define CF_CASE(NPV, SWV)                                                                                                  \
     if (np == NPV && g.SW2 == SWV)                                                                                         \
-        return prod == 128 ? launch_cost_path_v3<NPV, SWV, 128, 32>(ctx, g, batch, PL, PR, C, S, sc)                      \
-                           : launch_cost_path_v3<NPV, SWV, 256, 32>(ctx, g, batch, PL, PR, C, S, sc);
+        return prod == 128 ? launch_cost_path_v3<NPV, SWV, 128, 32>(ctx, tn, g, batch, PL, PR, C, S, sc)                      \
+                           : launch_cost_path_v3<NPV, SWV, 256, 32>(ctx, tn, g, batch, PL, PR, C, S, sc);
     CF_CASE(8, 2) CF_CASE(8, 1) CF_CASE(4, 2) CF_CASE(4, 1)
 #undef CF_CASE
     return -1;
@@ -1563,17 +1579,13 @@ int launch_cost_path_fused(sdr_ctx* ctx, const Geom& g, int batch, const int4* P
 // ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
-static std::atomic<int> g_live_sgbm[64];   // matcher handles alive per device (chooses the horizontal kernel variant)
 struct sdr_sgbm {
     sdr_ctx* ctx = nullptr;
     sdr_sgbm_params p{};
     DevBuf inL, inR, PL, PR, C, S, dispraw, wta, matched, out;
     SpeckleScratch speckle;
     V3Scratch v3;
-    bool use_fused_sweep = true;
-    bool use_cost_fusion = true;
-    int cf_cols = 0;                           // its strip width: 0 = automatic, 32 / 64 forced by SDR_CF_COLS
-    int hh_mode = -1;                          // both horizontal paths in one launch (k_path_hh): 1 / 0 forced by SDR_PATH_HH, -1 = automatic               // cost volume + top-down sweep in one kernel (k_cost_path_v3)
+    SgbmTune tune;                             // kernel-selection knobs (sdr_sgbm_set_option); results never depend on them
     int stripe_first = 0, stripe_count = -1;   // MODE_SGBM_3WAY: subset of the four stripes to match (-1 = all)
     bool skip_post = false;                    // stop after the raw matcher output (median / speckle run elsewhere)
     DevBuf post_in;
@@ -1581,6 +1593,8 @@ struct sdr_sgbm {
     Geom g{};
     int last_batch = 0;
 };
+
+int sdr_sgbm_take_sweep_error(sdr_sgbm* m);
 
 static int validate_params(sdr_ctx* ctx, const sdr_sgbm_params* p) {
     if (p->numDisparities <= 0 || p->numDisparities % 16 != 0)
@@ -1610,18 +1624,12 @@ extern "C" int sdr_sgbm_create(sdr_ctx* ctx, const sdr_sgbm_params* params, sdr_
     sdr_sgbm* m = new sdr_sgbm();
     m->ctx = ctx;
     m->p = *params;
-    m->use_fused_sweep = getenv("SDR_DISABLE_FUSED_SWEEP") == nullptr;   // A/B switch for the cooperative sweep
-    m->hh_mode = getenv("SDR_PATH_HH") ? (atoi(getenv("SDR_PATH_HH")) != 0 ? 1 : 0) : -1;
-    g_live_sgbm[ctx->device & 63].fetch_add(1);
-    m->cf_cols = getenv("SDR_CF_COLS") ? atoi(getenv("SDR_CF_COLS")) : 0;
-    m->use_cost_fusion = getenv("SDR_DISABLE_COST_FUSION") == nullptr;   // A/B switch for the fused cost + sweep kernel
     *out = m;
     return SDR_OK;
 }
 
 extern "C" void sdr_sgbm_destroy(sdr_sgbm* m) {
     if (!m) return;
-    g_live_sgbm[m->ctx->device & 63].fetch_sub(1);
     cudaSetDevice(m->ctx->device);
     for (DevBuf* b : {&m->inL, &m->inR, &m->PL, &m->PR, &m->C, &m->S, &m->dispraw, &m->wta, &m->matched, &m->out,
                       &m->speckle.parent, &m->speckle.count, &m->v3.halo, &m->v3.err, &m->post_in})
@@ -1690,6 +1698,8 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
         g.nseg = k;
         g.crows = crow;
     }
+    g.hrow0 = g.seg[0].dst_start;
+    g.hrows = g.seg[g.nseg - 1].src_end - g.hrow0;
     m->last_batch = batch;
     cudaStream_t st = ctx->stream;
     m->timer.begin(st);
@@ -1716,20 +1726,22 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
         if ((rc = m->S.reserve(ctx, vol * H * batch))) return rc;
         if ((rc = m->dispraw.reserve(ctx, img16 * batch))) return rc;
         if ((rc = m->wta.reserve(ctx, (size_t)batch * H * g.W1 * sizeof(uint32_t)))) return rc;
-        k_prefilter<<<dim3(div_up(W, 128), H, batch * 2), 128, 0, st>>>(g, L, lpitch, lframe, R, rpitch, rframe,
-                                                                         m->PL.as<int4>(), m->PR.as<uint8_t>());
+        // only the rows the selected stripes read (all of them unless a stripe subset was asked for)
+        const int py0 = g.seg[0].src_start, py1 = std::min(g.seg[g.nseg - 1].src_end + g.SH2, H);
+        k_prefilter<<<dim3(div_up(W, 128), py1 - py0, batch * 2), 128, 0, st>>>(g, L, lpitch, lframe, R, rpitch, rframe,
+                                                                                 m->PL.as<int4>(), m->PR.as<uint8_t>(), py0);
         SDR_LAUNCHED(ctx);
         m->timer.mark(st, "prefilter");
         const int16_t* C = m->C.as<int16_t>();
         int16_t* S = m->S.as<int16_t>();
         const int np = path_cfg(g.D).NP;
-        // a previous fused sweep that timed out on its neighbour flags poisons the handle
-        if (m->v3.host_err.p && *(volatile int*)m->v3.host_err.p)
-            return SDR_FAIL(ctx, SDR_ECUDA, "fused path sweep timed out waiting for a neighbouring strip");
+        // a fused sweep of an earlier, asynchronous (device-output) call that gave up on a neighbouring strip is reported
+        // here, once; the flag is cleared so the handle keeps working (calls that wait on the stream report it themselves)
+        if ((rc = sdr_sgbm_take_sweep_error(m))) return rc;
         // MODE_SGBM / MODE_HH: cost volume and top-down sweep in one kernel when the configuration is covered
         bool cost_done = false;
-        if (m->p.mode != SDR_MODE_SGBM_3WAY && m->use_fused_sweep && m->use_cost_fusion) {
-            rc = launch_cost_path_fused(ctx, g, batch, m->PL.as<int4>(), m->PR.as<uint8_t>(), m->C.as<int16_t>(), S, m->v3, m->cf_cols);
+        if (m->p.mode != SDR_MODE_SGBM_3WAY && m->tune.fused_sweep && m->tune.cost_fusion) {
+            rc = launch_cost_path_fused(ctx, m->tune, g, batch, m->PL.as<int4>(), m->PR.as<uint8_t>(), m->C.as<int16_t>(), S, m->v3);
             if (rc > 0) return rc;
             if (rc == SDR_OK) {
                 cost_done = true;
@@ -1766,9 +1778,9 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
             m->timer.mark(st, "path_v");
         } else {
             const int npass = m->p.mode == SDR_MODE_HH ? 2 : 1;
-            bool fused = m->use_fused_sweep;
+            bool fused = m->tune.fused_sweep != 0;
             for (int pass = cost_done ? 1 : 0; pass < npass && fused; pass++) {
-                NP_SWITCH(np, rc = launch_path_v3<NPc>(ctx, g, batch, C, S, pass == 0 ? +1 : -1, pass, m->v3));
+                NP_SWITCH(np, rc = launch_path_v3<NPc>(ctx, m->tune, g, batch, C, S, pass == 0 ? +1 : -1, pass, m->v3));
                 if (rc == -1) { fused = false; break; }   // grid cannot be co-resident: separate launches per direction
                 if (rc) return rc;
                 m->timer.mark(st, pass == 0 ? "path_v_fused_down" : "path_v_fused_up");
@@ -1785,16 +1797,16 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
         }
         // One matcher on this device (the reference's usage): the two-direction kernel is 4-13 % faster. Several handles in
         // flight (frame-parallel throughput): the two separate kernels leave room for each other's work.
-        const bool use_hh = m->hh_mode >= 0 ? m->hh_mode == 1 : g_live_sgbm[ctx->device & 63].load() == 1;
+        const bool use_hh = m->tune.path_hh >= 0 ? m->tune.path_hh == 1 : m->tune.shared_device == 0;
         if (use_hh) {   // both horizontal paths in one launch
-            NP_SWITCH(np, rc = launch_path_hh<NPc>(ctx, g, batch, C, S, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>()));
+            NP_SWITCH(np, rc = launch_path_hh<NPc>(ctx, m->tune, g, batch, C, S, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>()));
             if (rc) return rc;
             m->timer.mark(st, "path_h_both_wta");
         } else {
-            NP_SWITCH(np, rc = launch_path_h<NPc>(ctx, g, batch, C, S, +1, 1, false, nullptr, nullptr));
+            NP_SWITCH(np, rc = launch_path_h<NPc>(ctx, m->tune, g, batch, C, S, +1, 1, false, nullptr, nullptr));
             if (rc) return rc;
             m->timer.mark(st, "path_h_fwd");
-            NP_SWITCH(np, rc = launch_path_h<NPc>(ctx, g, batch, C, S, -1, 1, true, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>()));
+            NP_SWITCH(np, rc = launch_path_h<NPc>(ctx, m->tune, g, batch, C, S, -1, 1, true, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>()));
             if (rc) return rc;
             m->timer.mark(st, "path_h_bwd_wta");
         }
@@ -1814,6 +1826,17 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
         m->timer.mark(st, "speckle");
     }
     return SDR_OK;
+}
+
+// The cooperative sweeps (k_path_v3, k_cost_path_v3) set a device flag instead of hanging when a neighbouring strip never
+// publishes its halo; the flag is copied to pinned host memory behind every launch. Call after a host wait on the ctx
+// stream: returns SDR_ECUDA (once) when the work just waited for contains such a sweep -- its S volume and disparity are
+// garbage -- and re-arms the flag so the next compute starts clean.
+int sdr_sgbm_take_sweep_error(sdr_sgbm* m) {
+    if (!m->v3.host_err.p || !*(volatile int*)m->v3.host_err.p) return SDR_OK;
+    *(volatile int*)m->v3.host_err.p = 0;
+    if (m->v3.err.p) cudaMemsetAsync(m->v3.err.p, 0, sizeof(int), m->ctx->stream);
+    return SDR_FAIL(m->ctx, SDR_ECUDA, "fused path sweep timed out waiting for a neighbouring strip: the disparity of that compute is invalid");
 }
 
 int sdr_sgbm_run_device(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, size_t lframe, const uint8_t* R, size_t rpitch,
@@ -1884,7 +1907,10 @@ extern "C" int sdr_sgbm_compute_batch(sdr_sgbm* m, int n, const sdr_image* lefts
                                             cudaMemcpyDefault, ctx->stream));
             any_host |= disps[i].mem != SDR_MEM_DEVICE;
         }
-        if (any_host) SDR_CUDA(ctx, sdr_wait(ctx));
+        if (any_host) {
+            SDR_CUDA(ctx, sdr_wait(ctx));
+            if ((rc = sdr_sgbm_take_sweep_error(m))) return rc;   // this very call, not the next one, reports a broken sweep
+        }
     }
     return SDR_OK;
 }
@@ -1949,6 +1975,19 @@ extern "C" int sdr_sgbm_postfilter(sdr_sgbm* m, const sdr_image* raw, sdr_image*
                                  16 * m->p.speckleRange, m->speckle)))
         return rc;
     return sdr_stage_out_end(ctx, disp, vo);
+}
+
+extern "C" int sdr_sgbm_set_option(sdr_sgbm* m, const char* name, int value) {
+    if (!m || !name) return SDR_EINVAL;
+    SgbmTune& t = m->tune;
+    const struct { const char* n; int* p; } tab[] = {
+        {"fused_sweep", &t.fused_sweep}, {"cost_fusion", &t.cost_fusion}, {"path_hh", &t.path_hh}, {"shared_device", &t.shared_device},
+        {"cf_cols", &t.cf_cols}, {"cf_prod", &t.cf_prod}, {"cf_fpl", &t.cf_fpl}, {"v3_stages", &t.v3_stages}, {"h_legacy", &t.h_legacy},
+        {"h_k", &t.h_k}, {"h_stages", &t.h_stages}, {"h_warps", &t.h_warps}, {"hb_threads", &t.hb_threads}, {"hb_ring", &t.hb_ring},
+        {"hh_threads", &t.hh_threads}};
+    for (const auto& e : tab)
+        if (!strcmp(e.n, name)) { *e.p = value; return SDR_OK; }
+    return SDR_FAIL(m->ctx, SDR_EINVAL, "sdr_sgbm_set_option: unknown option '%s'", name);
 }
 
 extern "C" int sdr_sgbm_set_profiling(sdr_sgbm* m, int enabled) {

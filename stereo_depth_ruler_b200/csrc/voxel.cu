@@ -392,6 +392,13 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t* __res
 }
 
 // ---- run detection and reduction -------------------------------------------------------------
+// first output point of frame fr in the packed per-batch output arrays (every count is final before the reduction starts)
+__device__ __forceinline__ size_t cloud_base(const VoxParams* vp0, int fr, size_t npix) {
+    size_t base = 0;
+    for (int g = 0; g < fr; g++) base += vp0[g].overflow ? npix : (size_t)vp0[g].nvox;
+    return base;
+}
+
 __global__ void __launch_bounds__(256) k_vox_heads(const uint32_t* __restrict__ keys, int n, uint32_t* __restrict__ flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -408,7 +415,10 @@ __global__ void __launch_bounds__(256) k_vox_reduce(Source s, VoxParams* vp0, co
     const int i = blockIdx.x * blockDim.x + threadIdx.x, fr = blockIdx.y;
     VoxParams* vp = vp0 + fr;
     keys += (size_t)fr * n; vals += (size_t)fr * n; slot += (size_t)fr * n;
-    oxyz += (size_t)fr * n * 3; orgb += (size_t)fr * n * 3; oidx += (size_t)fr * n; ocnt += (size_t)fr * n;
+    {   // the clouds of a batch are packed back to back (frame fr starts where frame fr-1 ends): one copy brings them all home
+        const size_t base = cloud_base(vp0, fr, (size_t)s.W * s.H);
+        oxyz += base * 3; orgb += base * 3; oidx += base; ocnt += base;
+    }
     // every thread fetches the point at its own sorted position (parallel, coalesced key/val reads); the run heads then
     // add their run in sorted order (= ascending point index) out of shared memory, exactly the order of the sequential sum
     __shared__ float pxyz[256][3];
@@ -469,8 +479,11 @@ __global__ void __launch_bounds__(256) k_vox_passthrough(Source s, const VoxPara
     const int fr = blockIdx.y;
     const VoxParams* vp = vp0 + fr;
     if (!vp->overflow) return;   // the usual case: a small grid of blocks that leave at once
-    oxyz += (size_t)fr * s.W * s.H * 3;
-    orgb += (size_t)fr * s.W * s.H * 3;
+    {
+        const size_t base = cloud_base(vp0, fr, (size_t)s.W * s.H);
+        oxyz += base * 3;
+        orgb += base * 3;
+    }
     Source t = s;
     t.drop_invalid = 0;
     t.z_max = 0.f;
@@ -501,7 +514,7 @@ struct sdr_cloud {
     PinnedBuf host_params;
     cudaEvent_t done = nullptr;
     int frames = 0;                 // frames of the last enqueue
-    std::vector<int64_t> last_n;
+    std::vector<int64_t> last_n, last_off;   // points of frame f and where they start in the packed output arrays
     std::vector<int> last_passthrough;
     int W = 0, H = 0;
 };
@@ -621,18 +634,21 @@ int sdr_cloud_finish(sdr_cloud* c, sdr_cloud_view* views) {
     const VoxParams* hp = (const VoxParams*)c->host_params.p;
     const size_t n = (size_t)c->W * c->H;
     c->last_n.assign(c->frames, 0);
+    c->last_off.assign(c->frames + 1, 0);
     c->last_passthrough.assign(c->frames, 0);
     int status = SDR_OK;
     for (int f = 0; f < c->frames; f++) {
         c->last_passthrough[f] = hp[f].overflow;
         c->last_n[f] = hp[f].overflow ? (int64_t)n : (int64_t)hp[f].nvox;
+        c->last_off[f + 1] = c->last_off[f] + c->last_n[f];
         if (views) {
             sdr_cloud_view* view = views + f;
+            const size_t off = (size_t)c->last_off[f];
             view->n = c->last_n[f];
-            view->xyz = c->oxyz.as<float>() + (size_t)f * n * 3;
-            view->rgb = c->orgb.as<uint8_t>() + (size_t)f * n * 3;
-            view->idx = hp[f].overflow ? nullptr : c->oidx.as<uint32_t>() + (size_t)f * n;
-            view->cnt = hp[f].overflow ? nullptr : c->ocnt.as<uint32_t>() + (size_t)f * n;
+            view->xyz = c->oxyz.as<float>() + off * 3;
+            view->rgb = c->orgb.as<uint8_t>() + off * 3;
+            view->idx = hp[f].overflow ? nullptr : c->oidx.as<uint32_t>() + off;
+            view->cnt = hp[f].overflow ? nullptr : c->ocnt.as<uint32_t>() + off;
             for (int i = 0; i < 3; i++) { view->min_b[i] = hp[f].minb[i]; view->div_b[i] = hp[f].divb[i]; }
             view->passthrough = hp[f].overflow;
         }
@@ -646,13 +662,28 @@ int sdr_cloud_finish(sdr_cloud* c, sdr_cloud_view* views) {
 int sdr_cloud_download_frame(sdr_cloud* c, int f, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt, bool wait) {
     sdr_ctx* ctx = c->ctx;
     if (f < 0 || f >= c->frames || f >= (int)c->last_n.size()) return SDR_FAIL(ctx, SDR_EINVAL, "cloud_download: no such frame %d", f);
-    const size_t n = (size_t)c->last_n[f], N = (size_t)c->W * c->H;
-    if (xyz) SDR_CUDA(ctx, cudaMemcpyAsync(xyz, c->oxyz.as<float>() + (size_t)f * N * 3, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
-    if (rgb) SDR_CUDA(ctx, cudaMemcpyAsync(rgb, c->orgb.as<uint8_t>() + (size_t)f * N * 3, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t n = (size_t)c->last_n[f], off = (size_t)c->last_off[f];
+    if (xyz) SDR_CUDA(ctx, cudaMemcpyAsync(xyz, c->oxyz.as<float>() + off * 3, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rgb) SDR_CUDA(ctx, cudaMemcpyAsync(rgb, c->orgb.as<uint8_t>() + off * 3, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
     if (!c->last_passthrough[f]) {
-        if (idx) SDR_CUDA(ctx, cudaMemcpyAsync(idx, c->oidx.as<uint32_t>() + (size_t)f * N, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (cnt) SDR_CUDA(ctx, cudaMemcpyAsync(cnt, c->ocnt.as<uint32_t>() + (size_t)f * N, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (idx) SDR_CUDA(ctx, cudaMemcpyAsync(idx, c->oidx.as<uint32_t>() + off, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (cnt) SDR_CUDA(ctx, cudaMemcpyAsync(cnt, c->ocnt.as<uint32_t>() + off, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    if (wait) SDR_CUDA(ctx, sdr_wait(ctx));
+    return SDR_OK;
+}
+
+// All clouds of the last batch, packed back to back as they sit on the device: ONE copy per array. offsets[frames + 1]
+// (in points) says where each frame's cloud starts. idx / cnt are meaningless for passthrough frames.
+int sdr_cloud_download_packed(sdr_cloud* c, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt, int64_t* offsets, bool wait) {
+    sdr_ctx* ctx = c->ctx;
+    if ((int)c->last_off.size() != c->frames + 1) return SDR_FAIL(ctx, SDR_EINVAL, "cloud_download_packed: no finished batch");
+    const size_t total = (size_t)c->last_off[c->frames];
+    if (offsets) memcpy(offsets, c->last_off.data(), sizeof(int64_t) * (c->frames + 1));
+    if (xyz && total) SDR_CUDA(ctx, cudaMemcpyAsync(xyz, c->oxyz.p, total * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rgb && total) SDR_CUDA(ctx, cudaMemcpyAsync(rgb, c->orgb.p, total * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    if (idx && total) SDR_CUDA(ctx, cudaMemcpyAsync(idx, c->oidx.p, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cnt && total) SDR_CUDA(ctx, cudaMemcpyAsync(cnt, c->ocnt.p, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (wait) SDR_CUDA(ctx, sdr_wait(ctx));
     return SDR_OK;
 }

@@ -1,4 +1,7 @@
-"""Row-strip split of ONE oversize frame across the GPUs of a box (BASELINE config 5).
+"""Row-strip split of ONE oversize frame across the GPUs of a box (BASELINE config 5) -- the multi-PROCESS
+form (one rank per GPU under torchrun). The native single-process form, with peer copies instead of NCCL, is
+sdr_sgbm_split_* / capi.SgbmSplit (csrc/split.cu); this module is the same plan for callers that already run one
+process per GPU.
 
 MODE_SGBM_3WAY is four independent stripes by construction (OpenCV recomputes the warm-up rows of each stripe), so each
 rank matches its stripes from the input rows it needs, the raw strips travel to rank 0 (NCCL send/recv over NVLink, a
@@ -43,6 +46,9 @@ def compute(sgbm, left, right, rank=0, world=1, dist=None):
                 dist.send(raw[y0:y1].view(torch.uint8), dst=0)
             elif rank == 0:
                 dist.recv(raw[y0:y1].view(torch.uint8), src=r)
+        # dist.recv only orders torch's current stream; the handle's own (non-blocking) stream knows nothing of it, so
+        # the host waits for the received strips before the post-filter is queued there
+        torch.cuda.current_stream().synchronize()
     if rank != 0:
         return None
     out = sgbm.postfilter(raw)

@@ -54,15 +54,15 @@ def test_against_oracle(ctx, orc, W, H, args, kind):
     m.close()
 
 
-def test_cost_and_aggregate_volumes(ctx, orc, monkeypatch):
+def test_cost_and_aggregate_volumes(ctx, orc):
     """Stage-level parity: C volume and the 4-path aggregate S of MODE_SGBM."""
     from stereo_depth_ruler_b200 import capi, synth
-    monkeypatch.setenv("SDR_PATH_HH", "0")   # the separate L->R kernel leaves the 4-path aggregate in S
     W, H, D = 200, 60, 48
     l, r = synth.stereo_pair(W, H, D, 9)
     po = orc.make_params(0, D, 5, 600, 2400, 1, 63, 12, 0, 0, 0)
     raw, Cv, Sv, Sp = orc.sgbm_match(l, r, po, want_volumes=True)
     m = capi.Sgbm(ctx, capi.make_params(0, D, 5, 600, 2400, 1, 63, 12, 0, 0, 0))
+    m.set_option("path_hh", 0)   # the separate L->R kernel leaves the 4-path aggregate in S
     m.compute(l, r)
     W1 = W - D
     assert np.array_equal(m.debug_read(0, (H, W1, D)).astype(np.int32) + 2400, Cv)
@@ -156,24 +156,21 @@ FUSED = [(300, 70, 128, 5, 0), (290, 45, 128, 3, 0), (333, 40, 128, 5, 1), (197,
 
 
 @pytest.mark.parametrize("W,H,D,bs,mode", FUSED)
-def test_fused_cost_sweep_kernel(ctx, orc, W, H, D, bs, mode, monkeypatch):
+def test_fused_cost_sweep_kernel(ctx, orc, W, H, D, bs, mode):
     """The configurations the fused cost + top-down sweep kernel covers (D = 64 / 128, blockSize 3 / 5, MODE_SGBM and the
     first pass of MODE_HH), ragged strip widths and fewer rows than the box window: bit-exact against the oracle incl.
     the C and S volumes, identical to the two-kernel path, and the stage timer shows which path ran."""
     from stereo_depth_ruler_b200 import capi, synth
     args = (0, D, bs, 8 * bs * bs, 32 * bs * bs, 1, 63, 12, 50, 2, mode)
-    monkeypatch.setenv("SDR_PATH_HH", "0")   # the separate L->R kernel leaves the 4-path aggregate in S
     B = 3
     pairs = [synth.stereo_pair(W, H, D, 20 + s) for s in range(B)]
     po = orc.make_params(*args)
     refs = [orc.sgbm_compute(l, r, po) for l, r in pairs]
     outs = {}
     for fused in (True, False):
-        if fused:
-            monkeypatch.delenv("SDR_DISABLE_COST_FUSION", raising=False)
-        else:
-            monkeypatch.setenv("SDR_DISABLE_COST_FUSION", "1")
-        m = capi.Sgbm(ctx, capi.make_params(*args))          # the switch is read when the handle is created
+        m = capi.Sgbm(ctx, capi.make_params(*args))
+        m.set_option("path_hh", 0)   # the separate L->R kernel leaves the 4-path aggregate in S
+        m.set_option("cost_fusion", int(fused))
         m.set_profiling(True)
         got = m.compute_batch(np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs]), np.empty((B, H, W), np.int16))
         names = [k for k, _ in m.stage_times()]
@@ -195,14 +192,13 @@ def test_fused_cost_sweep_kernel(ctx, orc, W, H, D, bs, mode, monkeypatch):
 @pytest.mark.parametrize("W,H,args", [(300, 41, (0, 128, 5, 600, 2400, 1, 63, 12, 50, 2, 0)), (203, 33, (0, 64, 3, 72, 288, 1, 63, 12, 0, 0, 1)),
                                       (177, 50, (0, 80, 5, 600, 2400, 1, 63, 12, 200, 2, 2)), (97, 9, (-16, 48, 5, 600, 2400, 2, 63, 5, 0, 0, 0)),
                                       (67, 3, (0, 64, 5, 600, 2400, 1, 63, 12, 0, 0, 2)), (68, 5, (0, 64, 5, 600, 2400, 1, 63, 12, 0, 0, 0))])
-def test_two_direction_horizontal_kernel(ctx, orc, W, H, args, monkeypatch):
-    """SDR_PATH_HH=1: both horizontal paths of a row in one launch, meeting in the middle (odd and even W1,
+def test_two_direction_horizontal_kernel(ctx, orc, W, H, args):
+    """Option path_hh=1: both horizontal paths of a row in one launch, meeting in the middle (odd and even W1,
     W1 = 3 and 4, every mode): same CV_16S map and raw matcher output as the oracle."""
     from stereo_depth_ruler_b200 import capi, synth
-    monkeypatch.setenv("SDR_PATH_HH", "1")
     l, r = synth.stereo_pair(W, H, args[1], 31)
     po = orc.make_params(*args)
-    m = capi.Sgbm(ctx, capi.make_params(*args))       # the switch is read when the handle is created
+    m = capi.Sgbm(ctx, capi.make_params(*args)).set_option("path_hh", 1)
     m.set_profiling(True)
     got = m.compute(l, r)
     assert "path_h_both_wta" in [k for k, _ in m.stage_times()]
@@ -217,14 +213,13 @@ def test_two_direction_horizontal_kernel(ctx, orc, W, H, args, monkeypatch):
 
 
 @pytest.mark.parametrize("mode", [0, 1])
-def test_per_direction_fallback_kernels(ctx, orc, mode, monkeypatch):
-    """SDR_DISABLE_FUSED_SWEEP=1: the one-launch-per-direction path kernels (the fallback when a cooperative grid does not
+def test_per_direction_fallback_kernels(ctx, orc, mode):
+    """Option fused_sweep=0: the one-launch-per-direction path kernels (the fallback when a cooperative grid does not
     fit on the device) give the same map."""
     from stereo_depth_ruler_b200 import capi, synth
-    monkeypatch.setenv("SDR_DISABLE_FUSED_SWEEP", "1")
     W, H, args = 230, 37, (0, 64, 5, 600, 2400, 1, 63, 12, 30, 2, mode)
     l, r = synth.stereo_pair(W, H, args[1], 17)
-    m = capi.Sgbm(ctx, capi.make_params(*args))
+    m = capi.Sgbm(ctx, capi.make_params(*args)).set_option("fused_sweep", 0)
     m.set_profiling(True)
     got = m.compute(l, r)
     names = [k for k, _ in m.stage_times()]
@@ -234,14 +229,13 @@ def test_per_direction_fallback_kernels(ctx, orc, mode, monkeypatch):
 
 
 @pytest.mark.parametrize("W,H,bs", [(300, 40, 5), (333, 23, 3), (257, 31, 5)])
-def test_fused_kernel_wide_strips_small(ctx, orc, W, H, bs, monkeypatch):
-    """SDR_CF_COLS=64: the 64-column-strip form of the fused kernel (one CTA per SM; what a batch of 8 at 1280 wide runs)
+def test_fused_kernel_wide_strips_small(ctx, orc, W, H, bs):
+    """Option cf_cols=64: the 64-column-strip form of the fused kernel (one CTA per SM; what a batch of 8 at 1280 wide runs)
     on ragged widths (last strip partial, a single strip + 1 column), against the oracle."""
     from stereo_depth_ruler_b200 import capi, synth
-    monkeypatch.setenv("SDR_CF_COLS", "64")
     args = (0, 128, bs, 8 * bs * bs, 32 * bs * bs, 1, 63, 12, 50, 2, 0)
     pairs = [synth.stereo_pair(W, H, 128, 50 + s) for s in range(2)]
-    m = capi.Sgbm(ctx, capi.make_params(*args))
+    m = capi.Sgbm(ctx, capi.make_params(*args)).set_option("cf_cols", 64)
     m.set_profiling(True)
     out = m.compute_batch(np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs]), np.empty((2, H, W), np.int16))
     assert "cost_path_v_fused" in [k for k, _ in m.stage_times()]
@@ -252,8 +246,8 @@ def test_fused_kernel_wide_strips_small(ctx, orc, W, H, bs, monkeypatch):
 
 def test_headline_batch_of_8_equals_single_frames(ctx, golden):
     """The benchmark's shape: 8 frames of 1280x720x128 in one call (fused kernel with 64-column strips, several handles'
-    worth of work per launch) give, frame by frame, the maps of one-frame calls (32-column strips); frame 0 is the cv2
-    golden map."""
+    worth of work per launch) give, frame by frame, the maps cv2 itself computes for the same pairs and the maps of
+    one-frame calls (32-column strips); frame 0 is also the committed cv2 golden map."""
     import torch
     from stereo_depth_ruler_b200 import capi, synth
     B = 8
@@ -266,6 +260,9 @@ def test_headline_batch_of_8_equals_single_frames(ctx, golden):
     ctx.synchronize()
     out = O.cpu().numpy()
     assert sha(out[0]) == str(golden["full_c1_sha"])
-    for i in range(1, B):
+    import cv2
+    ref = cv2.StereoSGBM_create(0, 128, 5, 600, 2400, 1, 63, 12, 200, 2, cv2.STEREO_SGBM_MODE_SGBM)
+    for i in range(B):
+        assert np.array_equal(out[i], ref.compute(*pairs[i])), "frame %d differs from cv2" % i
         assert np.array_equal(out[i], m.compute(*pairs[i])), i
     m.close()

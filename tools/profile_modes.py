@@ -10,6 +10,9 @@ for (W, H, D, mode, B) in ((1280, 720, 128, 0, 8), (1280, 720, 128, 0, 1), (1280
     O = torch.empty((B, H, W), dtype=torch.int16, device="cuda")
     m = capi.Sgbm(ctx, capi.make_params(0, D, 5, 600, 2400, 1, 63, 12, 200, 2, mode))
     m.set_profiling(True)
+    for kv in sys.argv[1:]:            # kernel-selection knobs: name=value (sdr_sgbm_set_option)
+        k, v = kv.split("=")
+        m.set_option(k, int(v))
     for _ in range(3):
         m.compute_batch(L, R, O); ctx.synchronize()
     st = m.stage_times()

@@ -1,5 +1,5 @@
-"""Run bench.py under a list of environment-variable settings (tuning knobs of the SGBM kernels) and print one compact
-line per setting: value, e2e and the per-kernel stage times. Usage: python tools/tune_env.py "A=1 B=2" "A=3" ..."""
+"""Run bench.py under a list of kernel-knob settings (sdr_sgbm_set_option names) and print one compact line per setting:
+value, e2e and the per-kernel stage times. Usage: python tools/tune_env.py "h_k=2 h_stages=3" "cf_cols=32" ..."""
 import json
 import os
 import subprocess
@@ -8,11 +8,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 extra = os.environ.get("TUNE_BENCH_ARGS", "--steps 30 --warmup 3 --no-cpu-baseline").split()
 for setting in sys.argv[1:] or [""]:
-    env = dict(os.environ)
+    opts = []
     for kv in setting.split():
-        k, v = kv.split("=", 1)
-        env[k] = v
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + extra, env=env, capture_output=True, text=True)
+        opts += ["--sgbm-opt", kv]
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + extra + opts, capture_output=True, text=True)
     try:
         j = json.loads(p.stdout.strip().splitlines()[-1])
         st = j["roofline"]["stage_ms_per_batch"]
