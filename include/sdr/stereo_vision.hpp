@@ -1,11 +1,14 @@
 // C++17 facade over the C ABI (sdr_c.h) with the reference's class and method names:
 //   StereoConfiguration  stereo_vision/include/stereo_configuration.hpp:6-16
 //   StereoRectifier      stereo_vision/include/stereo_rectifier.hpp:7-19   (ctor + rectify)
-//   StereoDisparity      stereo_vision/include/stereo_disparity.hpp:8-24   (computeDisparity, computeDepth, get_matcher)
+//   StereoDisparity      stereo_vision/include/stereo_disparity.hpp:8-24   (computeDisparity, show_disparityMap, computeDepth,
+//                        show_depthMap, get_matcher; the WLS filter is NOT provided -- see the class comment)
 //   convertCVMatToPCL + pcl::VoxelGrid usage of point_cloud/src/pcd_write.cpp:17-51, :123-130 -> VoxelGrid / PointCloud
 // OpenCV is not a dependency: images travel as sdr::Mat, whose {data, rows, cols, step} fields are
 // layout-compatible with cv::Mat's, so `sdr::Mat::view(m.data, m.rows, m.cols, m.channels(), m.elemSize1(), m.step)`
 // adapts a cv::Mat in one line where OpenCV exists.
+// Constructors come in the reference's shapes (StereoRectifier(config), StereoDisparity(Q), StereoSGBM::create(...),
+// VoxelGrid()) on a process-wide default context, plus overloads that take an explicit sdr::Context (one per device).
 // Error behaviour mirrors the reference: loadFromFile/saveToFile return bool and print to stderr; bad arguments
 // throw sdr::Error (where OpenCV would throw cv::Exception); rectify() on empty input prints and returns.
 #pragma once
@@ -40,6 +43,12 @@ class Context {
     Context(const Context&) = delete;
     Context& operator=(const Context&) = delete;
     sdr_ctx* get() const { return h_; }
+    // The context behind the reference-shaped constructors (StereoRectifier(config), StereoDisparity(Q), ...): device 0,
+    // created on first use, alive until the process exits -- the reference has no notion of a device either.
+    static Context& shared() {
+        static Context ctx(0);
+        return ctx;
+    }
     void check(int rc, bool allow_voxel_overflow = false) const {
         if (rc == SDR_OK || (allow_voxel_overflow && rc == SDR_EVOXEL_OVERFLOW)) return;
         throw Error(rc, sdr_last_error(h_));
@@ -162,6 +171,8 @@ struct StereoConfiguration {
 
 class StereoRectifier {
   public:
+    // stereo_rectifier.hpp:15: explicit StereoRectifier(const StereoConfiguration &config)
+    explicit StereoRectifier(const StereoConfiguration& config) : StereoRectifier(config, Context::shared()) {}
     StereoRectifier(const StereoConfiguration& config, Context& ctx) : config_(config), ctx_(ctx) {
         sdr_calibration c = config.to_c();
         ctx_.check(sdr_rectifier_create(ctx_.get(), &c, &h_));
@@ -196,6 +207,20 @@ class StereoSGBM {
                           speckleWindowSize, speckleRange, mode};
         return std::shared_ptr<StereoSGBM>(new StereoSGBM(ctx, p));
     }
+    // cv::StereoSGBM::create(minDisparity, numDisparities, blockSize, P1, P2, disp12MaxDiff, preFilterCap, uniquenessRatio,
+    // speckleWindowSize, speckleRange, mode): same defaults, the shared context
+    static std::shared_ptr<StereoSGBM> create(int minDisparity = 0, int numDisparities = 16, int blockSize = 3, int P1 = 0, int P2 = 0,
+                                              int disp12MaxDiff = 0, int preFilterCap = 0, int uniquenessRatio = 0, int speckleWindowSize = 0,
+                                              int speckleRange = 0, int mode = MODE_SGBM) {
+        return create(Context::shared(), minDisparity, numDisparities, blockSize, P1, P2, disp12MaxDiff, preFilterCap, uniquenessRatio,
+                      speckleWindowSize, speckleRange, mode);
+    }
+    // cv::ximgproc::createRightMatcher(matcher_left) (stereo_disparity.cpp:10)
+    static std::shared_ptr<StereoSGBM> createRightMatcher(const std::shared_ptr<StereoSGBM>& left) {
+        sdr_sgbm_params r;
+        sdr_sgbm_right_matcher_params(&left->p_, &r);
+        return std::shared_ptr<StereoSGBM>(new StereoSGBM(left->ctx_, r));
+    }
     ~StereoSGBM() { sdr_sgbm_destroy(h_); }
     void compute(const Mat& left, const Mat& right, Mat& disp) {
         disp.create(left.rows(), left.cols(), 1, 2);
@@ -213,24 +238,61 @@ class StereoSGBM {
 
 class StereoDisparity {
   public:
-    // stereo_disparity.cpp:4-7: the reference's parameter tuple. (The right matcher + WLS filter of :8-13 need
-    // opencv_contrib ximgproc and are out of scope; computeDisparity follows pcd_write.cpp:88-112.)
+    // stereo_disparity.hpp:16 / stereo_disparity.cpp:4-14: StereoDisparity(const cv::Mat &Q_matrix) -- the reference's
+    // parameter tuple (0, 80, 5, 600, 2400, 1, 63, 12, 200, 2, MODE_SGBM_3WAY) and its right matcher.
+    // NOT provided: cv::ximgproc::DisparityWLSFilter (:11-13, :31). ximgproc exists in no oracle available to this build,
+    // so a restatement could not be pinned; computeDisparity therefore returns the matcher's UNFILTERED left disparity
+    // where the reference returns the WLS-filtered one (same size, same type, different values). wlsFilterApplied() says so.
+    explicit StereoDisparity(const std::array<double, 16>& Q_matrix) : StereoDisparity(Q_matrix, Context::shared()) {}
     StereoDisparity(const std::array<double, 16>& Q_matrix, Context& ctx) : ctx_(ctx), Q_(Q_matrix) {
         matcher_ = StereoSGBM::create(ctx, 0, 80, 5, 8 * 5 * 5 * 3, 32 * 5 * 5 * 3, 1, 63, 12, 200, 2, StereoSGBM::MODE_SGBM_3WAY);
+        right_matcher_ = StereoSGBM::createRightMatcher(matcher_);
+        ctx_.check(sdr_vis_create(ctx_.get(), &vis_));
     }
-    // left/right: BGR or gray. Returns CV_32F disparity (pixels).
+    ~StereoDisparity() { sdr_vis_destroy(vis_); }
+    StereoDisparity(const StereoDisparity&) = delete;
+    static constexpr bool wlsFilterApplied() { return false; }
+    // stereo_disparity.cpp:17-39 without the WLS filter: BGR2GRAY, half-size INTER_AREA, matcher on (left, right) and the
+    // right matcher on (right, left) (kept in lastRightDisparity(), what wls_filter->filter would consume), convertTo
+    // (CV_32F, 1/16). Returns the HALF-resolution CV_32F map, like the reference. left / right: BGR or gray, even size.
     Mat computeDisparity(const Mat& left, const Mat& right) {
+        Mat lg = gray(left), rg = gray(right);
+        Mat ls(lg.rows() / 2, lg.cols() / 2, 1, 1), rs(rg.rows() / 2, rg.cols() / 2, 1, 1);
+        ctx_.check(sdr_resize_half_area(ctx_.get(), lg.c(), ls.c()));
+        ctx_.check(sdr_resize_half_area(ctx_.get(), rg.c(), rs.c()));
+        Mat disp_left;
+        matcher_->compute(ls, rs, disp_left);
+        right_matcher_->compute(rs, ls, disp_right_);
+        Mat out(disp_left.rows(), disp_left.cols(), 1, 4);
+        ctx_.check(sdr_disp_to_float(ctx_.get(), disp_left.c(), out.c()));
+        return out;
+    }
+    const Mat& lastRightDisparity() const { return disp_right_; }   // CV_16S, as right_matcher->compute gives it
+    // The un-resized path of point_cloud/src/pcd_write.cpp:88-112 (gray, matcher, convertTo 1/16) at full resolution.
+    Mat computeDisparityFullRes(const Mat& left, const Mat& right) {
         Mat lg = gray(left), rg = gray(right), d16;
         matcher_->compute(lg, rg, d16);
         Mat out(d16.rows(), d16.cols(), 1, 4);
         ctx_.check(sdr_disp_to_float(ctx_.get(), d16.c(), out.c()));   // convertTo(CV_32F, 1/16) on the device
         return out;
     }
-    // cv::reprojectImageTo3D(disparity, depth, Q)
+    // stereo_disparity.cpp:42-73
+    Mat show_disparityMap(const Mat& disparity) {
+        Mat out(disparity.rows(), disparity.cols(), 1, 1);
+        ctx_.check(sdr_vis_disparity(vis_, disparity.c(), matcher_->getNumDisparities(), out.c()));
+        return out;
+    }
+    // cv::reprojectImageTo3D(disparity, depth, Q)  (stereo_disparity.cpp:76-80)
     Mat computeDepth(const Mat& disparity, bool handleMissingValues = false) {
         Mat depth(disparity.rows(), disparity.cols(), 3, 4);
         ctx_.check(sdr_reproject_to_3d(ctx_.get(), disparity.c(), Q_.data(), handleMissingValues ? 1 : 0, depth.c()));
         return depth;
+    }
+    // stereo_disparity.cpp:83-124 (the argument is the depth image, 3-channel points or 1-channel Z)
+    Mat show_depthMap(const Mat& depth) {
+        Mat out(depth.rows(), depth.cols(), 3, 1);
+        ctx_.check(sdr_vis_depth(vis_, depth.c(), out.c()));
+        return out;
     }
     const std::shared_ptr<StereoSGBM> get_matcher() const { return matcher_; }
 
@@ -243,7 +305,9 @@ class StereoDisparity {
     }
     Context& ctx_;
     std::array<double, 16> Q_;
-    std::shared_ptr<StereoSGBM> matcher_;
+    std::shared_ptr<StereoSGBM> matcher_, right_matcher_;
+    Mat disp_right_;
+    sdr_vis* vis_ = nullptr;
 };
 
 // pcl::PointCloud<pcl::PointXYZRGB> stand-in: what convertCVMatToPCL + VoxelGrid::filter produce.
@@ -257,6 +321,7 @@ struct PointCloud {
 
 class VoxelGrid {
   public:
+    VoxelGrid() : VoxelGrid(Context::shared()) {}   // pcl::VoxelGrid<pcl::PointXYZRGB> sor;  (pcd_write.cpp:123)
     explicit VoxelGrid(Context& ctx) : ctx_(ctx) { ctx_.check(sdr_cloud_create(ctx_.get(), &h_)); }
     ~VoxelGrid() { sdr_cloud_destroy(h_); }
     void setLeafSize(float lx, float ly, float lz) { opt_.leaf[0] = lx; opt_.leaf[1] = ly; opt_.leaf[2] = lz; }

@@ -235,6 +235,28 @@ SDR_API int sdr_depth_coverage(sdr_ctx* ctx, const sdr_image* points, int first_
  * (the reference prints "No points to save" and returns, :143-146). */
 SDR_API int sdr_cloud_save_pcd_binary(sdr_cloud* c, int frame, const char* path);
 
+/* ---- the reference's live path around the matcher (StereoDisparity, stereo_disparity.cpp) ---- */
+/* cv::resize(src, dst, Size(), 0.5, 0.5, INTER_AREA) (stereo_disparity.cpp:23-24): u8, 1 or 3 channels, even width and
+ * height (OpenCV's exact-factor-2 path, (a+b+c+d+2)>>2); odd sizes return SDR_EINVAL. */
+SDR_API int sdr_resize_half_area(sdr_ctx* ctx, const sdr_image* src, sdr_image* dst);
+/* cv::ximgproc::createRightMatcher(matcher) (stereo_disparity.cpp:10): parameters of the matcher that, run on (right, left),
+ * gives the right-view disparity: minDisparity = -(minD + D) + 1, uniquenessRatio 0, disp12MaxDiff 1000000, no speckle
+ * filter, same P1 / P2 / preFilterCap / mode. The cv::ximgproc::DisparityWLSFilter that consumes it (:11-13, :31) is NOT
+ * provided: ximgproc is absent from every oracle available here, so its parity could not be pinned. */
+SDR_API int sdr_sgbm_right_matcher_params(const sdr_sgbm_params* left, sdr_sgbm_params* right);
+/* Visualisation helpers. The handle owns what the reference keeps between frames: prev_vis, prev_depth_vis
+ * (stereo_disparity.hpp:11) and the smoothed depth range (function-static in show_depthMap, stereo_disparity.cpp:93). */
+typedef struct sdr_vis sdr_vis;
+SDR_API int sdr_vis_create(sdr_ctx* ctx, sdr_vis** out);
+SDR_API void sdr_vis_destroy(sdr_vis* v);
+SDR_API int sdr_vis_reset(sdr_vis* v);
+/* StereoDisparity::show_disparityMap (stereo_disparity.cpp:42-73): disparity f32 1-ch -> u8 1-ch. */
+SDR_API int sdr_vis_disparity(sdr_vis* v, const sdr_image* disparity32f, int num_disparities, sdr_image* out_u8);
+/* StereoDisparity::show_depthMap (stereo_disparity.cpp:83-124): f32 3-ch point image (Z = channel 2) or 1-ch depth ->
+ * u8 BGR (COLORMAP_TURBO over the smoothed valid range, blended with the previous frame). */
+SDR_API int sdr_vis_depth(sdr_vis* v, const sdr_image* depth32f, sdr_image* out_bgr);
+SDR_API int sdr_vis_depth_range(sdr_vis* v, double* zmin_smooth, double* zmax_smooth);
+
 /* ---- whole path per frame (stereo_displayer.cpp:155-162 + pcd_write.cpp:82-130) ---- */
 typedef struct sdr_pipeline_options {
     sdr_sgbm_params sgbm;

@@ -75,7 +75,8 @@ SYMBOLS = [
     "sdr_remap_with_maps", "sdr_bgr2gray",
     "sdr_sgbm_create", "sdr_sgbm_destroy", "sdr_sgbm_compute", "sdr_sgbm_compute_batch",
     "sdr_sgbm_set_profiling", "sdr_sgbm_stage_times", "sdr_sgbm_debug_read", "sdr_sgbm_set_option",
-    "sdr_pipeline_set_sgbm_option", "sdr_sgbm_split_create", "sdr_sgbm_split_destroy", "sdr_sgbm_split_compute",
+    "sdr_pipeline_set_sgbm_option", "sdr_resize_half_area", "sdr_sgbm_right_matcher_params", "sdr_vis_create", "sdr_vis_destroy",
+    "sdr_vis_reset", "sdr_vis_disparity", "sdr_vis_depth", "sdr_vis_depth_range", "sdr_sgbm_split_create", "sdr_sgbm_split_destroy", "sdr_sgbm_split_compute",
     "sdr_sgbm_split_synchronize", "sdr_sgbm_split_last_stats", "sdr_sgbm_split_last_error",
     "sdr_sgbm_stripe_rows", "sdr_sgbm_match_stripes", "sdr_sgbm_postfilter",
     "sdr_median3_16s", "sdr_filter_speckles", "sdr_disp_to_float", "sdr_reproject_to_3d",
@@ -107,7 +108,7 @@ def lib():
         L.sdr_kernel_launches.argtypes = [C.c_void_p]
         L.sdr_destroy.argtypes = [C.c_void_p]
         L.sdr_destroy.restype = None
-        for n in ("sdr_rectifier_destroy", "sdr_sgbm_destroy", "sdr_cloud_destroy", "sdr_pipeline_destroy", "sdr_stream_destroy", "sdr_sgbm_split_destroy"):
+        for n in ("sdr_rectifier_destroy", "sdr_sgbm_destroy", "sdr_cloud_destroy", "sdr_pipeline_destroy", "sdr_stream_destroy", "sdr_sgbm_split_destroy", "sdr_vis_destroy"):
             if hasattr(L, n):
                 getattr(L, n).argtypes = [C.c_void_p]
                 getattr(L, n).restype = None
@@ -431,6 +432,64 @@ def bgr2gray(ctx, bgr):
     si, _ = as_image(bgr, 3); di, _ = as_image(out, 1)
     ctx.check(lib().sdr_bgr2gray(ctx._h, C.byref(si), C.byref(di)))
     return out
+
+
+def resize_half_area(ctx, src):
+    """cv::resize(src, Size(), 0.5, 0.5, INTER_AREA) for even sizes (stereo_disparity.cpp:23-24)."""
+    shp = (src.shape[0] // 2, src.shape[1] // 2) + tuple(src.shape[2:])
+    out = _empty_like_kind(src, shp, np.uint8, "uint8")
+    si, _ = as_image(src); di, _ = as_image(out)
+    ctx.check(lib().sdr_resize_half_area(ctx._h, C.byref(si), C.byref(di)))
+    return out
+
+
+def right_matcher_params(left_params):
+    """cv::ximgproc::createRightMatcher (stereo_disparity.cpp:10) as parameters."""
+    r = SgbmParams()
+    rc = lib().sdr_sgbm_right_matcher_params(C.byref(left_params), C.byref(r))
+    if rc != SDR_OK:
+        raise SdrError(rc, "sdr_sgbm_right_matcher_params failed")
+    return r
+
+
+class Vis:
+    """show_disparityMap / show_depthMap with the reference's frame-to-frame state (sdr_vis_*)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        ctx.check(lib().sdr_vis_create(ctx._h, C.byref(self._h)))
+
+    def disparity(self, disp32f, num_disparities):
+        out = _empty_like_kind(disp32f, tuple(disp32f.shape), np.uint8, "uint8")
+        di, _ = as_image(disp32f, 1); oi, _ = as_image(out, 1)
+        self.ctx.check(lib().sdr_vis_disparity(self._h, C.byref(di), int(num_disparities), C.byref(oi)))
+        return out
+
+    def depth(self, depth32f):
+        out = _empty_like_kind(depth32f, tuple(depth32f.shape[:2]) + (3,), np.uint8, "uint8")
+        di, _ = as_image(depth32f); oi, _ = as_image(out, 3)
+        self.ctx.check(lib().sdr_vis_depth(self._h, C.byref(di), C.byref(oi)))
+        return out
+
+    def depth_range(self):
+        a, b = C.c_double(), C.c_double()
+        lib().sdr_vis_depth_range(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def reset(self):
+        lib().sdr_vis_reset(self._h)
+
+    def close(self):
+        if self._h:
+            lib().sdr_vis_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def disp_to_float(ctx, disp16):
