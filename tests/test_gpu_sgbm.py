@@ -212,6 +212,46 @@ def test_two_direction_horizontal_kernel(ctx, orc, W, H, args):
     m.close()
 
 
+@pytest.mark.parametrize("W,H,args,lanes", [(300, 41, (0, 128, 5, 600, 2400, 1, 63, 12, 50, 2, 0), 32), (300, 41, (0, 128, 5, 600, 2400, 1, 63, 12, 50, 2, 0), 16),
+                                            (203, 33, (0, 64, 3, 72, 288, 1, 63, 12, 0, 0, 1), 32), (177, 50, (0, 96, 5, 600, 2400, 1, 63, 12, 200, 2, 2), 16),
+                                            (420, 37, (0, 256, 5, 600, 2400, 1, 63, 12, 100, 2, 2), 32), (97, 9, (-16, 64, 5, 600, 2400, 2, 63, 5, 0, 0, 0), 32),
+                                            (69, 4, (0, 64, 5, 600, 2400, 1, 63, 12, 0, 0, 0), 16), (330, 21, (0, 80, 5, 600, 2400, 1, 63, 12, 0, 0, 2), 32)])
+def test_two_direction_kernel_wide_lanes(ctx, orc, W, H, args, lanes):
+    """Option h_lanes = 16 / 32: a row's D costs over 16 or 32 lanes (what one frame or one stripe gets automatically; D = 80
+    cannot and falls back to 8): same maps as the oracle, single frame and batch."""
+    from stereo_depth_ruler_b200 import capi, synth
+    l, r = synth.stereo_pair(W, H, args[1], 61)
+    po = orc.make_params(*args)
+    m = capi.Sgbm(ctx, capi.make_params(*args)).set_option("path_hh", 1).set_option("h_lanes", lanes)
+    got = m.compute(l, r)
+    assert np.array_equal(got, orc.sgbm_compute(l, r, po))
+    assert np.array_equal(m.debug_read(2, (H, W)), orc.sgbm_match(l, r, po))
+    pairs = [synth.stereo_pair(W, H, args[1], 70 + s) for s in range(2)]
+    out = m.compute_batch(np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs]), np.empty((2, H, W), np.int16))
+    for i in range(2):
+        assert np.array_equal(out[i], orc.sgbm_compute(pairs[i][0], pairs[i][1], po)), i
+    m.close()
+
+
+@pytest.mark.parametrize("ws", [0, 1])
+@pytest.mark.parametrize("W,H,args", [(300, 41, (0, 128, 5, 600, 2400, 1, 63, 12, 50, 2, 0)), (177, 50, (0, 80, 5, 600, 2400, 1, 63, 12, 200, 2, 2)),
+                                      (97, 9, (-16, 48, 5, 600, 2400, 2, 63, 5, 0, 0, 0)), (203, 33, (0, 64, 3, 72, 288, 1, 63, 12, 0, 0, 1)),
+                                      (340, 19, (0, 256, 5, 600, 2400, 1, 63, 12, 0, 0, 0))])
+def test_backward_wta_kernel_variants(ctx, orc, W, H, args, ws):
+    """The separate R->L + WTA kernel in its two forms (h_ws = 1: chain warp + tail warp through a shared-memory ring, the
+    default with several matchers per device; h_ws = 0: one instruction stream): raw matcher output equals the oracle."""
+    from stereo_depth_ruler_b200 import capi, synth
+    l, r = synth.stereo_pair(W, H, args[1], 33)
+    po = orc.make_params(*args)
+    m = capi.Sgbm(ctx, capi.make_params(*args)).set_option("path_hh", 0).set_option("h_ws", ws)
+    m.set_profiling(True)
+    got = m.compute(l, r)
+    assert "path_h_bwd_wta" in [k for k, _ in m.stage_times()]
+    assert np.array_equal(m.debug_read(2, (H, W)), orc.sgbm_match(l, r, po))
+    assert np.array_equal(got, orc.sgbm_compute(l, r, po))
+    m.close()
+
+
 @pytest.mark.parametrize("mode", [0, 1])
 def test_per_direction_fallback_kernels(ctx, orc, mode):
     """Option fused_sweep=0: the one-launch-per-direction path kernels (the fallback when a cooperative grid does not
