@@ -254,6 +254,22 @@ static void wta_row(const int16_t* S, int W, int W1, int D, int minD, int minX1,
         int minS = 32767, best = three_way ? 0 : -1;
         for (int d = 0; d < D; d++)
             if (Sp[d] < minS) { minS = Sp[d]; best = d; }
+        if (three_way) {
+            /* QUIRK (pinned against cv2 4.13.0, tools/probes/diag3.py: 24 image/parameter cases, 0 differing pixels):
+             * computeDisparity3WaySGBM searches the minimum with 8-lane int16 vectors (128-bit universal intrinsics in the
+             * pip build). Lane r sees d = r, r+8, ...; an equal value REPLACES the lane's best position (last occurrence
+             * per lane), then min_pos() takes the smallest position among the lanes that hold the global minimum.
+             * Only visible with uniquenessRatio = 0 (createRightMatcher): any uq >= 1 rejects a pixel whose minimum is
+             * tied 8 or more disparities apart. MODE_SGBM / MODE_HH take the first minimum (probed the same way). */
+            int pick = D;
+            for (int r = 0; r < 8 && r < D; r++) {
+                int lm = 32767, lp = -1;
+                for (int d = r; d < D; d += 8)
+                    if (Sp[d] <= lm) { lm = Sp[d]; lp = d; }
+                if (lm == minS && lp < pick) pick = lp;
+            }
+            if (pick < D) best = pick;
+        }
         int d;
         if (three_way) {
             if (uq > 0) {
@@ -414,7 +430,7 @@ static int sgbm_full(const uint8_t* left, size_t lstep, const uint8_t* right, si
 /* A.5  computeDisparity3WaySGBM: 4 fixed stripes, paths L->R, top->down, R->L */
 /* ------------------------------------------------------------------------- */
 static int sgbm_3way(const uint8_t* left, size_t lstep, const uint8_t* right, size_t rstep, int W, int H,
-                     const orc_sgbm_params* p, int16_t* disp, size_t dstep_elems) {
+                     const orc_sgbm_params* p, int16_t* disp, size_t dstep_elems, int16_t* Svol_out) {
     const int minD = p->minDisparity, D = p->numDisparities;
     const int uq = p->uniquenessRatio >= 0 ? p->uniquenessRatio : 10;
     const int d12 = p->disp12MaxDiff > 0 ? p->disp12MaxDiff : 1;
@@ -482,8 +498,10 @@ static int sgbm_3way(const uint8_t* left, size_t lstep, const uint8_t* right, si
                     Sp[d] = sat16(leftb[(size_t)x * D + d] + rc[d] + top[(size_t)x * D + d]);
                 int16_t* t = rp; rp = rc; rc = t;
             }
-            if (y >= dst_off)
+            if (y >= dst_off) {
+                if (Svol_out) memcpy(Svol_out + row * y, S, row * sizeof(int16_t));
                 wta_row(S, W, W1, D, minD, minX1, maxX1, uq, d12, 1, disp + (size_t)y * dstep_elems, &rs);
+            }
         }
     }
     free(hs); free(pix); free(C); free(top); free(topMin); free(leftb); free(S); free(rbuf); free(zero);
@@ -574,7 +592,7 @@ ORC_API int orc_sgbm_match(const uint8_t* left, size_t lstep, const uint8_t* rig
                            int16_t* Spre_out) {
     int rc = check_params(p, W, H);
     if (rc) return rc;
-    if (p->mode == ORC_MODE_SGBM_3WAY) return sgbm_3way(left, lstep, right, rstep, W, H, p, disp, (size_t)W);
+    if (p->mode == ORC_MODE_SGBM_3WAY) return sgbm_3way(left, lstep, right, rstep, W, H, p, disp, (size_t)W, Svol_out);
     return sgbm_full(left, lstep, right, rstep, W, H, p, disp, (size_t)W, Cvol_out, Svol_out, Spre_out);
 }
 

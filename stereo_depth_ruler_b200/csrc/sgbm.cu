@@ -30,6 +30,7 @@ struct Geom {
     int hrow0, hrows;   // output rows of the selected stripes [hrow0, hrow0 + hrows): what the horizontal kernels cover
     Seg seg[4];
     int SW2, SH2, P1, P2, ftzero, uq, d12, three_way;
+    int tie8;           // MODE_SGBM_3WAY with uniquenessRatio 0: OpenCV's 8-lane minimum search decides ties (wta_pixel)
     uint32_t uq_magic;  // ceil(2^32 / (100 - uq)): exact n / (100 - uq) for n < 2^32 / 100 by one __umulhi
     int Wp;  // padded width of the right-image byte planes (multiple of 16); PR = [b][y][Wp/16][24 plane-copies][16 B]
 };
@@ -995,7 +996,8 @@ __device__ __forceinline__ void wta_pixel(const uint32_t (&Sr)[NP], int lg, cons
     }
 #pragma unroll
     for (int o = G / 2; o >= 1; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o, G));
-    const int minS = (int)(key >> 8), best = (int)(key & 0xFFu);
+    const int minS = (int)(key >> 8);
+    int best = (int)(key & 0xFFu);
     // S[d] < thr  <=>  the uniqueness predicate of the mode; the division by 100 - uq is one
     // multiply-high with a precomputed reciprocal (exact in this range)
     const int q = 100 - g.uq;
@@ -1016,6 +1018,19 @@ __device__ __forceinline__ void wta_pixel(const uint32_t (&Sr)[NP], int lg, cons
     // neighbours of the minimum through shared memory
     store_regs<NP>(sm + d0, Sr);
     __syncwarp();
+    if (g.tie8) {
+        // cv2's computeDisparity3WaySGBM looks for the minimum with 8-lane vectors: lane r keeps the LAST d = r (mod 8) that
+        // holds its minimum, min_pos() then takes the smallest position among the lanes at the global minimum. It shows only
+        // with uniquenessRatio 0 (any uq >= 1 rejects a minimum tied 8 or more disparities apart), i.e. for the matcher
+        // createRightMatcher makes (stereo_disparity.cpp:10); pinned against cv2 4.13.0 (oracle/sdr_oracle.c wta_row).
+        int pos = 0x7FFF;
+        if (lg < 8)
+            for (int d = lg; d < g.D; d += 8)
+                if (sm[d] == minS) pos = d;
+#pragma unroll
+        for (int o = G / 2; o >= 1; o >>= 1) pos = min(pos, __shfl_xor_sync(0xffffffffu, pos, o, G));
+        best = pos;
+    }
     const int Sm = best > 0 ? sm[best - 1] : 0, Sp = best < g.D - 1 ? sm[best + 1] : 0;
     __syncwarp();
     int nexcl = (minS < thr) + (best > 0 && Sm < thr) + (best < g.D - 1 && Sp < thr);
@@ -1101,178 +1116,6 @@ __global__ void __launch_bounds__(THREADS) k_path_h(Geom g, const int16_t* __res
             if (active) store_regs<NP>(Sb + (size_t)x * D, L);
         }
         x = xn;
-    }
-}
-
-// R->L + WTA with the two halves of the work in different warps. The path step is one long dependent chain per row
-// (previous pixel -> minimum over D -> this pixel); winner-take-all, uniqueness and the sub-pixel fit of a pixel depend on
-// nothing but that pixel's final S. In k_path_h<.., true> both sit in the same instruction stream, so every pixel's chain
-// also waits for ~60 % extra instructions and three more shuffle reductions. Here warp 0 of a CTA runs the four chains
-// (8 lanes per row, exactly the step of k_path_h) and hands each finished S vector to warp 1 through a small shared-memory
-// ring (mbarrier full / empty per slot); warp 1 does the per-pixel tail for the same four rows, a few pixels behind, with no
-// dependence between its pixels. The chain gets ~2.5x shorter, the tail's instructions fill the issue slots the chain
-// leaves idle, and HBM sees the requests sooner.
-constexpr int HW_SLOTS = 8;
-
-// as wta_pixel, but S sits in shared memory (`srow`, register quad q of lane lg at int16 offset (q*8 + lg)*8 when NP % 4 == 0,
-// natural order otherwise) so the neighbours of the minimum are read in place
-template <int NP>
-__device__ __forceinline__ int s_index(int d) {
-    if constexpr (NP % 4 == 0) {
-        const int l = d / (2 * NP), j = d - l * 2 * NP;
-        return ((j >> 3) * 8 + l) * 8 + (j & 7);
-    } else {
-        return d;
-    }
-}
-template <int NP, int G>
-__device__ __forceinline__ void wta_pixel_sm(const uint32_t (&Sr)[NP], int lg, const Geom& g, const int16_t* srow, int& disp_out,
-                                             uint32_t& wta_out) {
-    uint32_t key = 0xFFFFFFFFu;
-    const int d0 = lg * 2 * NP;
-    const uint32_t dw0 = (uint32_t)d0 | ((uint32_t)(d0 + 1) << 8);
-#pragma unroll
-    for (int k = 0; k < NP; k++) {
-        const uint32_t dw = dw0 + 0x0202u * k;
-        key = __vimin3_u32(key, prmt(Sr[k], dw, 0x6104), prmt(Sr[k], dw, 0x6325));
-    }
-#pragma unroll
-    for (int o = G / 2; o >= 1; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o, G));
-    const int minS = (int)(key >> 8), best = (int)(key & 0xFFu);
-    const int q = 100 - g.uq;
-    const uint32_t num = g.three_way ? (uint32_t)(100 * minS) : (uint32_t)(minS * 100 + q - 1);
-    const int quot = q == 1 ? (int)num : (int)__umulhi(num, g.uq_magic);
-    int thr = g.three_way ? (g.uq > 0 ? quot + 1 : 0) : quot;
-    thr = min(thr, 0x8000);
-    const uint32_t cst = 0x80008000u - pack16(thr, thr);
-    uint32_t nge2 = 0;
-#pragma unroll
-    for (int k = 0; k < NP; k++) {
-        const uint32_t t = Sr[k] + cst;
-        nge2 = __vadd2(nge2, prmt_full(t, t, 0xBB99));
-    }
-    int nlt = 2 * NP + (int)(int16_t)(nge2 & 0xFFFFu) + (int)(int16_t)(nge2 >> 16);
-#pragma unroll
-    for (int o = G / 2; o >= 1; o >>= 1) nlt += __shfl_xor_sync(0xffffffffu, nlt, o, G);
-    const int Sm = best > 0 ? srow[s_index<NP>(best - 1)] : 0, Sp = best < g.D - 1 ? srow[s_index<NP>(best + 1)] : 0;
-    int nexcl = (minS < thr) + (best > 0 && Sm < thr) + (best < g.D - 1 && Sp < thr);
-    if (nlt > nexcl) {
-        disp_out = (g.minD - 1) * 16;
-        wta_out = 0xFFFFFFFFu;
-        return;
-    }
-    int d = best * 16;
-    if (best > 0 && best < g.D - 1) {
-        const int den2 = 2 * max(Sm + Sp - 2 * minS, 1), numr = (Sm - Sp) * 16 + (den2 >> 1);
-        int qd = __float2int_rz(__fdividef((float)numr, (float)den2));
-        int rem = numr - qd * den2;
-        if (numr >= 0) {
-            if (rem < 0) qd--;
-            else if (rem >= den2) qd++;
-        } else {
-            if (rem > 0) qd++;
-            else if (rem <= -den2) qd--;
-        }
-        d += qd;
-    }
-    disp_out = d + g.minD * 16;
-    wta_out = ((uint32_t)minS << 16) | (uint32_t)best;
-}
-
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
-    while (!mbar_test(bar, parity)) {}
-}
-
-template <int NP>
-__global__ void __launch_bounds__(64) k_path_hw(Geom g, const int16_t* __restrict__ C, const int16_t* __restrict__ S, int16_t* __restrict__ dispraw,
-                                                uint32_t* __restrict__ wta) {
-    constexpr int G = 8, ROWS = 4;
-    __shared__ __align__(16) int16_t ring[HW_SLOTS][ROWS][2 * NP * G];
-    __shared__ __align__(8) uint64_t full[HW_SLOTS], empty[HW_SLOTS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gidx = lane / G, lg = lane & (G - 1);
-    const int row = g.hrow0 + blockIdx.x * ROWS + gidx;
-    bool active = row < g.hrow0 + g.hrows;
-    int y = min(row, g.hrow0 + g.hrows - 1);
-    const int b = blockIdx.z;
-    const int D = g.D, W1 = g.W1;
-    int si = -1;
-    for (int i = 0; i < g.nseg; i++)
-        if (y >= g.seg[i].dst_start && y < g.seg[i].src_end) si = i;
-    if (si < 0) { si = 0; y = g.seg[0].dst_start; active = false; }
-    const Seg sg = g.seg[si];
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < HW_SLOTS; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (warp == 0) {
-        // ---- the four chains ----
-        const uint32_t P1x2 = pack16(g.P1, g.P1), P2x2 = pack16(g.P2, g.P2);
-        const int pad = 32767 - g.P1;
-        const uint32_t PADx2 = pack16(pad, pad);
-        uint32_t P[NP], c[NP], s[NP], L[NP], cn[NP], sn[NP], m = 0;
-#pragma unroll
-        for (int k = 0; k < NP; k++) P[k] = 0;
-        const size_t lane_off = (size_t)lg * 2 * NP;
-        const int16_t* Cb = C + (((size_t)b * g.crows + sg.crow0 + (y - sg.src_start)) * W1) * D + lane_off;
-        const int16_t* Sb = S + (((size_t)b * g.H + y) * W1) * D + lane_off;
-        int x = W1 - 1;
-        load_regs<NP>(Cb + (size_t)x * D, cn);
-        load_regs<NP>(Sb + (size_t)x * D, sn);
-        int slot = 0;
-        uint32_t phase = 0;
-        for (int step = 0; step < W1; step++) {
-#pragma unroll
-            for (int k = 0; k < NP; k++) { c[k] = cn[k]; s[k] = sn[k]; }
-            if (step + 1 < W1) {
-                load_regs<NP>(Cb + (size_t)(x - 1) * D, cn);
-                load_regs<NP>(Sb + (size_t)(x - 1) * D, sn);
-            }
-            sgm_step<NP, G>(P, m, c, P1x2, P2x2, PADx2, lg);
-#pragma unroll
-            for (int k = 0; k < NP; k++) L[k] = __vminu2(__vadd2(s[k], P[k]), 0x7FFF7FFFu);
-            if (step >= HW_SLOTS) mbar_spin(&empty[slot], phase ^ 1);   // the tail warp is done with this slot's previous use
-            store_col_sm<NP>(&ring[slot][gidx][0], lg, L);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[slot]);
-            if (++slot == HW_SLOTS) { slot = 0; phase ^= 1; }
-            x--;
-        }
-    } else {
-        // ---- per-pixel tail: WTA, uniqueness, sub-pixel ----
-        int slot = 0;
-        uint32_t phase = 0;
-        uint32_t Sr[NP];
-        int x = W1 - 1;
-        for (int step = 0; step < W1; step++) {
-            mbar_spin(&full[slot], phase);
-            const int16_t* srow = &ring[slot][gidx][0];
-            load_col_sm<NP>(srow, lg, Sr);
-            int dv;
-            uint32_t wv;
-            wta_pixel_sm<NP, G>(Sr, lg, g, srow, dv, wv);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[slot]);
-            if (active && lg == 0) {
-                dispraw[((size_t)b * g.H + y) * g.W + x + g.minX1] = (int16_t)dv;
-                wta[((size_t)b * g.H + y) * W1 + x] = wv;
-            }
-            if (++slot == HW_SLOTS) { slot = 0; phase ^= 1; }
-            x--;
-        }
     }
 }
 
@@ -1537,7 +1380,6 @@ struct SgbmTune {
     int v3_stages = 0;      // TMA ring depth of k_path_v3
     int h_legacy = 0;       // register-prefetch k_path_h instead of the TMA-ring k_path_h2 for L->R
     int h_lanes = 0;        // lanes per row chain in k_path_hh: 8 / 16 / 32, 0 = by the number of rows in flight
-    int h_ws = 1;           // R->L + WTA as a chain warp + a tail warp (k_path_hw); 0: both in one instruction stream (k_path_h)
     int h_k = 0, h_stages = 0, h_warps = 0, hb_threads = 0, hb_ring = -1, hh_threads = 0;
 };
 
@@ -1581,11 +1423,6 @@ int launch_path_h(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, co
             SDR_CUDA(ctx, cudaFuncSetAttribute(k_path_h2<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_path_h2<NP, false><<<grid, 32 * nwarp, smem, ctx->stream>>>(g, C, S, dir, acc, K, nst, dispraw, wta);
         }
-        SDR_LAUNCHED(ctx);
-        return SDR_OK;
-    }
-    if (wta_on && dir < 0 && acc && tn.h_ws != 0) {   // warp-specialised chain + tail (default)
-        k_path_hw<NP><<<dim3(div_up(g.hrows, 4), 1, batch), 64, 0, ctx->stream>>>(g, C, S, dispraw, wta);
         SDR_LAUNCHED(ctx);
         return SDR_OK;
     }
@@ -1856,6 +1693,7 @@ static void make_geom(const sdr_sgbm_params& p, int W, int H, Geom& g) {
     g.P2 = std::max(p.P2 > 0 ? p.P2 : 5, g.P1 + 1);
     g.ftzero = std::max(p.preFilterCap, 15) | 1;
     g.three_way = p.mode == SDR_MODE_SGBM_3WAY;
+    g.tie8 = g.three_way && g.uq == 0;
     g.uq_magic = (uint32_t)(((1ull << 32) + (uint64_t)(100 - g.uq) - 1) / (uint64_t)(100 - g.uq));   // unused when 100 - uq == 1
     g.Wp = ((W + 15) & ~15) + 16;
     if (g.three_way) {
@@ -2187,7 +2025,7 @@ extern "C" int sdr_sgbm_set_option(sdr_sgbm* m, const char* name, int value) {
     SgbmTune& t = m->tune;
     const struct { const char* n; int* p; } tab[] = {
         {"fused_sweep", &t.fused_sweep}, {"cost_fusion", &t.cost_fusion}, {"path_hh", &t.path_hh}, {"shared_device", &t.shared_device},
-        {"cf_cols", &t.cf_cols}, {"cf_prod", &t.cf_prod}, {"cf_fpl", &t.cf_fpl}, {"v3_stages", &t.v3_stages}, {"h_legacy", &t.h_legacy}, {"h_ws", &t.h_ws}, {"h_lanes", &t.h_lanes},
+        {"cf_cols", &t.cf_cols}, {"cf_prod", &t.cf_prod}, {"cf_fpl", &t.cf_fpl}, {"v3_stages", &t.v3_stages}, {"h_legacy", &t.h_legacy}, {"h_lanes", &t.h_lanes},
         {"h_k", &t.h_k}, {"h_stages", &t.h_stages}, {"h_warps", &t.h_warps}, {"hb_threads", &t.hb_threads}, {"hb_ring", &t.hb_ring},
         {"hh_threads", &t.hh_threads}};
     for (const auto& e : tab)

@@ -233,23 +233,42 @@ def test_two_direction_kernel_wide_lanes(ctx, orc, W, H, args, lanes):
     m.close()
 
 
-@pytest.mark.parametrize("ws", [0, 1])
 @pytest.mark.parametrize("W,H,args", [(300, 41, (0, 128, 5, 600, 2400, 1, 63, 12, 50, 2, 0)), (177, 50, (0, 80, 5, 600, 2400, 1, 63, 12, 200, 2, 2)),
                                       (97, 9, (-16, 48, 5, 600, 2400, 2, 63, 5, 0, 0, 0)), (203, 33, (0, 64, 3, 72, 288, 1, 63, 12, 0, 0, 1)),
                                       (340, 19, (0, 256, 5, 600, 2400, 1, 63, 12, 0, 0, 0))])
-def test_backward_wta_kernel_variants(ctx, orc, W, H, args, ws):
-    """The separate R->L + WTA kernel in its two forms (h_ws = 1: chain warp + tail warp through a shared-memory ring, the
-    default with several matchers per device; h_ws = 0: one instruction stream): raw matcher output equals the oracle."""
+def test_backward_wta_kernel(ctx, orc, W, H, args):
+    """The separate R->L + WTA kernel (what runs with several matchers per device): raw matcher output equals the oracle."""
     from stereo_depth_ruler_b200 import capi, synth
     l, r = synth.stereo_pair(W, H, args[1], 33)
     po = orc.make_params(*args)
-    m = capi.Sgbm(ctx, capi.make_params(*args)).set_option("path_hh", 0).set_option("h_ws", ws)
+    m = capi.Sgbm(ctx, capi.make_params(*args)).set_option("path_hh", 0)
     m.set_profiling(True)
     got = m.compute(l, r)
     assert "path_h_bwd_wta" in [k for k, _ in m.stage_times()]
     assert np.array_equal(m.debug_read(2, (H, W)), orc.sgbm_match(l, r, po))
     assert np.array_equal(got, orc.sgbm_compute(l, r, po))
     m.close()
+
+
+@pytest.mark.parametrize("opts", [{}, {"path_hh": 0}, {"path_hh": 1, "h_lanes": 16}, {"path_hh": 1, "h_lanes": 32}])
+def test_three_way_without_uniqueness_takes_cv2s_tied_minimum(ctx, orc, opts):
+    """MODE_SGBM_3WAY with uniquenessRatio 0 (the matcher createRightMatcher builds, stereo_disparity.cpp:10): where the
+    minimum of S is tied 8 or more disparities apart cv2's 8-lane search does not return the first minimum. Half-size frames
+    with such ties (seed 2 has them: the first-minimum rule differs from cv2 in 10 pixels) against cv2 itself."""
+    cv2 = pytest.importorskip("cv2")
+    from stereo_depth_ruler_b200 import capi, synth
+    l, r = synth.stereo_pair(1280, 720, 128, 2)
+    ls = cv2.resize(l, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_AREA)
+    rs = cv2.resize(r, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_AREA)
+    for a, b, args in ((rs, ls, (-79, 80, 5, 600, 2400, 1000000, 63, 0, 0, 0, 2)), (ls, rs, (0, 64, 5, 600, 2400, 1000000, 63, 0, 0, 0, 2))):
+        m = capi.Sgbm(ctx, capi.make_params(*args))
+        for k, v in opts.items():
+            m.set_option(k, v)
+        got = m.compute(a, b)
+        ref = cv2.StereoSGBM_create(*args).compute(a, b)
+        assert np.array_equal(got, ref), (args, int((got != ref).sum()))
+        assert np.array_equal(got, orc.sgbm_compute(a, b, orc.make_params(*args)))
+        m.close()
 
 
 @pytest.mark.parametrize("mode", [0, 1])

@@ -28,6 +28,19 @@ def test_sgbm_sweep(orc, W, H, args, kind):
     assert np.array_equal(ref, got)
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_tied_minimum_without_uniqueness(orc, mode):
+    """uniquenessRatio 0 (the matcher createRightMatcher builds, stereo_disparity.cpp:10) exposes how cv2 resolves a tied
+    minimum of S: first minimum in MODE_SGBM / MODE_HH, the 8-lane rule of computeDisparity3WaySGBM in MODE_SGBM_3WAY
+    (oracle/sdr_oracle.c wta_row). The half-size seed-2 frame has ties 8 and 16 disparities apart (rows 240..300)."""
+    l, r = synth.stereo_pair(1280, 720, 128, 2)
+    ls = cv2.resize(l, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_AREA)[240:300]
+    rs = cv2.resize(r, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_AREA)[240:300]
+    for a, b, minD, D in ((rs, ls, -79, 80), (ls, rs, 0, 64)):
+        args = (minD, D, 5, 600, 2400, 1000000, 63, 0, 0, 0, mode)
+        assert np.array_equal(cv2.StereoSGBM_create(*args).compute(a, b), orc.sgbm_compute(a, b, orc.make_params(*args)))
+
+
 def test_reproject_bits(orc, golden):
     rng = np.random.default_rng(3)
     d = rng.integers(-16, 1600, size=(30, 40)).astype(np.int16)
