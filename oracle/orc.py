@@ -22,10 +22,41 @@ class SgbmParams(C.Structure):
         "preFilterCap", "uniquenessRatio", "speckleWindowSize", "speckleRange", "mode")]
 
 
+def _src_digest():
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("sdr_oracle.c", "Makefile"):
+        with open(os.path.join(_HERE, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def build(force=False):
-    src = os.path.join(_HERE, "sdr_oracle.c")
-    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libsdr_oracle.so"])
+    """Builds libsdr_oracle.so when it is missing or was built from other sources (content hash in a sidecar file: file
+    times mean nothing after the tree has been copied to another machine). Safe against concurrent callers -- the worker
+    processes of the CPU baseline all come through here: one builder at a time (flock), the library is written under a
+    temporary name and moved into place, so nobody ever maps a half-written file."""
+    import fcntl
+    stamp = _LIB + ".sha256"
+    want = _src_digest()
+
+    def fresh():
+        try:
+            with open(stamp) as fh:
+                return os.path.exists(_LIB) and fh.read().strip() == want
+        except OSError:
+            return False
+    if not force and fresh():
+        return _LIB
+    with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if force or not fresh():
+            tmp = "%s.tmp.%d" % (_LIB, os.getpid())
+            subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libsdr_oracle.so", "OUT=" + tmp])
+            os.replace(tmp, _LIB)
+            with open(stamp + ".tmp", "w") as fh:
+                fh.write(want)
+            os.replace(stamp + ".tmp", stamp)
     return _LIB
 
 
