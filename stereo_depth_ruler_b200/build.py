@@ -28,7 +28,7 @@ def _stale(out, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".inl"))]
     hdrs += [os.path.join(ROOT, "include", "sdr_c.h")]
     jobs = []
     objs = []

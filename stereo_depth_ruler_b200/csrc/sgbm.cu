@@ -723,6 +723,137 @@ __host__ __device__ inline CfLayout cf_layout(int D, int SW2, int SH2, int COLS)
     return L;
 }
 
+// The producer role of k_wave_fwd (the same code as the producer branch of k_cost_path_v3, which keeps its own inlined copy:
+// routed through this function ptxas spills 20 bytes there and the kernel loses 5 %): CF_PROD threads compute the C row tiles of one COLS-column
+// strip of frame b, one image row after the other, into the ring `ringC` (CF_NST slots, hand-shake fullC / emptyC with the
+// readers) and write every finished tile to the C volume with one TMA bulk store.
+template <int NP, int SW2, int CF_PROD, int COLS>
+__device__ __forceinline__ void cost_producer(const Geom& g, const int4* __restrict__ PL, const uint8_t* __restrict__ PR, int16_t* __restrict__ C,
+                                              int b, int x0, uint8_t* cfsm, const CfLayout& lay, uint64_t (&fullC)[CF_NST], uint64_t (&emptyC)[CF_NST],
+                                              uint64_t (&fullIn)[2], uint32_t tile_bytes) {
+    int16_t* ringC = (int16_t*)(cfsm + lay.off_ring_c);
+    constexpr int D = 16 * NP, DQ = D / 8;
+    constexpr int XG = CF_PROD / DQ;            // producer column groups
+    constexpr int CPT = COLS / XG;              // consecutive output columns per producer thread
+    constexpr int NX = 2 * SW2;                 // halo columns of the strip (box-sum window minus one)
+    constexpr int CW = COLS + NX;
+    static_assert(CF_PROD % DQ == 0 && COLS % XG == 0 && NX <= XG, "producer tiling");
+    const int n = 2 * g.SH2 + 1;
+    const int tid = threadIdx.x;
+    const int q = tid % DQ, xg = tid / DQ;
+    uint8_t* stage = cfsm + lay.off_stage;
+    uint8_t* ring8 = cfsm + lay.off_ring8;                 // [n][CW][D] u8
+    uint16_t* Vs = (uint16_t*)(cfsm + lay.off_vs);         // [CW][D] u16
+    const int lo = max(x0 - SW2, 0), hi = min(x0 - SW2 + CW, g.W1);
+    const int j0_min = (g.W - 1 - (hi - 1 + g.minX1)) + g.minD, j0_max = (g.W - 1 - (lo + g.minX1)) + g.minD + 8 * (DQ - 1);
+    const int cs = max(j0_min - 3, 0) >> 4, nchunks = ((j0_max + 7) >> 4) - cs + 1;
+    const uint32_t pl_bytes = (uint32_t)(hi - lo) * 16, pr_bytes = (uint32_t)nchunks * PR_CHUNK;
+    constexpr int ITEMS = CPT + 1;
+    // item k < CPT: strip column h = CPT*xg + k (h counts from x0 - SW2); item CPT: halo column h = 32 + xg (xg < NX)
+    uint32_t tab[ITEMS];   // per item: o0 (low 16 bits) | ix << 16 | "second word is in the next chunk" << 31
+    uint32_t V[ITEMS][4];
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        const int h = k < CPT ? CPT * xg + k : COLS + xg;
+        const int xc = min(max(x0 - SW2 + h, 0), g.W1 - 1);
+        const int ix = min(max(xc - lo, 0), CW - 1);
+        const int j0 = (g.W - 1 - (xc + g.minX1)) + g.minD + 8 * q;
+        const int a = j0 & 3, p0 = j0 - a;
+        const int o0 = ((p0 >> 4) - cs) * PR_CHUNK + (p0 & 15) + a * 16;
+        tab[k] = (uint32_t)o0 | ((uint32_t)ix << 16) | ((p0 & 15) == 12 ? 0x80000000u : 0u);
+        V[k][0] = V[k][1] = V[k][2] = V[k][3] = 0;
+    }
+    const int NV = g.H + 2 * g.SH2;
+    auto issue_in = [&](int i) {   // one thread: stage virtual row i (image row clamp(i - SH2))
+        const int rc = min(max(i - g.SH2, 0), g.H - 1);
+        uint8_t* st = stage + (size_t)(i & 1) * lay.stage_bytes;
+        mbar_expect_tx(&fullIn[i & 1], pl_bytes + pr_bytes);
+        bulk_g2s(st, PL + ((size_t)b * g.H + rc) * g.W + lo + g.minX1, pl_bytes, &fullIn[i & 1]);
+        bulk_g2s(st + CW * 16, PR + (((size_t)b * g.H + rc) * (g.Wp >> 4) + cs) * PR_CHUNK, pr_bytes, &fullIn[i & 1]);
+    };
+    if (tid == 0) {
+        issue_in(0);
+        if (NV > 1) issue_in(1);
+    }
+    int slot = 0, cst = 0;
+    uint32_t cphase = 0;
+    for (int i = 0; i < NV; i++) {
+        const uint8_t* st = stage + (size_t)(i & 1) * lay.stage_bytes;
+        mbar_wait(&fullIn[i & 1], (uint32_t)((i >> 1) & 1));
+        const int4* pls = (const int4*)st;
+        const uint8_t* prs = st + CW * 16;
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+            if (k < CPT || xg < NX) {
+                const int h = k < CPT ? CPT * xg + k : COLS + xg;
+                const int o0 = (int)(tab[k] & 0xFFFFu), ix = (int)((tab[k] >> 16) & 0x7FFFu);
+                const int o1 = o0 + ((int)tab[k] < 0 ? PR_CHUNK - 12 : 4);
+                uint32_t n0, n1;
+                bt_item(pls[ix], prs, o0, o1, n0, n1);
+                uint2* rp = (uint2*)(ring8 + ((size_t)slot * CW + h) * D + 8 * q);
+                const uint2 old = *rp;
+                *rp = make_uint2(n0, n1);
+                // V += new - old per 16-bit half: new (bytes, zero-extended) minus old (bytes, zero-extended)
+                V[k][0] = __vsub2(__vadd2(V[k][0], prmt(n0, 0, 0x4140)), prmt(old.x, 0, 0x4140));
+                V[k][1] = __vsub2(__vadd2(V[k][1], prmt(n0, 0, 0x4342)), prmt(old.x, 0, 0x4342));
+                V[k][2] = __vsub2(__vadd2(V[k][2], prmt(n1, 0, 0x4140)), prmt(old.y, 0, 0x4140));
+                V[k][3] = __vsub2(__vadd2(V[k][3], prmt(n1, 0, 0x4342)), prmt(old.y, 0, 0x4342));
+            }
+        }
+        slot = slot + 1 == n ? 0 : slot + 1;
+        const int y = i - 2 * g.SH2;          // output row finished by this virtual row
+        if (y >= 0) {
+#pragma unroll
+            for (int k = 0; k < ITEMS; k++)
+                if (k < CPT || xg < NX) {
+                    const int h = k < CPT ? CPT * xg + k : COLS + xg;
+                    *(uint4*)(Vs + (size_t)h * D + 8 * q) = make_uint4(V[k][0], V[k][1], V[k][2], V[k][3]);
+                }
+            // the bulk store that last read ring slot cst must be done reading before the slot is rewritten
+            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(CF_NST - 1) : "memory");
+        }
+        named_bar_sync(2, CF_PROD);   // Vs complete; every producer thread is done with this input stage
+        if (tid == 0 && i + 2 < NV) issue_in(i + 2);
+        if (y >= 0) {
+            if (y >= CF_NST) mbar_wait(&emptyC[cst], cphase ^ 1);   // consumers released the slot (use number y/NST - 1)
+            // horizontal box sum: window of CPT + NX columns = own columns (registers) + NX right neighbours (Vs)
+            uint32_t w[CPT + NX][4];
+#pragma unroll
+            for (int k = 0; k < CPT; k++) { w[k][0] = V[k][0]; w[k][1] = V[k][1]; w[k][2] = V[k][2]; w[k][3] = V[k][3]; }
+#pragma unroll
+            for (int j = 0; j < NX; j++) {
+                const uint4 v = *(const uint4*)(Vs + (size_t)(CPT * xg + CPT + j) * D + 8 * q);
+                w[CPT + j][0] = v.x; w[CPT + j][1] = v.y; w[CPT + j][2] = v.z; w[CPT + j][3] = v.w;
+            }
+            uint32_t acc[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                acc[r] = w[0][r];
+#pragma unroll
+                for (int j = 1; j <= NX; j++) acc[r] = __vadd2(acc[r], w[j][r]);
+            }
+            int16_t* ct = ringC + (size_t)cst * COLS * D;
+#pragma unroll
+            for (int k = 0; k < CPT; k++) {
+                if (k > 0) {
+#pragma unroll
+                    for (int r = 0; r < 4; r++) acc[r] = __vsub2(__vadd2(acc[r], w[k + NX][r]), w[k - 1][r]);
+                }
+                *(uint4*)(ct + (size_t)(CPT * xg + k) * D + 8 * q) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
+            named_bar_sync(3, CF_PROD);   // tile complete (and every read of Vs is done)
+            if (tid == 0) {
+                bulk_s2g(C + (((size_t)b * g.crows + y) * g.W1 + x0) * D, ct, tile_bytes);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                mbar_arrive(&fullC[cst]);
+            }
+            if (++cst == CF_NST) { cst = 0; cphase ^= 1; }
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <int NP, int SW2, int CF_PROD, int COLS>
 __global__ void __launch_bounds__(CF_PROD + COLS * 8, COLS == 32 ? 2 : 1)
 k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ PR, int16_t* __restrict__ C, int16_t* __restrict__ S, int b0,
@@ -982,7 +1113,8 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
 
 // WTA + uniqueness + sub-pixel for one pixel whose final S is in registers (all lanes of the group
 // take part; results are uniform across the group).
-template <int NP, int G>
+// STORE = false: `sm` already holds the pixel's S in natural order (a staged row tile), nothing is written.
+template <int NP, int G, bool STORE = true>
 __device__ __forceinline__ void wta_pixel(const uint32_t (&Sr)[NP], int lg, const Geom& g, int16_t* sm, int& disp_out,
                                           uint32_t& wta_out) {
     // first minimum: keys (S << 8 | d) built with one PRMT per half, reduced with 3-input minima
@@ -1016,8 +1148,10 @@ __device__ __forceinline__ void wta_pixel(const uint32_t (&Sr)[NP], int lg, cons
 #pragma unroll
     for (int o = G / 2; o >= 1; o >>= 1) nlt += __shfl_xor_sync(0xffffffffu, nlt, o, G);
     // neighbours of the minimum through shared memory
-    store_regs<NP>(sm + d0, Sr);
-    __syncwarp();
+    if constexpr (STORE) {
+        store_regs<NP>(sm + d0, Sr);
+        __syncwarp();
+    }
     if (g.tie8) {
         // cv2's computeDisparity3WaySGBM looks for the minimum with 8-lane vectors: lane r keeps the LAST d = r (mod 8) that
         // holds its minimum, min_pos() then takes the smallest position among the lanes at the global minimum. It shows only
@@ -1370,6 +1504,8 @@ __global__ void __launch_bounds__(256) k_lrcheck(Geom g, const int16_t* __restri
 // bit-exact (tests/test_gpu_sgbm.py runs them against the oracle); they exist for A/B measurements and for callers that
 // know how many matchers share the device. 0 = the built-in default unless stated otherwise.
 struct SgbmTune {
+    int wave = 0;           // MODE_SGBM as two wavefront strip sweeps (k_wave_fwd + k_wave_bwd, 4 volume passes); 2: forward sweep only,
+                            // the / path and <- + WTA by the per-direction kernels (validation of the forward sweep alone)
     int fused_sweep = 1;    // cooperative down/diagonal sweep (k_path_v3); 0: one launch per direction (k_path_v)
     int cost_fusion = 1;    // cost volume inside the sweep kernel (k_cost_path_v3)
     int path_hh = -1;       // both horizontal paths in one launch (k_path_hh): 1 / 0, -1 = automatic (on for a lone matcher)
@@ -1482,6 +1618,8 @@ struct V3Scratch {
     DevBuf halo, err;
     PinnedBuf host_err;
 };
+
+#include "sgbm_wave.inl"
 
 // Returns SDR_OK, an error, or -1 when the cooperative grid cannot be co-resident (caller falls back).
 template <int NP>
@@ -1627,6 +1765,7 @@ struct sdr_sgbm {
     DevBuf inL, inR, PL, PR, C, S, dispraw, wta, matched, out;
     SpeckleScratch speckle;
     V3Scratch v3;
+    WaveScratch wave;
     SgbmTune tune;                             // kernel-selection knobs (sdr_sgbm_set_option); results never depend on them
     int stripe_first = 0, stripe_count = -1;   // MODE_SGBM_3WAY: subset of the four stripes to match (-1 = all)
     bool skip_post = false;                    // stop after the raw matcher output (median / speckle run elsewhere)
@@ -1674,7 +1813,7 @@ extern "C" void sdr_sgbm_destroy(sdr_sgbm* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
     for (DevBuf* b : {&m->inL, &m->inR, &m->PL, &m->PR, &m->C, &m->S, &m->dispraw, &m->wta, &m->matched, &m->out,
-                      &m->speckle.parent, &m->speckle.count, &m->v3.halo, &m->v3.err, &m->post_in})
+                      &m->speckle.parent, &m->speckle.count, &m->v3.halo, &m->v3.err, &m->post_in, &m->wave.haloD, &m->wave.haloH})
         b->release();
     m->v3.host_err.release();
     m->timer.release();
@@ -1781,8 +1920,33 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
         // a fused sweep of an earlier, asynchronous (device-output) call that gave up on a neighbouring strip is reported
         // here, once; the flag is cleared so the handle keeps working (calls that wait on the stream report it themselves)
         if ((rc = sdr_sgbm_take_sweep_error(m))) return rc;
+        // MODE_SGBM as two wavefront sweeps (option "wave"): everything up to the raw disparity in two kernels
+        bool wave_done = false;
+        if (m->p.mode == SDR_MODE_SGBM && m->tune.wave != 0 && g.nseg == 1 && g.SW2 == g.SH2 && (np == 4 || np == 8) && (g.SW2 == 1 || g.SW2 == 2)) {
+            const bool bwd = m->tune.wave != 2;
+            rc = -1;
+#define WAVE_CASE(NPV, SWV)                                                                                                                    \
+    if (np == NPV && g.SW2 == SWV)                                                                                                             \
+        rc = launch_wave<NPV, SWV>(ctx, g, batch, m->PL.as<int4>(), m->PR.as<uint8_t>(), m->C.as<int16_t>(), S, m->dispraw.as<int16_t>(),       \
+                                   m->wta.as<uint32_t>(), m->v3, m->wave, m->timer, bwd);
+            WAVE_CASE(8, 2) WAVE_CASE(8, 1) WAVE_CASE(4, 2) WAVE_CASE(4, 1)
+#undef WAVE_CASE
+            if (rc > 0) return rc;
+            if (rc == SDR_OK) {
+                wave_done = true;
+                if (!bwd) {
+                    NP_SWITCH(np, rc = launch_path_v<NPc>(ctx, g, batch, C, S, -1, +1, 1));
+                    if (rc) return rc;
+                    m->timer.mark(st, "path_v2");
+                    NP_SWITCH(np, rc = launch_path_h<NPc>(ctx, m->tune, g, batch, C, S, -1, 1, true, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>()));
+                    if (rc) return rc;
+                    m->timer.mark(st, "path_h_bwd_wta");
+                }
+            }
+        }
         // MODE_SGBM / MODE_HH: cost volume and top-down sweep in one kernel when the configuration is covered
         bool cost_done = false;
+        if (!wave_done) {
         if (m->p.mode != SDR_MODE_SGBM_3WAY && m->tune.fused_sweep && m->tune.cost_fusion) {
             rc = launch_cost_path_fused(ctx, m->tune, g, batch, m->PL.as<int4>(), m->PR.as<uint8_t>(), m->C.as<int16_t>(), S, m->v3);
             if (rc > 0) return rc;
@@ -1853,6 +2017,7 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
             if (rc) return rc;
             m->timer.mark(st, "path_h_bwd_wta");
         }
+        }   // !wave_done
         const int ry0 = g.seg[0].dst_start, ry1 = g.seg[g.nseg - 1].src_end;   // output rows of the selected stripes
         k_lrcheck<<<dim3(ry1 - ry0, 1, batch), 256, (size_t)W * sizeof(uint32_t), st>>>(g, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>(),
                                                                                           m->matched.as<int16_t>(), (size_t)W * 2, img16, ry0);
@@ -2024,7 +2189,7 @@ extern "C" int sdr_sgbm_set_option(sdr_sgbm* m, const char* name, int value) {
     if (!m || !name) return SDR_EINVAL;
     SgbmTune& t = m->tune;
     const struct { const char* n; int* p; } tab[] = {
-        {"fused_sweep", &t.fused_sweep}, {"cost_fusion", &t.cost_fusion}, {"path_hh", &t.path_hh}, {"shared_device", &t.shared_device},
+        {"wave", &t.wave}, {"fused_sweep", &t.fused_sweep}, {"cost_fusion", &t.cost_fusion}, {"path_hh", &t.path_hh}, {"shared_device", &t.shared_device},
         {"cf_cols", &t.cf_cols}, {"cf_prod", &t.cf_prod}, {"cf_fpl", &t.cf_fpl}, {"v3_stages", &t.v3_stages}, {"h_legacy", &t.h_legacy}, {"h_lanes", &t.h_lanes},
         {"h_k", &t.h_k}, {"h_stages", &t.h_stages}, {"h_warps", &t.h_warps}, {"hb_threads", &t.hb_threads}, {"hb_ring", &t.hb_ring},
         {"hh_threads", &t.hh_threads}};

@@ -325,3 +325,36 @@ def test_headline_batch_of_8_equals_single_frames(ctx, golden):
         assert np.array_equal(out[i], ref.compute(*pairs[i])), "frame %d differs from cv2" % i
         assert np.array_equal(out[i], m.compute(*pairs[i])), i
     m.close()
+
+
+@pytest.mark.parametrize("wave", [1, 2])
+@pytest.mark.parametrize("W,H,args", [(200, 24, (0, 64, 5, 600, 2400, 1, 63, 12, 0, 0, 0)), (161, 9, (0, 64, 3, 72, 288, 1, 63, 12, 0, 0, 0)),
+                                      (300, 40, (0, 128, 5, 600, 2400, 1, 63, 12, 50, 2, 0)), (257, 31, (0, 128, 3, 72, 288, 2, 63, 5, 0, 0, 0)),
+                                      (400, 50, (-16, 64, 5, 600, 2400, 1, 63, 12, 0, 0, 0))])
+def test_wavefront_sweeps(ctx, orc, W, H, args, wave):
+    """Option wave: MODE_SGBM as two strip sweeps whose strips run one behind the other (k_wave_fwd: cost + -> \\ |,
+    k_wave_bwd: / <- + WTA; wave = 2: the forward sweep followed by the per-direction kernels). Ragged strips (W1 not a
+    multiple of 32), fewer rows than strips, D = 64 / 128, blockSize 3 / 5, a batch of two: raw matcher output == oracle."""
+    from stereo_depth_ruler_b200 import capi, synth
+    l, r = synth.stereo_pair(W, H, args[1], 21)
+    po = orc.make_params(*args)
+    m = capi.Sgbm(ctx, capi.make_params(*args)).set_option("wave", wave)
+    m.set_profiling(True)
+    got = m.compute(l, r)
+    assert "wave_fwd" in [k for k, _ in m.stage_times()]
+    assert np.array_equal(m.debug_read(2, (H, W)), orc.sgbm_match(l, r, po))
+    assert np.array_equal(got, orc.sgbm_compute(l, r, po))
+    pairs = [synth.stereo_pair(W, H, args[1], 80 + s) for s in range(2)]
+    out = m.compute_batch(np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs]), np.empty((2, H, W), np.int16))
+    for i in range(2):
+        assert np.array_equal(out[i], orc.sgbm_compute(pairs[i][0], pairs[i][1], po)), i
+    m.close()
+
+
+def test_wavefront_sweeps_headline_equals_cv2(ctx, golden):
+    """The headline shape through the wavefront sweeps: bit-exact against the cv2 fixture (sha256 of the CV_16S map)."""
+    from stereo_depth_ruler_b200 import capi, synth
+    l, r = synth.stereo_pair(1280, 720, 128, 0)
+    m = capi.Sgbm(ctx, capi.make_params()).set_option("wave", 1)
+    assert sha(m.compute(l, r)) == str(golden["full_c1_sha"])
+    m.close()
