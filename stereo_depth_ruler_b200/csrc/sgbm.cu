@@ -854,8 +854,15 @@ __device__ __forceinline__ void cost_producer(const Geom& g, const int4* __restr
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// register split between the roles (setmaxnreg), per strip width: producer / consumer registers per thread
+template <int CF_PROD, int COLS> struct CfRegs {
+    static constexpr int prod = COLS == 16 ? 56 : (2 * CF_PROD == COLS * 8 ? 64 : 48);
+    static constexpr int cons = COLS == 16 ? 96 : (2 * CF_PROD == COLS * 8 ? 88 : 80);
+    static constexpr int min_blocks = COLS == 16 ? 3 : COLS == 32 ? 2 : 1;   // fixes the launch register count: 80 / 80 or 64 / 80
+};
+
 template <int NP, int SW2, int CF_PROD, int COLS>
-__global__ void __launch_bounds__(CF_PROD + COLS * 8, COLS == 32 ? 2 : 1)
+__global__ void __launch_bounds__(CF_PROD + COLS * 8, CfRegs<CF_PROD, COLS>::min_blocks)
 k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ PR, int16_t* __restrict__ C, int16_t* __restrict__ S, int b0,
                unsigned long long* halo, int* err) {
     constexpr int G = 8, NW = NP + 1, D = 16 * NP, DQ = D / 8;
@@ -892,9 +899,9 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
     // consumer chain priority while the producer's independent arithmetic fills the remaining issue slots.
     if (threadIdx.x < CF_PROD) {
         // =============================== producer: cost rows ===============================
-        // register split (per thread): 128 producers 64 / consumers 88 (launch 80); 256 producers 48 / consumers 80 (launch 64)
-        if constexpr (2 * CF_PROD == COLS * 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
-        else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;\n");
+        // register split (per thread): 128 producers 64 / consumers 88 (launch 80); 256 producers 48 / consumers 80 (launch 64);
+        // 16-column strips: 128 producers 56 / 128 consumers 96 (launch 80)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(CfRegs<CF_PROD, COLS>::prod));
         const int tid = threadIdx.x;
         const int q = tid % DQ, xg = tid / DQ;
         uint8_t* stage = cfsm + lay.off_stage;
@@ -1012,8 +1019,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
     }
 
     // =============================== consumer: the three top-down paths ===============================
-    if constexpr (2 * CF_PROD == COLS * 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;\n");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 80;\n");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(CfRegs<CF_PROD, COLS>::cons));
     const int ct = threadIdx.x - CF_PROD;
     const int gidx = ct / G, lg = ct & (G - 1);
     const int x = x0 + gidx;
@@ -1510,7 +1516,7 @@ struct SgbmTune {
     int cost_fusion = 1;    // cost volume inside the sweep kernel (k_cost_path_v3)
     int path_hh = -1;       // both horizontal paths in one launch (k_path_hh): 1 / 0, -1 = automatic (on for a lone matcher)
     int shared_device = 0;  // 1: other matchers run on this device at the same time (what "automatic" looks at)
-    int cf_cols = 0;        // strip width of the fused kernel: 32 / 64
+    int cf_cols = 0;        // strip width of the fused kernel: 16 / 32 / 64 (0 = by the number of strips in flight)
     int cf_prod = 0;        // its producer threads: 128 / 256
     int cf_fpl = 0;         // frames per cooperative launch
     int v3_stages = 0;      // TMA ring depth of k_path_v3
@@ -1723,6 +1729,16 @@ int launch_cost_path_fused(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int 
         if (g.SW2 == 2) rc64 = launch_cost_path_v3<8, 2, 256, 64>(ctx, tn, g, batch, PL, PR, C, S, sc);
         else if (g.SW2 == 1) rc64 = launch_cost_path_v3<8, 1, 256, 64>(ctx, tn, g, batch, PL, PR, C, S, sc);
         if (rc64 != -1) return rc64;   // -1: does not fit this device, try the smaller CTAs
+    }
+    // Few frames in flight (the reference's usage: one frame at a time): 16-column strips put twice as many CTAs on the machine
+    // (one 1280x720 frame: 72 instead of 36), each with half the work per row.
+    if (env_cols == 16 || (env_cols == 0 && (long long)div_up(g.W1, 32) * batch * 2 <= ctx->sm_count)) {
+        int rc16 = -1;
+        if (np == 8 && g.SW2 == 2) rc16 = launch_cost_path_v3<8, 2, 128, 16>(ctx, tn, g, batch, PL, PR, C, S, sc);
+        else if (np == 8 && g.SW2 == 1) rc16 = launch_cost_path_v3<8, 1, 128, 16>(ctx, tn, g, batch, PL, PR, C, S, sc);
+        else if (np == 4 && g.SW2 == 2) rc16 = launch_cost_path_v3<4, 2, 128, 16>(ctx, tn, g, batch, PL, PR, C, S, sc);
+        else if (np == 4 && g.SW2 == 1) rc16 = launch_cost_path_v3<4, 1, 128, 16>(ctx, tn, g, batch, PL, PR, C, S, sc);
+        if (rc16 != -1) return rc16;
     }
 #define CF_CASE(NPV, SWV)                                                                                                  \
     if (np == NPV && g.SW2 == SWV)                                                                                         \

@@ -287,14 +287,16 @@ def test_per_direction_fallback_kernels(ctx, orc, mode):
     m.close()
 
 
+@pytest.mark.parametrize("cols,D", [(64, 128), (16, 128), (16, 64), (32, 128)])
 @pytest.mark.parametrize("W,H,bs", [(300, 40, 5), (333, 23, 3), (257, 31, 5)])
-def test_fused_kernel_wide_strips_small(ctx, orc, W, H, bs):
-    """Option cf_cols=64: the 64-column-strip form of the fused kernel (one CTA per SM; what a batch of 8 at 1280 wide runs)
-    on ragged widths (last strip partial, a single strip + 1 column), against the oracle."""
+def test_fused_kernel_strip_widths_small(ctx, orc, W, H, bs, cols, D):
+    """Option cf_cols: the fused kernel with 64-column strips (one CTA per SM; what a batch of 8 at 1280 wide runs), 32-column
+    strips and 16-column strips (what a single frame runs: twice the CTAs) on ragged widths (last strip partial, a single
+    strip + 1 column), against the oracle."""
     from stereo_depth_ruler_b200 import capi, synth
-    args = (0, 128, bs, 8 * bs * bs, 32 * bs * bs, 1, 63, 12, 50, 2, 0)
-    pairs = [synth.stereo_pair(W, H, 128, 50 + s) for s in range(2)]
-    m = capi.Sgbm(ctx, capi.make_params(*args)).set_option("cf_cols", 64)
+    args = (0, D, bs, 8 * bs * bs, 32 * bs * bs, 1, 63, 12, 50, 2, 0)
+    pairs = [synth.stereo_pair(W, H, D, 50 + s) for s in range(2)]
+    m = capi.Sgbm(ctx, capi.make_params(*args)).set_option("cf_cols", cols)
     m.set_profiling(True)
     out = m.compute_batch(np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs]), np.empty((2, H, W), np.int16))
     assert "cost_path_v_fused" in [k for k, _ in m.stage_times()]
