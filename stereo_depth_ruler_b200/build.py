@@ -13,6 +13,7 @@ LIB = os.path.join(HERE, "libsdr_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+FLAGS += os.environ.get("SDR_NVCC_EXTRA", "").split()   # experiments only (e.g. -DSDR_EXP_...); the shipped library is built without
 
 
 def sources():

@@ -1360,6 +1360,8 @@ __global__ void __launch_bounds__(THREADS) k_path_hh(Geom g, const int16_t* __re
     }
 }
 
+#include "sgbm_chain32.inl"
+
 // Horizontal chains with a TMA-fed shared-memory ring (default): a warp owns 4 rows (8 lanes each); lane 0 of every row
 // group stages the next chunks of K steps of its row (K*D*2 contiguous bytes of C, and of S) with bulk async copies,
 // H_STAGES chunks deep, completion on a per-warp mbarrier. That keeps ~16 KB per warp in flight instead of the 2 KB a
@@ -1522,6 +1524,7 @@ struct SgbmTune {
     int v3_stages = 0;      // TMA ring depth of k_path_v3
     int h_legacy = 0;       // register-prefetch k_path_h instead of the TMA-ring k_path_h2 for L->R
     int h_lanes = 0;        // lanes per row chain in k_path_hh: 8 / 16 / 32, 0 = by the number of rows in flight
+    int h_ws = 1;           // few rows in flight: chain warps + tail warps (k_path_hh_ws) instead of k_path_hh with 16 / 32 lanes
     int h_k = 0, h_stages = 0, h_warps = 0, hb_threads = 0, hb_ring = -1, hh_threads = 0;
 };
 
@@ -1596,6 +1599,14 @@ int launch_path_hh(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, c
         if (lanes == 32 && NP % 4) lanes = 16;
         if (lanes == 16 && NP % 2) lanes = 8;
         if constexpr (NP % 4 == 0) {
+            // latency mode: chains and per-pixel tails in different warps (k_path_hh_ws), as long as every row's CTA is resident at once
+            // latency mode (a single frame of up to ~900 rows): beyond ~24 warps per SM the 32-lane chains, two registers per lane,
+            // cost more issue slots than they save in latency (4K x 256: 4.1 -> 9.5 ms)
+            if (tn.h_ws != 0 && lanes != 8 && rows <= (long)ctx->sm_count * 6) {
+                k_path_hh_ws<NP / 4><<<dim3(g.hrows, 1, batch), HWS_THREADS, 0, ctx->stream>>>(g, C, S, dispraw, wta);
+                SDR_LAUNCHED(ctx);
+                return SDR_OK;
+            }
             if (lanes == 32) {
                 k_path_hh<NP / 4, 32, 64><<<dim3(g.hrows, 1, batch), 64, 0, ctx->stream>>>(g, C, S, dispraw, wta);
                 SDR_LAUNCHED(ctx);
@@ -2206,7 +2217,7 @@ extern "C" int sdr_sgbm_set_option(sdr_sgbm* m, const char* name, int value) {
     SgbmTune& t = m->tune;
     const struct { const char* n; int* p; } tab[] = {
         {"wave", &t.wave}, {"fused_sweep", &t.fused_sweep}, {"cost_fusion", &t.cost_fusion}, {"path_hh", &t.path_hh}, {"shared_device", &t.shared_device},
-        {"cf_cols", &t.cf_cols}, {"cf_prod", &t.cf_prod}, {"cf_fpl", &t.cf_fpl}, {"v3_stages", &t.v3_stages}, {"h_legacy", &t.h_legacy}, {"h_lanes", &t.h_lanes},
+        {"cf_cols", &t.cf_cols}, {"cf_prod", &t.cf_prod}, {"cf_fpl", &t.cf_fpl}, {"v3_stages", &t.v3_stages}, {"h_legacy", &t.h_legacy}, {"h_lanes", &t.h_lanes}, {"h_ws", &t.h_ws},
         {"h_k", &t.h_k}, {"h_stages", &t.h_stages}, {"h_warps", &t.h_warps}, {"hb_threads", &t.hb_threads}, {"hb_ring", &t.hb_ring},
         {"hh_threads", &t.hh_threads}};
     for (const auto& e : tab)

@@ -19,28 +19,6 @@ constexpr int WV_CONS = WV_COLS * 8;
 constexpr int WV_NSTA = 3;         // partial-S row tiles in flight between the column-parallel warps and the chain warp
 constexpr int WB_NST = 5;          // k_wave_bwd: (C, S) row tiles in flight: loader 2 ahead, diagonal, chain, winner-take-all
 constexpr int WB_LAG = 2;          // rows between the diagonal step and the winner-take-all of a tile
-constexpr int WV_WAIT_LIMIT = 1 << 22;
-
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// mbarrier wait that cannot hang the GPU: a broken hand-shake inside the CTA ends the kernel with a trap (the launch fails
-// loudly) instead of spinning until the watchdog
-__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
-    for (int i = 0; i < WV_WAIT_LIMIT; i++)
-        if (mbar_test(bar, parity)) return;
-    __trap();
-}
 
 struct WvLayout {
     CfLayout cf;          // what the producer role needs (stage, pixel-cost ring, vertical sums, C ring)
@@ -64,45 +42,6 @@ __host__ __device__ inline WvLayout wv_layout(int D, int SW2, int SH2) {
     L.total = o;
     W.total = o;
     return W;
-}
-
-// One step of a horizontal path held by a whole warp: lane l owns disparities [2*NPc*l, 2*NPc*(l+1)).
-template <int NPc>
-__device__ __forceinline__ void sgm_step32(uint32_t (&P)[NPc], uint32_t& m, const uint32_t (&c)[NPc], uint32_t P1x2, uint32_t P2x2, uint32_t PADx2,
-                                           int lane) {
-    uint32_t up = __shfl_up_sync(0xffffffffu, P[NPc - 1], 1);
-    uint32_t dn = __shfl_down_sync(0xffffffffu, P[0], 1);
-    if (lane == 0) up = PADx2;
-    if (lane == 31) dn = PADx2;
-    uint32_t T[NPc + 1];
-    T[0] = prmt(up, P[0], 0x5432);
-#pragma unroll
-    for (int k = 1; k < NPc; k++) T[k] = prmt(P[k - 1], P[k], 0x5432);
-    T[NPc] = prmt(P[NPc - 1], dn, 0x5432);
-    const uint32_t negm = __vadd2(~m, 0x00010001u);
-    uint32_t mm = 0x7FFF7FFFu;
-#pragma unroll
-    for (int k = 0; k < NPc; k++) {
-        uint32_t t = __vmins2(T[k], T[k + 1]);
-        t = __viaddmin_s16x2(t, P1x2, P[k]);
-        t = __viaddmin_s16x2(t, negm, P2x2);
-        P[k] = __vadd2(c[k], t);
-        mm = __vmins2(mm, P[k]);
-    }
-    mm = __vmins2(mm, prmt(mm, mm, 0x1032));   // both halves = the lane's minimum (>= 0), so the u32 order is the int16 order
-    asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(m) : "r"(mm));
-}
-template <int N>
-__device__ __forceinline__ void ld_chain(const int16_t* p, uint32_t (&r)[N]) {
-    if constexpr (N == 4) { const uint4 v = *(const uint4*)p; r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w; }
-    else if constexpr (N == 2) { const uint2 v = *(const uint2*)p; r[0] = v.x; r[1] = v.y; }
-    else { r[0] = *(const uint32_t*)p; }
-}
-template <int N>
-__device__ __forceinline__ void st_chain(int16_t* p, const uint32_t (&r)[N]) {
-    if constexpr (N == 4) *(uint4*)p = make_uint4(r[0], r[1], r[2], r[3]);
-    else if constexpr (N == 2) *(uint2*)p = make_uint2(r[0], r[1]);
-    else *(uint32_t*)p = r[0];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
