@@ -6,8 +6,9 @@
 Workload c2 (default; config.workload = BASELINE.json configs[1]): the full pipeline per frame -- remap rectification of
 both halves of a 2560x720 SBS frame, StereoSGBM-compatible MODE_SGBM (D=128, reference parameter tuple) with LR check,
 median and speckle filter, reprojectImageTo3D and the 5 mm VoxelGrid -- on synthetic textured frames. A step = one pass
-over a batch of B frames per GPU. `value` is measured with the frames resident in HBM; `e2e` goes through the native
-frame-parallel runner of the C ABI (sdr_stream_*) with pinned HOST frames: H2D of the frames and D2H of the disparity
+over a batch of B frames per GPU. `value` is measured with the frames resident in HBM and `e2e` with pinned HOST frames,
+both through the native
+frame-parallel runner of the C ABI (sdr_stream_*); e2e has the H2D of the frames and the D2H of the disparity
 maps and the clouds inside the timed region. After the timed legs rank 0 pushes its timed frames through cv2 (the
 OpenCV calls the reference makes) and compares: `parity_gate`; a mismatch exits non-zero.
 Workload c4 (configs[3]): the same pipeline over a stream of --frames (4096) SBS frames from 64 unique pairs, sharded
@@ -334,7 +335,7 @@ def run_ours(args):
     # ---- value: frames resident in HBM. Several pipeline handles on their own streams, one host thread each (a handle is
     # one device <-> one stream; different handles may run concurrently): kernels of one batch overlap those of another ----
     slots = []
-    for k in range(NSLOT):
+    for k in range(NSLOT if args.value_runner == "python" else 1):
         if k == 0:
             c_k, st_k, p_k = ctx, stream, pipe
         else:
@@ -403,7 +404,8 @@ def run_ours(args):
         return ms, st, t0, t1
 
     sampler = ClockSampler(local) if rank == 0 else None
-    if c4:
+    if args.value_runner == "native":
+        # the library's own worker threads (one per handle) over the device-resident pool: no host language on the path
         rv = capi.Stream([local], NSLOT, calib, params, vox, handle_missing=True, batch=B, download_clouds=False)
         ms, st_v, t0, t1 = timed_stream(rv, dev_pool, steps * B, max(args.warmup, NSLOT) * B)
         launches = int(st_v.kernel_launches)
@@ -510,6 +512,22 @@ def run_ours(args):
     runner.close()
     fps_e = sharding.aggregate_throughput(B * steps, world, ms_e)
 
+    # ---- the same end-to-end leg fed with NV12 frames, the format a hardware decoder delivers (sdr_stream_set_input_format):
+    # half the host->device bytes, the colour conversion runs on the device in front of the rectification ----
+    e2e_nv12 = None
+    if not args.no_ingest_leg:
+        from stereo_depth_ruler_b200 import synth
+        nv_pool = torch.from_numpy(np.stack([synth.bgr_to_nv12(f) for f in mine])).pin_memory()
+        runner = capi.Stream([local], NSLOT, calib, params, vox, handle_missing=True, batch=B, download_clouds=True)
+        runner.set_input_format(capi.PIX_NV12)
+        ms_n, st_n, _, _ = timed_stream(runner, nv_pool.numpy(), steps * B, max(args.warmup, NSLOT) * B)
+        runner.close()
+        e2e_nv12 = {"value": sharding.aggregate_throughput(B * steps, world, ms_n), "unit": "frames/s", "ms_per_step": ms_n / steps,
+                    "h2d_bytes_per_step": int(st_n.h2d_bytes // steps), "d2h_bytes_per_step": int(st_n.d2h_bytes // steps),
+                    "input": "NV12 SBS frames in pinned host memory (sdr_ingest_to_bgr on the device); not the headline e2e: the "
+                             "reference arm starts from BGR frames"}
+        del nv_pool
+
     # ---- parity gate: the frames the timed legs ran on, through the same C-ABI call, against cv2 ----
     gate = None
     if rank == 0 and gate_ref is not None:
@@ -540,9 +558,10 @@ def run_ours(args):
                     "sharding": "frame i -> rank i mod N, no collective", "numa_node": numa_node, "sgbm_options": dict((k, int(v)) for k, v in sgbm_opts),
                     "concurrency": "%d pipeline handles (own stream + host thread each) per GPU alternate batches, so the copies and the "
                                    "ALU-bound kernels of one batch overlap the HBM-bound kernels of another; value: %s; e2e: native worker "
-                                   "threads of sdr_stream_*" % (NSLOT, "native runner on a device-resident pool" if c4 else "Python threads over sdr_pipeline_run")},
+                                   "threads of sdr_stream_*" % (NSLOT, "native runner (sdr_stream_process_pool) on a device-resident pool" if args.value_runner == "native" else "Python threads over sdr_pipeline_run")},
             "e2e": {"value": fps_e, "unit": "frames/s", "h2d_bytes_per_step": int(st_e.h2d_bytes // steps), "d2h_bytes_per_step": int(st_e.d2h_bytes // steps),
                     "ms_per_step": ms_e / steps, "api": "sdr_stream_create / sdr_stream_process_pool (include/sdr_c.h)"},
+            "e2e_ingest_nv12": e2e_nv12,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "parity_gate": gate["status"] if gate else "skipped", "parity": gate,
         }
@@ -577,6 +596,9 @@ def main():
     ap.add_argument("--frames", type=int, default=4096, help="c4: frames of the whole stream")
     ap.add_argument("--gate-frames", type=int, default=16, help="frames of rank 0's timed pool the parity gate checks against cv2")
     ap.add_argument("--sgbm-opt", action="append", default=[], help="name=value kernel knob (sdr_sgbm_set_option); results never change")
+    ap.add_argument("--value-runner", default="native", choices=["native", "python"],
+                    help="who drives the HBM-resident leg: the library's worker threads (default) or Python threads over sdr_pipeline_run")
+    ap.add_argument("--no-ingest-leg", action="store_true", help="skip the extra e2e leg fed with NV12 frames")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-gate", action="store_true")
     args = ap.parse_args()

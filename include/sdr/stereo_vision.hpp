@@ -350,4 +350,14 @@ class VoxelGrid {
     sdr_voxel_options opt_{{0.005f, 0.005f, 0.005f}, 0, 0.f, 0};
 };
 
+// Frame ingest in front of the loop of stereo_displayer.cpp:145-156 (`cap >> frame`): a decoder surface (NV12) or a UVC camera
+// buffer (YUYV) becomes the BGR side-by-side frame cv::VideoCapture would have returned: cv::cvtColor(src, bgr,
+// COLOR_YUV2BGR_NV12 / COLOR_YUV2BGR_YUY2), bit-exact, on the device. format: SDR_PIX_NV12 or SDR_PIX_YUYV.
+inline void cvtColorToBGR(Context& ctx, const Mat& src, Mat& bgr, int format) {
+    const int rows = format == SDR_PIX_NV12 ? src.rows() * 2 / 3 : src.rows();
+    bgr.create(rows, src.cols(), 3, 1);
+    ctx.check(sdr_ingest_to_bgr(ctx.get(), format, src.c(), bgr.c()));
+}
+inline void cvtColorToBGR(const Mat& src, Mat& bgr, int format) { cvtColorToBGR(Context::shared(), src, bgr, format); }
+
 }  // namespace sdr

@@ -257,6 +257,19 @@ SDR_API int sdr_vis_disparity(sdr_vis* v, const sdr_image* disparity32f, int num
 SDR_API int sdr_vis_depth(sdr_vis* v, const sdr_image* depth32f, sdr_image* out_bgr);
 SDR_API int sdr_vis_depth_range(sdr_vis* v, double* zmin_smooth, double* zmax_smooth);
 
+/* ---- frame ingest: what sits between the video source and the BGR side-by-side frame the reference's
+ *      loops start from (cv::VideoCapture >> frame, stereo_displayer.cpp:132-156, pcd_write.cpp:59-84). A hardware decoder
+ *      (NVDEC) delivers NV12 surfaces and the ZED 2 streams YUYV 4:2:2 over UVC; the frame crosses PCIe in that format (12 / 16
+ *      instead of 24 bits per pixel) and is converted on the device: cv::cvtColor(COLOR_YUV2BGR_NV12 / COLOR_YUV2BGR_YUY2),
+ *      bit-exact. The bitstream decode itself is not part of this library. ---- */
+typedef enum sdr_pixel_format {
+    SDR_PIX_BGR = 0,  /* u8 3-ch, what cv::VideoCapture returns */
+    SDR_PIX_NV12 = 1, /* u8 1-ch, rows * 3 / 2 rows: Y plane, then interleaved U,V at half resolution (even width and height) */
+    SDR_PIX_YUYV = 2  /* u8 2-ch: Y0 U Y1 V (even width) */
+} sdr_pixel_format;
+/* src: the picture in `format` (NV12: rows = bgr->rows * 3 / 2, 1 channel; YUYV: 2 channels); bgr: u8 3-ch output. */
+SDR_API int sdr_ingest_to_bgr(sdr_ctx* ctx, int format, const sdr_image* src, sdr_image* bgr);
+
 /* ---- whole path per frame (stereo_displayer.cpp:155-162 + pcd_write.cpp:82-130) ---- */
 typedef struct sdr_pipeline_options {
     sdr_sgbm_params sgbm;
@@ -274,6 +287,9 @@ SDR_API void sdr_pipeline_destroy(sdr_pipeline* p);
  * (valid until the next run). */
 SDR_API int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sdr_image* disp, sdr_image* points,
                              sdr_image* left_rect, sdr_cloud_view* views);
+/* Format of the SBS frames sdr_pipeline_run is handed (default SDR_PIX_BGR). With SDR_PIX_NV12 / SDR_PIX_YUYV the frames are
+ * copied to the device as they are and converted there (sdr_ingest_to_bgr) in front of the rectification. */
+SDR_API int sdr_pipeline_set_input_format(sdr_pipeline* p, int format);
 /* sdr_sgbm_set_option on the pipeline's matcher. */
 SDR_API int sdr_pipeline_set_sgbm_option(sdr_pipeline* p, const char* name, int value);
 /* Per-stage device times (ms) of the last run (CUDA events on the ctx stream); enable first. */
@@ -323,6 +339,9 @@ SDR_API int sdr_stream_create(const int* devices, int n_devices, int handles_per
 SDR_API void sdr_stream_destroy(sdr_stream* s);
 SDR_API int sdr_stream_process(sdr_stream* s, int64_t n_frames, sdr_frame_source source, sdr_frame_sink sink, sdr_cloud_sink cloud_sink,
                                void* user, sdr_stream_stats* stats);
+/* sdr_pipeline_set_input_format on every worker's pipeline (call between create and process; sources then return frames in
+ * that format and sdr_stream_process_pool reads its pool as such). */
+SDR_API int sdr_stream_set_input_format(sdr_stream* s, int format);
 /* process() over a pool of SBS frames at a constant stride, frame i of the stream = pool frame (i mod n_pool), no callback
  * into the host language (BASELINE config 4: 64 unique pairs cycled to 4096); results land in the workers' pinned
  * buffers and are dropped. mem: sdr_mem of the pool. */

@@ -206,3 +206,15 @@ def depth_coverage(points):
     n = C.c_long()
     pct = lib().orc_depth_coverage(_p(pts), pts.shape[1], pts.shape[0], C.byref(n))
     return n.value, pct
+
+
+def ingest_to_bgr(fmt, src):
+    """cv2.cvtColor(src, COLOR_YUV2BGR_NV12 (fmt 1) | COLOR_YUV2BGR_YUY2 (fmt 2)) restated."""
+    src = np.ascontiguousarray(src, np.uint8)
+    H = src.shape[0] * 2 // 3 if fmt == 1 else src.shape[0]
+    W = src.shape[1]
+    out = np.empty((H, W, 3), np.uint8)
+    rc = lib().orc_ingest_to_bgr(int(fmt), _p(src), C.c_long(src.strides[0]), W, H, _p(out), C.c_long(out.strides[0]))
+    if rc:
+        raise ValueError("ingest: bad format or odd size")
+    return out

@@ -749,3 +749,33 @@ ORC_API double orc_depth_coverage(const float* points, int W, int H, long* count
     if (count_out) *count_out = counter;
     return ((double)counter / total_pixels) * 100;
 }
+
+/* ---- frame ingest: cv::cvtColor(COLOR_YUV2BGR_NV12 / COLOR_YUV2BGR_YUY2) of OpenCV 4.13 (imgproc color_yuv: ITU-R BT.601
+ * constants, 20-bit fixed point), the conversion between a decoder / UVC camera and the BGR frame cv::VideoCapture hands the
+ * reference's loops (stereo_displayer.cpp:145-156, pcd_write.cpp:59-84). Pinned exhaustively over (Y,U,V) against cv2
+ * (tests/test_oracle_vs_cv2.py). fmt: 1 = NV12 (src rows = H*3/2, Y plane then interleaved UV), 2 = YUYV. ---- */
+static inline uint8_t orc_sat8(int v) { return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v); }
+static void orc_yuv_px(int Y, int U, int V, uint8_t* bgr) {
+    const int u = U - 128, v = V - 128;
+    const int y = (Y - 16 > 0 ? Y - 16 : 0) * 1220542;
+    bgr[0] = orc_sat8((y + (1 << 19) + 2116026 * u) >> 20);
+    bgr[1] = orc_sat8((y + (1 << 19) - 852492 * v - 409993 * u) >> 20);
+    bgr[2] = orc_sat8((y + (1 << 19) + 1673527 * v) >> 20);
+}
+ORC_API int orc_ingest_to_bgr(int fmt, const uint8_t* src, long sstep, int W, int H, uint8_t* dst, long dstep) {
+    if ((W & 1) || (fmt == 1 && (H & 1)) || (fmt != 1 && fmt != 2)) return 1;
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            int Y, U, V;
+            if (fmt == 1) {
+                Y = src[(long)y * sstep + x];
+                const uint8_t* c = src + (long)(H + y / 2) * sstep + (x & ~1);
+                U = c[0]; V = c[1];
+            } else {
+                const uint8_t* r = src + (long)y * sstep + 4 * (x >> 1);
+                Y = r[(x & 1) * 2]; U = r[1]; V = r[3];
+            }
+            orc_yuv_px(Y, U, V, dst + (long)y * dstep + 3 * x);
+        }
+    return 0;
+}

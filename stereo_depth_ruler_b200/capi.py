@@ -86,6 +86,7 @@ SYMBOLS = [
     "sdr_pipeline_set_profiling",
     "sdr_measure_distance", "sdr_depth_coverage", "sdr_cloud_save_pcd_binary", "sdr_stream_run",
     "sdr_stream_create", "sdr_stream_destroy", "sdr_stream_process", "sdr_stream_process_pool", "sdr_bind_host_to_device",
+    "sdr_ingest_to_bgr", "sdr_pipeline_set_input_format", "sdr_stream_set_input_format",
 ]
 
 _lib = None
@@ -443,6 +444,20 @@ def resize_half_area(ctx, src):
     return out
 
 
+PIX_BGR, PIX_NV12, PIX_YUYV = 0, 1, 2
+_PIX_CHANNELS = {PIX_BGR: 3, PIX_NV12: 1, PIX_YUYV: 2}
+
+
+def ingest_to_bgr(ctx, fmt, src):
+    """cv::cvtColor(src, COLOR_YUV2BGR_NV12 | COLOR_YUV2BGR_YUY2) (sdr_ingest_to_bgr): the colour conversion between a
+    hardware decoder / UVC camera and the BGR frame of stereo_displayer.cpp:145-156. src: NV12 [H*3/2][W] or YUYV [H][W][2]."""
+    H = src.shape[0] * 2 // 3 if fmt == PIX_NV12 else src.shape[0]
+    out = _empty_like_kind(src, (H, src.shape[1], 3), np.uint8, "uint8")
+    si, _ = as_image(src, _PIX_CHANNELS.get(fmt)); di, _ = as_image(out, 3)
+    ctx.check(lib().sdr_ingest_to_bgr(ctx._h, int(fmt), C.byref(si), C.byref(di)))
+    return out
+
+
 def right_matcher_params(left_params):
     """cv::ximgproc::createRightMatcher (stereo_disparity.cpp:10) as parameters."""
     r = SgbmParams()
@@ -596,9 +611,14 @@ class Pipeline:
         ctx.check(lib().sdr_pipeline_create(ctx._h, C.byref(calib), C.byref(self.opt), C.byref(self._h)))
         self.views = (CloudView * batch)()
 
+    def set_input_format(self, fmt):
+        """SBS frames arrive as PIX_BGR (default), PIX_NV12 or PIX_YUYV and are converted on the device."""
+        self.ctx.check(lib().sdr_pipeline_set_input_format(self._h, int(fmt)))
+        self.input_format = int(fmt)
+
     def run(self, sbs_frames, disp=None, points=None, left_rect=None, clouds=True):
         n = len(sbs_frames)
-        S = (Image * n)(*[as_image(f, 3)[0] for f in sbs_frames])
+        S = (Image * n)(*[as_image(f, _PIX_CHANNELS[getattr(self, "input_format", PIX_BGR)])[0] for f in sbs_frames])
         D = (Image * n)(*[as_image(d, 1)[0] for d in disp]) if disp is not None else None
         Pn = (Image * n)(*[as_image(p, 3)[0] for p in points]) if points is not None else None
         Lr = (Image * n)(*[as_image(p, 3)[0] for p in left_rect]) if left_rect is not None else None
@@ -697,8 +717,14 @@ class Stream:
         if rc != SDR_OK:
             raise SdrError(rc, "sdr_stream_create failed")
 
+    def set_input_format(self, fmt):
+        rc = lib().sdr_stream_set_input_format(self._h, int(fmt))
+        if rc != SDR_OK:
+            raise SdrError(rc, "sdr_stream_set_input_format failed")
+
     def process_pool(self, n_frames, pool, mem=None):
-        """pool: [P][H][2W][3] uint8, numpy (host / pinned) or torch cuda tensor; frame i of the stream = pool[i mod P]."""
+        """pool: [P][H][2W][3] uint8 (or [P][H*3/2][2W] NV12 / [P][H][2W][2] YUYV after set_input_format), numpy (host /
+        pinned) or torch cuda tensor; frame i of the stream = pool[i mod P]."""
         if _is_torch(pool):
             ptr, stride, step = pool.data_ptr(), pool.stride(0), pool.stride(1)
             mem = MEM_DEVICE if mem is None else mem

@@ -13,7 +13,8 @@ struct sdr_pipeline {
     sdr_rectifier* rect = nullptr;
     sdr_sgbm* sgbm = nullptr;
     sdr_cloud* cloud = nullptr;
-    DevBuf sbs, rectL, rectR, grayL, grayR, disp, points, minkey;
+    DevBuf sbs, raw, rectL, rectR, grayL, grayR, disp, points, minkey;
+    int input_format = SDR_PIX_BGR;   // what the caller's SBS frames are (sdr_pipeline_set_input_format)
     StageTimer timer;
 };
 
@@ -77,7 +78,7 @@ extern "C" void sdr_pipeline_destroy(sdr_pipeline* p) {
     if (p->rect) sdr_rectifier_destroy(p->rect);
     if (p->sgbm) sdr_sgbm_destroy(p->sgbm);
     if (p->cloud) sdr_cloud_destroy(p->cloud);
-    for (DevBuf* b : {&p->sbs, &p->rectL, &p->rectR, &p->grayL, &p->grayR, &p->disp, &p->points, &p->minkey}) b->release();
+    for (DevBuf* b : {&p->sbs, &p->raw, &p->rectL, &p->rectR, &p->grayL, &p->grayR, &p->disp, &p->points, &p->minkey}) b->release();
     p->timer.release();
     delete p;
 }
@@ -91,10 +92,15 @@ extern "C" int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sd
     const int W = p->calib.image_width, H = p->calib.image_height;
     cudaStream_t st = ctx->stream;
     int rc;
+    const int fmt = p->input_format;
+    int in_rows;
+    size_t in_row_bytes;
+    sdr_ingest_layout(fmt, 2 * W, H, &in_rows, &in_row_bytes);
     for (int i = 0; i < n; i++) {
-        if ((rc = sdr_check_image(ctx, &sbs[i], 3, 1, "sbs"))) return rc;
-        if (sbs[i].cols != 2 * W || sbs[i].rows != H)
-            return SDR_FAIL(ctx, SDR_ESIZE, "pipeline: SBS frame must be %dx%d, got %dx%d", 2 * W, H, sbs[i].cols, sbs[i].rows);
+        if ((rc = sdr_check_image(ctx, &sbs[i], fmt == SDR_PIX_BGR ? 3 : fmt == SDR_PIX_NV12 ? 1 : 2, 1, "sbs"))) return rc;
+        if (sbs[i].cols != 2 * W || sbs[i].rows != in_rows)
+            return SDR_FAIL(ctx, SDR_ESIZE, "pipeline: SBS frame must be %d cols x %d rows in this input format, got %dx%d", 2 * W, in_rows,
+                            sbs[i].cols, sbs[i].rows);
     }
     // every caller-owned output is checked before anything is queued: exactly W x H (a smaller Mat, e.g. the half-resolution
     // map of the reference's live path, would be overrun by the copies below)
@@ -106,7 +112,7 @@ extern "C" int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sd
     }
     p->timer.begin(st);
     // 1. frames to the device (used in place when they are already there at a constant stride)
-    const size_t sbs_row = (size_t)2 * W * 3, sbs_frame_c = sbs_row * H;
+    const size_t sbs_row = in_row_bytes, sbs_frame_c = sbs_row * in_rows;
     const uint8_t* S0;
     size_t sstep, sframe;
     bool in_place = sbs[0].mem == SDR_MEM_DEVICE;
@@ -117,11 +123,19 @@ extern "C" int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sd
     if (in_place) {
         S0 = (const uint8_t*)sbs[0].data; sstep = sbs[0].step_bytes;
     } else {
-        if ((rc = p->sbs.reserve(ctx, sbs_frame_c * n))) return rc;
-        if ((rc = copy_frames(ctx, true, p->sbs.as<uint8_t>(), sbs_frame_c, sbs_row, sbs, n, H))) return rc;
-        S0 = p->sbs.as<uint8_t>(); sstep = sbs_row; sframe = sbs_frame_c;
+        DevBuf& land = fmt == SDR_PIX_BGR ? p->sbs : p->raw;
+        if ((rc = land.reserve(ctx, sbs_frame_c * n))) return rc;
+        if ((rc = copy_frames(ctx, true, land.as<uint8_t>(), sbs_frame_c, sbs_row, sbs, n, in_rows))) return rc;
+        S0 = land.as<uint8_t>(); sstep = sbs_row; sframe = sbs_frame_c;
     }
     p->timer.mark(st, "h2d");
+    if (fmt != SDR_PIX_BGR) {   // decoder / camera format -> the BGR frame cv::VideoCapture would have handed out
+        const size_t bgr_row = (size_t)2 * W * 3, bgr_frame_c = bgr_row * H;
+        if ((rc = p->sbs.reserve(ctx, bgr_frame_c * n))) return rc;
+        if ((rc = sdr_launch_ingest(ctx, fmt, S0, sstep, sframe, p->sbs.as<uint8_t>(), bgr_row, bgr_frame_c, 2 * W, H, n))) return rc;
+        S0 = p->sbs.as<uint8_t>(); sstep = bgr_row; sframe = bgr_frame_c;
+        p->timer.mark(st, "ingest");
+    }
     // 2. rectify both eyes (+ gray) in one launch
     const size_t bgr_frame = (size_t)W * H * 3, gray_frame = (size_t)W * H;
     if ((rc = p->rectL.reserve(ctx, bgr_frame * n)) || (rc = p->rectR.reserve(ctx, bgr_frame * n)) ||
@@ -172,6 +186,16 @@ extern "C" int sdr_pipeline_run(sdr_pipeline* p, int n, const sdr_image* sbs, sd
     SDR_CUDA(ctx, sdr_wait(ctx));
     if ((rc = sdr_sgbm_take_sweep_error(p->sgbm))) return rc;   // a sweep of THIS run gave up on a halo: its maps are garbage
     return status;
+}
+
+extern "C" int sdr_pipeline_set_input_format(sdr_pipeline* p, int format) {
+    if (!p) return SDR_EINVAL;
+    if (format != SDR_PIX_BGR && format != SDR_PIX_NV12 && format != SDR_PIX_YUYV)
+        return SDR_FAIL(p->ctx, SDR_EINVAL, "pipeline: unknown input format %d", format);
+    if (format != SDR_PIX_BGR && ((p->calib.image_width & 1) || (format == SDR_PIX_NV12 && (p->calib.image_height & 1))))
+        return SDR_FAIL(p->ctx, SDR_EINVAL, "pipeline: this input format needs an even picture size");
+    p->input_format = format;
+    return SDR_OK;
 }
 
 extern "C" int sdr_pipeline_set_sgbm_option(sdr_pipeline* p, const char* name, int value) {

@@ -113,5 +113,9 @@ int sdr_cloud_finish(sdr_cloud* c, sdr_cloud_view* views);
 int sdr_cloud_download_frame(sdr_cloud* c, int f, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt, bool wait);
 int sdr_cloud_download_packed(sdr_cloud* c, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt, int64_t* offsets, bool wait);
 StageTimer* sdr_sgbm_timer(sdr_sgbm* m);
+// frame ingest (ingest.cu): rows / bytes per row of a cols x rows picture in pixel format fmt; batched conversion to BGR
+void sdr_ingest_layout(int fmt, int cols, int rows, int* src_rows, size_t* row_bytes);
+int sdr_launch_ingest(sdr_ctx* ctx, int fmt, const uint8_t* src, size_t sstep, size_t sframe, uint8_t* dst, size_t dstep, size_t dframe, int W,
+                      int H, int batch);
 // after a host wait on the ctx stream: SDR_ECUDA (once) if a cooperative sweep of the finished work timed out on a halo
 int sdr_sgbm_take_sweep_error(sdr_sgbm* m);

@@ -72,6 +72,7 @@ struct sdr_stream {
     sdr_calibration calib{};
     sdr_pipeline_options opt{};
     int download_clouds = 0;
+    std::atomic<int> input_format{SDR_PIX_BGR};   // applied by every worker at the start of its next job
 
     // one job at a time; workers sleep between jobs
     std::mutex mu;
@@ -133,6 +134,11 @@ void sdr_stream::worker(int di) {
         }
         const uint64_t l0 = ctx ? sdr_kernel_launches(ctx) : 0;
         int jrc = rc;
+        const int fmt = input_format.load();
+        if (jrc == SDR_OK) jrc = sdr_pipeline_set_input_format(pipe, fmt);
+        int in_rows;
+        size_t in_row_bytes;
+        sdr_ingest_layout(fmt, 2 * W, H, &in_rows, &in_row_bytes);
         while (jrc == SDR_OK && first_error.load() == SDR_OK) {
             const int64_t start = cursor.fetch_add(B);
             if (start >= n_frames) break;
@@ -150,7 +156,7 @@ void sdr_stream::worker(int di) {
             if (jrc != SDR_OK) break;
             int64_t bytes_out = (int64_t)n * W * H * 2;
             for (int k = 0; k < n; k++)
-                if (sbs[k].mem != SDR_MEM_DEVICE) h2d_bytes += (int64_t)H * 2 * W * 3;
+                if (sbs[k].mem != SDR_MEM_DEVICE) h2d_bytes += (int64_t)in_rows * (int64_t)in_row_bytes;
             if (download_clouds) {
                 jrc = sdr_pipeline_clouds_download_packed(pipe, (float*)xyz_host.p, (uint8_t*)rgb_host.p, nullptr, nullptr, offs.data());
                 if (jrc != SDR_OK) break;
@@ -267,6 +273,14 @@ extern "C" int sdr_stream_process(sdr_stream* s, int64_t n_frames, sdr_frame_sou
     return s->first_error.load();
 }
 
+extern "C" int sdr_stream_set_input_format(sdr_stream* s, int format) {
+    if (!s || (format != SDR_PIX_BGR && format != SDR_PIX_NV12 && format != SDR_PIX_YUYV)) return SDR_EINVAL;
+    const int W = s->calib.image_width, H = s->calib.image_height;
+    if (format != SDR_PIX_BGR && ((W & 1) || (format == SDR_PIX_NV12 && (H & 1)))) return SDR_EINVAL;
+    s->input_format = format;
+    return SDR_OK;
+}
+
 extern "C" int sdr_stream_run(const int* devices, int n_devices, int handles_per_device, const sdr_calibration* calib,
                               const sdr_pipeline_options* opt, int64_t n_frames, sdr_frame_source source, sdr_frame_sink sink, void* user,
                               sdr_stream_stats* stats) {
@@ -285,17 +299,22 @@ struct sdr_frame_pool {
     const uint8_t* base;
     int64_t n_pool;
     size_t frame_stride, step_bytes;
-    int rows, cols, mem;
+    int rows, cols, mem, channels;
 };
 extern "C" int sdr_frame_pool_source(void* user, int64_t index, sdr_image* sbs) {
     const sdr_frame_pool* p = (const sdr_frame_pool*)user;
     if (!p || p->n_pool <= 0) return SDR_EINVAL;
-    *sbs = sdr_image{(void*)(p->base + (size_t)(index % p->n_pool) * p->frame_stride), p->rows, p->cols, 3, 1, p->step_bytes, p->mem};
+    *sbs = sdr_image{(void*)(p->base + (size_t)(index % p->n_pool) * p->frame_stride), p->rows, p->cols, p->channels, 1, p->step_bytes, p->mem};
     return SDR_OK;
 }
 extern "C" int sdr_stream_process_pool(sdr_stream* s, int64_t n_frames, const void* pool_base, int64_t n_pool, size_t frame_stride,
                                        size_t step_bytes, int mem, sdr_stream_stats* stats) {
     if (!s || !pool_base || n_pool <= 0) return SDR_EINVAL;
-    sdr_frame_pool p{(const uint8_t*)pool_base, n_pool, frame_stride, step_bytes, s->calib.image_height, 2 * s->calib.image_width, mem};
+    const int fmt = s->input_format.load();
+    int rows;
+    size_t row_bytes;
+    sdr_ingest_layout(fmt, 2 * s->calib.image_width, s->calib.image_height, &rows, &row_bytes);
+    sdr_frame_pool p{(const uint8_t*)pool_base, n_pool, frame_stride, step_bytes, rows, 2 * s->calib.image_width, mem,
+                     fmt == SDR_PIX_BGR ? 3 : fmt == SDR_PIX_NV12 ? 1 : 2};
     return sdr_stream_process(s, n_frames, sdr_frame_pool_source, nullptr, nullptr, &p, stats);
 }

@@ -58,3 +58,19 @@ def noise_pair(W, H, seed=0, amplitude=256):
     a = rng.integers(0, amplitude, size=(H, W)).astype(np.uint8)
     b = rng.integers(0, amplitude, size=(H, W)).astype(np.uint8)
     return a, b
+
+
+def bgr_to_nv12(bgr):
+    """A BGR picture as a hardware decoder would hand it over: NV12, BT.601 limited range, 2x2 chroma average.
+    [H][W][3] -> [H * 3 / 2][W] (Y plane, then interleaved U, V). Synthetic-input helper: integer BT.601 approximation."""
+    H, W = bgr.shape[:2]
+    b = bgr[..., 0].astype(np.int32); g = bgr[..., 1].astype(np.int32); r = bgr[..., 2].astype(np.int32)
+    y = ((66 * r + 129 * g + 25 * b + 128) >> 8) + 16
+    u = ((-38 * r - 74 * g + 112 * b + 128) >> 8) + 128
+    v = ((112 * r - 94 * g - 18 * b + 128) >> 8) + 128
+    avg = lambda c: (c[0::2, 0::2] + c[0::2, 1::2] + c[1::2, 0::2] + c[1::2, 1::2] + 2) >> 2
+    out = np.empty((H * 3 // 2, W), np.uint8)
+    out[:H] = np.clip(y, 0, 255)
+    out[H:, 0::2] = np.clip(avg(u), 0, 255)
+    out[H:, 1::2] = np.clip(avg(v), 0, 255)
+    return out
