@@ -271,12 +271,14 @@ def run_ours(args):
     numa_node = capi.bind_host_to_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    B = args.batch
+    B = args.batch                                                # frames per submission (one launch of every kernel)
+    FPS = max(args.frames_per_step, B)                            # frames per step per GPU
+    FPS -= FPS % B
     c4 = args.workload == "c4"
     sgbm_opts = [kv.split("=") for kv in args.sgbm_opt]
 
     # ---- CPU legs first (rank 0): baseline timing at N=1, and the parity gate's reference maps at every N ----
-    n_pool = max(64 if c4 else args.pool, 2 * B)
+    n_pool = max(64 if c4 else args.pool, 2 * FPS)
     n_pool -= n_pool % B                                         # whole batches: consecutive frames are consecutive in memory
     frames_np = make_frames(n_pool, base=64 if c4 else 4)   # c4: 64 unique pairs cycled
     mine = [frames_np[i % n_pool] for i in sharding.frames_for_rank(n_pool * world, rank, world)]
@@ -386,7 +388,7 @@ def run_ours(args):
         ms = sharding.max_over_ranks(e0.elapsed_time(e1), dist if world > 1 else None)
         return ms, sum(sl["ctx"].kernel_launches for sl in slots) - l0, t0, t1
 
-    steps = args.steps if not c4 else max(1, -(-args.frames // (world * B)))
+    steps = args.steps if not c4 else max(1, -(-args.frames // (world * FPS)))
 
     def timed_stream(runner, pool, n_frames, warmup_frames):
         """Native runner: warm-up frames, then exactly n_frames between CUDA events; max over ranks."""
@@ -407,13 +409,13 @@ def run_ours(args):
     if args.value_runner == "native":
         # the library's own worker threads (one per handle) over the device-resident pool: no host language on the path
         rv = capi.Stream([local], NSLOT, calib, params, vox, handle_missing=True, batch=B, download_clouds=False)
-        ms, st_v, t0, t1 = timed_stream(rv, dev_pool, steps * B, max(args.warmup, NSLOT) * B)
+        ms, st_v, t0, t1 = timed_stream(rv, dev_pool, steps * FPS, max(args.warmup * FPS, NSLOT * B))
         launches = int(st_v.kernel_launches)
         rv.close()
     else:
-        ms, launches, t0, t1 = timed_slots(dev_step, steps, args.warmup)
+        ms, launches, t0, t1 = timed_slots(dev_step, steps * (FPS // B), args.warmup * (FPS // B))
     clocks = sampler.stop(t0, t1) if sampler else None
-    fps = sharding.aggregate_throughput(B * steps, world, ms)
+    fps = sharding.aggregate_throughput(FPS * steps, world, ms)
 
     # ---- per-kernel times of one step (CUDA events on the launching stream, inside the library) ----
     sg = capi.Sgbm(ctx, params)
@@ -508,9 +510,9 @@ def run_ours(args):
     # ---- e2e: pinned host frames in, disparity maps + clouds out, through the native frame-parallel runner of the C ABI
     # (worker threads in the library, one per handle; Python only starts the run) ----
     runner = capi.Stream([local], NSLOT, calib, params, vox, handle_missing=True, batch=B, download_clouds=True)
-    ms_e, st_e, _, _ = timed_stream(runner, host_np, steps * B, max(args.warmup, NSLOT) * B)
+    ms_e, st_e, _, _ = timed_stream(runner, host_np, steps * FPS, max(args.warmup * FPS, NSLOT * B))
     runner.close()
-    fps_e = sharding.aggregate_throughput(B * steps, world, ms_e)
+    fps_e = sharding.aggregate_throughput(FPS * steps, world, ms_e)
 
     # ---- the same end-to-end leg fed with NV12 frames, the format a hardware decoder delivers (sdr_stream_set_input_format):
     # half the host->device bytes, the colour conversion runs on the device in front of the rectification ----
@@ -520,9 +522,9 @@ def run_ours(args):
         nv_pool = torch.from_numpy(np.stack([synth.bgr_to_nv12(f) for f in mine])).pin_memory()
         runner = capi.Stream([local], NSLOT, calib, params, vox, handle_missing=True, batch=B, download_clouds=True)
         runner.set_input_format(capi.PIX_NV12)
-        ms_n, st_n, _, _ = timed_stream(runner, nv_pool.numpy(), steps * B, max(args.warmup, NSLOT) * B)
+        ms_n, st_n, _, _ = timed_stream(runner, nv_pool.numpy(), steps * FPS, max(args.warmup * FPS, NSLOT * B))
         runner.close()
-        e2e_nv12 = {"value": sharding.aggregate_throughput(B * steps, world, ms_n), "unit": "frames/s", "ms_per_step": ms_n / steps,
+        e2e_nv12 = {"value": sharding.aggregate_throughput(FPS * steps, world, ms_n), "unit": "frames/s", "ms_per_step": ms_n / steps,
                     "h2d_bytes_per_step": int(st_n.h2d_bytes // steps), "d2h_bytes_per_step": int(st_n.d2h_bytes // steps),
                     "input": "NV12 SBS frames in pinned host memory (sdr_ingest_to_bgr on the device); not the headline e2e: the "
                              "reference arm starts from BGR frames"}
@@ -552,9 +554,9 @@ def run_ours(args):
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s16",
             "data": "synthetic", "mpix_disp_per_s": fps * MPIX_DISP_PER_FRAME,
             "config": base_config(args.workload),
-            "run": {"frames_per_step_per_gpu": B, "frame_pool": n_pool, "frames_timed_per_gpu": B * steps,
+            "run": {"frames_per_step_per_gpu": FPS, "frames_per_submission": B, "frame_pool": n_pool, "frames_timed_per_gpu": FPS * steps,
                     "l2": "inputs larger than L2 (frame pool %d MB, a different batch each step; volumes %d MB per step)" % (
-                        n_pool * H * 2 * W * 3 >> 20, 2 * vol * B >> 20),
+                        n_pool * H * 2 * W * 3 >> 20, 2 * vol * FPS >> 20),
                     "sharding": "frame i -> rank i mod N, no collective", "numa_node": numa_node, "sgbm_options": dict((k, int(v)) for k, v in sgbm_opts),
                     "concurrency": "%d pipeline handles (own stream + host thread each) per GPU alternate batches, so the copies and the "
                                    "ALU-bound kernels of one batch overlap the HBM-bound kernels of another; value: %s; e2e: native worker "
@@ -588,7 +590,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=8, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=8, help="frames per submission (one launch of every kernel)")
+    ap.add_argument("--frames-per-step", type=int, default=16, help="frames per step per GPU (a multiple of --batch): 20 steps time 320 frames")
     ap.add_argument("--pool", type=int, default=32, help="distinct frames resident per GPU (pool > L2)")
     ap.add_argument("--slots", type=int, default=4, help="pipeline handles (streams + host threads) per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
