@@ -727,10 +727,15 @@ __host__ __device__ inline CfLayout cf_layout(int D, int SW2, int SH2, int COLS)
 // routed through this function ptxas spills 20 bytes there and the kernel loses 5 %): CF_PROD threads compute the C row tiles of one COLS-column
 // strip of frame b, one image row after the other, into the ring `ringC` (CF_NST slots, hand-shake fullC / emptyC with the
 // readers) and write every finished tile to the C volume with one TMA bulk store.
+// The rows a producer walks: output rows [y0, y0 + nrows) of the image, input rows clamped to [ymin, ymax] (a stripe of
+// MODE_SGBM_3WAY replicates its own first row above it but reads on below its last row, as k_cost does), C rows from crow0.
+struct CfRows {
+    int y0, nrows, ymin, ymax, crow0;
+};
 template <int NP, int SW2, int CF_PROD, int COLS>
 __device__ __forceinline__ void cost_producer(const Geom& g, const int4* __restrict__ PL, const uint8_t* __restrict__ PR, int16_t* __restrict__ C,
                                               int b, int x0, uint8_t* cfsm, const CfLayout& lay, uint64_t (&fullC)[CF_NST], uint64_t (&emptyC)[CF_NST],
-                                              uint64_t (&fullIn)[2], uint32_t tile_bytes) {
+                                              uint64_t (&fullIn)[2], uint32_t tile_bytes, const CfRows rw) {
     int16_t* ringC = (int16_t*)(cfsm + lay.off_ring_c);
     constexpr int D = 16 * NP, DQ = D / 8;
     constexpr int XG = CF_PROD / DQ;            // producer column groups
@@ -763,9 +768,9 @@ __device__ __forceinline__ void cost_producer(const Geom& g, const int4* __restr
         tab[k] = (uint32_t)o0 | ((uint32_t)ix << 16) | ((p0 & 15) == 12 ? 0x80000000u : 0u);
         V[k][0] = V[k][1] = V[k][2] = V[k][3] = 0;
     }
-    const int NV = g.H + 2 * g.SH2;
-    auto issue_in = [&](int i) {   // one thread: stage virtual row i (image row clamp(i - SH2))
-        const int rc = min(max(i - g.SH2, 0), g.H - 1);
+    const int NV = rw.nrows + 2 * g.SH2;
+    auto issue_in = [&](int i) {   // one thread: stage virtual row i (image row clamp(y0 + i - SH2))
+        const int rc = min(max(rw.y0 + i - g.SH2, rw.ymin), rw.ymax);
         uint8_t* st = stage + (size_t)(i & 1) * lay.stage_bytes;
         mbar_expect_tx(&fullIn[i & 1], pl_bytes + pr_bytes);
         bulk_g2s(st, PL + ((size_t)b * g.H + rc) * g.W + lo + g.minX1, pl_bytes, &fullIn[i & 1]);
@@ -844,7 +849,7 @@ __device__ __forceinline__ void cost_producer(const Geom& g, const int4* __restr
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
             named_bar_sync(3, CF_PROD);   // tile complete (and every read of Vs is done)
             if (tid == 0) {
-                bulk_s2g(C + (((size_t)b * g.crows + y) * g.W1 + x0) * D, ct, tile_bytes);
+                bulk_s2g(C + (((size_t)b * g.crows + rw.crow0 + y) * g.W1 + x0) * D, ct, tile_bytes);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 mbar_arrive(&fullC[cst]);
             }
@@ -1113,6 +1118,91 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             if (right_edge) halo_complete<NW>(Hptr(s, cur, 1), (uint32_t)(t + 1), err, hq);
         }
         named_bar_sync(1, CF_CONS);   // the row's diagonal states are in shared memory
+        if (++stg == CF_NST) { stg = 0; ring_phase ^= 1; }
+    }
+}
+
+// ---- fused cost + vertical path of MODE_SGBM_3WAY -------------------------------------------------------------------
+// OpenCV's 3-way mode (the reference's own matcher, stereo_disparity.cpp:5-6, pcd_write.cpp:102-108) runs one top-down path
+// per stripe besides the two horizontal ones. CTA = one COLS-column strip of one stripe of one frame: the producer warps are
+// cost_producer (as in k_cost_path_v3), the consumer warps (8 lanes per column) run the path step on the C row tile out of the
+// shared-memory ring and write S. No diagonal paths, hence no halos between strips, no consumer barrier and an ordinary launch;
+// C crosses HBM once (written for the horizontal kernels) instead of written and read back by k_path_v.
+__host__ __device__ inline CfLayout cf_layout_v1(int D, int SW2, int SH2, int COLS) {
+    CfLayout L;
+    L.cw = COLS + 2 * SW2;
+    L.nchunks_max = (L.cw + D + 32) / 16 + 1;
+    L.stage_bytes = ((L.cw * 16 + L.nchunks_max * PR_CHUNK) + 127) & ~127;
+    size_t o = 0;
+    L.off_ma = 0;
+    L.off_ring_c = o;  o += (size_t)CF_NST * COLS * D * 2;
+    o = (o + 127) & ~(size_t)127;
+    L.off_stage = o;   o += (size_t)2 * L.stage_bytes;
+    L.off_ring8 = o;   o += (size_t)(2 * SH2 + 1) * L.cw * D;
+    o = (o + 15) & ~(size_t)15;
+    L.off_vs = o;      o += (size_t)L.cw * D * 2;
+    L.total = o;
+    return L;
+}
+
+// CM: columns per consumer lane group (the consumer's share of this kernel's work is small: one path step per column and
+// row against a BT item per column and octet, so fewer, busier consumer threads leave the SM to more producer warps).
+template <int NP, int SW2, int CF_PROD, int COLS, int CM>
+__global__ void __launch_bounds__(CF_PROD + COLS * 8 / CM, NP <= 8 ? (CF_PROD + COLS * 8 / CM <= 256 ? 4 : CF_PROD + COLS * 8 / CM <= 320 ? 3 : 2) : 1)
+k_cost_path_v1(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ PR, int16_t* __restrict__ C, int16_t* __restrict__ S) {
+    constexpr int G = 8, D = 16 * NP;
+    constexpr int CF_CONS = COLS * G / CM, CG = COLS / CM;   // consumer threads; column groups (columns gidx + h * CG, h < CM)
+    static_assert(COLS % CM == 0 && CF_CONS % 32 == 0, "consumer tiling");
+    extern __shared__ __align__(128) uint8_t cfsm[];
+    __shared__ __align__(8) uint64_t fullC[CF_NST], emptyC[CF_NST], fullIn[2];
+    const CfLayout lay = cf_layout_v1(D, SW2, g.SH2, COLS);
+    const int x0 = blockIdx.x * COLS, b = blockIdx.z;
+    const Seg sg = g.seg[blockIdx.y];
+    const CfRows rw{sg.src_start, sg.src_end - sg.src_start, sg.src_start, g.H - 1, sg.crow0};
+    for (int i = threadIdx.x; i < (int)((lay.off_vs - lay.off_ring8) / 4); i += blockDim.x) ((uint32_t*)(cfsm + lay.off_ring8))[i] = 0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < CF_NST; i++) { mbar_init(&fullC[i], 1); mbar_init(&emptyC[i], CF_CONS / 32); }
+        mbar_init(&fullIn[0], 1);
+        mbar_init(&fullIn[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t tile_bytes = (uint32_t)(min(COLS, g.W1 - x0) * D * 2);
+    if (threadIdx.x < CF_PROD) {
+        cost_producer<NP, SW2, CF_PROD, COLS>(g, PL, PR, C, b, x0, cfsm, lay, fullC, emptyC, fullIn, tile_bytes, rw);
+        return;
+    }
+    const int ct = threadIdx.x - CF_PROD;
+    const int gidx = ct / G, lg = ct & (G - 1);
+    const uint32_t P1x2 = pack16(g.P1, g.P1), P2x2 = pack16(g.P2, g.P2);
+    const int pad = 32767 - g.P1;
+    const uint32_t PADx2 = pack16(pad, pad);
+    const size_t lane_off = (size_t)lg * 2 * NP;
+    const int16_t* ringC = (const int16_t*)(cfsm + lay.off_ring_c);
+    int16_t* Sb = S + (size_t)b * g.H * g.W1 * D + lane_off;
+    const size_t rowstride = (size_t)g.W1 * D;
+    uint32_t Pv[CM][NP], c[CM][NP], mv[CM];
+#pragma unroll
+    for (int h = 0; h < CM; h++) {
+        mv[h] = 0;
+#pragma unroll
+        for (int k = 0; k < NP; k++) Pv[h][k] = 0;
+    }
+    int stg = 0;
+    uint32_t ring_phase = 0;
+    for (int t = 0; t < rw.nrows; t++) {
+        mbar_wait(&fullC[stg], ring_phase);
+#pragma unroll
+        for (int h = 0; h < CM; h++) load_regs<NP>(ringC + ((size_t)stg * COLS + gidx + h * CG) * D + lane_off, c[h]);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&emptyC[stg]);   // this warp holds its C values in registers
+        const int y = rw.y0 + t;
+#pragma unroll
+        for (int h = 0; h < CM; h++) {
+            sgm_step<NP, G>(Pv[h], mv[h], c[h], P1x2, P2x2, PADx2, lg);
+            const int x = x0 + gidx + h * CG;
+            if (x < g.W1 && y >= sg.dst_start) store_regs<NP>(Sb + (size_t)y * rowstride + (size_t)x * D, Pv[h]);
+        }
         if (++stg == CF_NST) { stg = 0; ring_phase ^= 1; }
     }
 }
@@ -1526,6 +1616,7 @@ struct SgbmTune {
     int h_lanes = 0;        // lanes per row chain in k_path_hh: 8 / 16 / 32, 0 = by the number of rows in flight
     int h_ws = 1;           // few rows in flight: chain warps + tail warps (k_path_hh_ws) instead of k_path_hh with 16 / 32 lanes
     int h_k = 0, h_stages = 0, h_warps = 0, hb_threads = 0, hb_ring = -1, hh_threads = 0;
+    int v1_cm = 0;          // columns per consumer lane group of the fused cost + vertical path kernel of MODE_SGBM_3WAY: 1 / 2 / 4
 };
 
 // ---- dispatch over (NP, G): D = 2*G*NP ----------------------------------------------------
@@ -1720,6 +1811,34 @@ int launch_cost_path_v3(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int bat
     }
     SDR_CUDA(ctx, cudaMemcpyAsync(sc.host_err.p, sc.err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     return SDR_OK;
+}
+
+// Fused cost + vertical path of MODE_SGBM_3WAY. Returns SDR_OK, an error, or -1 when the configuration is not covered.
+template <int NP, int SW2, int CF_PROD, int COLS, int CM>
+int launch_cost_path_v1(sdr_ctx* ctx, const Geom& g, int batch, const int4* PL, const uint8_t* PR, int16_t* C, int16_t* S) {
+    auto kern = k_cost_path_v1<NP, SW2, CF_PROD, COLS, CM>;
+    const CfLayout lay = cf_layout_v1(g.D, SW2, g.SH2, COLS);
+    if (lay.total > ctx->smem_optin) return -1;
+    SDR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+    kern<<<dim3(div_up(g.W1, COLS), g.nseg, batch), CF_PROD + COLS * 8 / CM, lay.total, ctx->stream>>>(g, PL, PR, C, S);
+    SDR_LAUNCHED(ctx);
+    return SDR_OK;
+}
+int launch_cost_path_3way(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, const int4* PL, const uint8_t* PR, int16_t* C, int16_t* S) {
+    if (g.SW2 != g.SH2 || g.D % 16) return -1;
+    const int np = g.D / 16;
+    // columns per consumer lane group, measured on B200 (1280x720 batch 8, D = 80 / 128: 1.37 / 1.62 ms with 1, 1.05 / 1.49 ms
+    // with 4; 4K x 256: 5.41 / 5.07 / 5.19 ms with 1 / 2 / 4 -- at NP = 16 four columns of state cost too many registers)
+    const int cm = tn.v1_cm == 1 || tn.v1_cm == 2 || tn.v1_cm == 4 ? tn.v1_cm : (np > 8 ? 2 : 4);
+#define V1_CASE(NPV, SWV, PRODV, COLSV)                                                                        \
+    if (np == NPV && g.SW2 == SWV)                                                                              \
+        return cm == 1   ? launch_cost_path_v1<NPV, SWV, PRODV, COLSV, 1>(ctx, g, batch, PL, PR, C, S)          \
+               : cm == 2 ? launch_cost_path_v1<NPV, SWV, PRODV, COLSV, 2>(ctx, g, batch, PL, PR, C, S)          \
+                         : launch_cost_path_v1<NPV, SWV, PRODV, COLSV, 4>(ctx, g, batch, PL, PR, C, S);
+    V1_CASE(4, 1, 128, 32) V1_CASE(4, 2, 128, 32) V1_CASE(5, 1, 160, 32) V1_CASE(5, 2, 160, 32)
+    V1_CASE(8, 1, 128, 32) V1_CASE(8, 2, 128, 32) V1_CASE(16, 1, 256, 32) V1_CASE(16, 2, 256, 32)
+#undef V1_CASE
+    return -1;
 }
 
 int launch_cost_path_fused(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, const int4* PL, const uint8_t* PR, int16_t* C, int16_t* S,
@@ -1982,6 +2101,15 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
                 m->timer.mark(st, "cost_path_v_fused");
             }
         }
+        bool v_done = false;   // MODE_SGBM_3WAY: the vertical path ran inside the cost kernel
+        if (m->p.mode == SDR_MODE_SGBM_3WAY && m->tune.cost_fusion) {
+            rc = launch_cost_path_3way(ctx, m->tune, g, batch, m->PL.as<int4>(), m->PR.as<uint8_t>(), m->C.as<int16_t>(), S);
+            if (rc > 0) return rc;
+            if (rc == SDR_OK) {
+                cost_done = v_done = true;
+                m->timer.mark(st, "cost_path_v1_fused");
+            }
+        }
         if (!cost_done) {
             const int n = 2 * g.SH2 + 1, DQ = g.D / 8;
             const int nthr = (256 / DQ) * DQ, XG = nthr / DQ;
@@ -2007,9 +2135,11 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
         }
         // direction list: {dirx, diry}; the first one initialises S
         if (m->p.mode == SDR_MODE_SGBM_3WAY) {
-            NP_SWITCH(np, rc = launch_path_v<NPc>(ctx, g, batch, C, S, 0, +1, 0));
-            if (rc) return rc;
-            m->timer.mark(st, "path_v");
+            if (!v_done) {
+                NP_SWITCH(np, rc = launch_path_v<NPc>(ctx, g, batch, C, S, 0, +1, 0));
+                if (rc) return rc;
+                m->timer.mark(st, "path_v");
+            }
         } else {
             const int npass = m->p.mode == SDR_MODE_HH ? 2 : 1;
             bool fused = m->tune.fused_sweep != 0;
@@ -2219,7 +2349,7 @@ extern "C" int sdr_sgbm_set_option(sdr_sgbm* m, const char* name, int value) {
         {"wave", &t.wave}, {"fused_sweep", &t.fused_sweep}, {"cost_fusion", &t.cost_fusion}, {"path_hh", &t.path_hh}, {"shared_device", &t.shared_device},
         {"cf_cols", &t.cf_cols}, {"cf_prod", &t.cf_prod}, {"cf_fpl", &t.cf_fpl}, {"v3_stages", &t.v3_stages}, {"h_legacy", &t.h_legacy}, {"h_lanes", &t.h_lanes}, {"h_ws", &t.h_ws},
         {"h_k", &t.h_k}, {"h_stages", &t.h_stages}, {"h_warps", &t.h_warps}, {"hb_threads", &t.hb_threads}, {"hb_ring", &t.hb_ring},
-        {"hh_threads", &t.hh_threads}};
+        {"hh_threads", &t.hh_threads}, {"v1_cm", &t.v1_cm}};
     for (const auto& e : tab)
         if (!strcmp(e.n, name)) { *e.p = value; return SDR_OK; }
     return SDR_FAIL(m->ctx, SDR_EINVAL, "sdr_sgbm_set_option: unknown option '%s'", name);

@@ -85,7 +85,7 @@ k_wave_fwd(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ PR, 
     if (threadIdx.x < WV_PROD) {
         // =============================== producer: cost rows ===============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
-        cost_producer<NP, SW2, WV_PROD, COLS>(g, PL, PR, C, b, x0, cfsm, lay, fullC, emptyC, fullIn, tile_bytes);
+        cost_producer<NP, SW2, WV_PROD, COLS>(g, PL, PR, C, b, x0, cfsm, lay, fullC, emptyC, fullIn, tile_bytes, CfRows{0, g.H, 0, g.H - 1, 0});
         return;
     }
     if (threadIdx.x >= WV_PROD + WV_CONS) {

@@ -189,6 +189,40 @@ def test_fused_cost_sweep_kernel(ctx, orc, W, H, D, bs, mode):
         assert np.array_equal(outs[True][1], Sp)
 
 
+FUSED_3WAY = [(300, 70, 80, 5, 1), (333, 64, 128, 5, 2), (197, 50, 64, 3, 4), (161, 9, 80, 3, 0), (420, 38, 256, 5, 0), (229, 3, 64, 5, 2),
+              (165, 61, 128, 3, 1)]
+
+
+@pytest.mark.parametrize("W,H,D,bs,cm", FUSED_3WAY)
+def test_fused_cost_vertical_kernel_3way(ctx, orc, W, H, D, bs, cm):
+    """MODE_SGBM_3WAY (the reference's own mode): cost volume + the top-down path of every stripe in one kernel
+    (k_cost_path_v1; D = 64 / 80 / 128 / 256, blockSize 3 / 5, 1 / 2 / 4 columns per consumer group, ragged strips, stripes
+    shorter than the box window): bit-exact against the oracle, C and S volumes identical to k_cost + k_path_v."""
+    from stereo_depth_ruler_b200 import capi, synth
+    args = (0, D, bs, 8 * bs * bs, 32 * bs * bs, 1, 63, 12, 50, 2, 2)
+    B = 2
+    pairs = [synth.stereo_pair(W, H, D, 40 + s) for s in range(B)]
+    po = orc.make_params(*args)
+    refs = [orc.sgbm_compute(l, r, po) for l, r in pairs]
+    outs = {}
+    for fused in (True, False):
+        m = capi.Sgbm(ctx, capi.make_params(*args))
+        m.set_option("path_hh", 0)
+        m.set_option("cost_fusion", int(fused))
+        m.set_option("v1_cm", cm)
+        m.set_profiling(True)
+        got = m.compute_batch(np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs]), np.empty((B, H, W), np.int16))
+        names = [k for k, _ in m.stage_times()]
+        assert ("cost_path_v1_fused" in names) == fused and ("path_v" in names) == (not fused), names
+        for i in range(B):
+            assert np.array_equal(got[i], refs[i]), (fused, i)
+        m.compute(*pairs[0])
+        crows = sum(e - s0 for s0, _, e in capi.stripe_rows(capi.make_params(*args), W, H))
+        outs[fused] = (m.debug_read(0, (crows, W - D, D)).copy(), m.debug_read(1, (H, W - D, D)).copy())
+        m.close()
+    assert np.array_equal(outs[True][0], outs[False][0]) and np.array_equal(outs[True][1], outs[False][1])
+
+
 @pytest.mark.parametrize("W,H,args", [(300, 41, (0, 128, 5, 600, 2400, 1, 63, 12, 50, 2, 0)), (203, 33, (0, 64, 3, 72, 288, 1, 63, 12, 0, 0, 1)),
                                       (177, 50, (0, 80, 5, 600, 2400, 1, 63, 12, 200, 2, 2)), (97, 9, (-16, 48, 5, 600, 2400, 2, 63, 5, 0, 0, 0)),
                                       (67, 3, (0, 64, 5, 600, 2400, 1, 63, 12, 0, 0, 2)), (68, 5, (0, 64, 5, 600, 2400, 1, 63, 12, 0, 0, 0))])
