@@ -537,27 +537,27 @@ __device__ __forceinline__ void halo_complete(const unsigned long long* p, uint3
     }
 }
 
-template <int NP, int MINB, bool ACC>
-__global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int diry, int b0,
+template <int NP, int MINB, bool ACC, int COLS>
+__global__ void __launch_bounds__(COLS * 8, MINB) k_path_v3(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int diry, int b0,
                                                        unsigned long long* halo, int* err, int V3_STAGES) {
     constexpr int G = 8, NW = NP + 1;   // halo words per lane: NP state registers + the path minimum
     extern __shared__ __align__(16) int16_t v3sm[];
     const int D = g.D;
     int16_t* Xa = v3sm;                                     // [2][COLS+2][D]  state of the "from (x-1)" diagonal, slot = column+1
-    int16_t* Xb = v3sm + 2 * (V3_COLS + 2) * D;             // [2][COLS+2][D]  state of the "from (x+1)" diagonal
-    uint32_t* Ma = (uint32_t*)(v3sm + 4 * (V3_COLS + 2) * D);   // [2][COLS+2] path minima of Xa
-    uint32_t* Mb = Ma + 2 * (V3_COLS + 2);
+    int16_t* Xb = v3sm + 2 * (COLS + 2) * D;             // [2][COLS+2][D]  state of the "from (x+1)" diagonal
+    uint32_t* Ma = (uint32_t*)(v3sm + 4 * (COLS + 2) * D);   // [2][COLS+2] path minima of Xa
+    uint32_t* Mb = Ma + 2 * (COLS + 2);
     // ring of C (and, when accumulating, S) row tiles filled by TMA bulk copies V3_STAGES rows ahead: the strip's 32
     // columns of one row are one contiguous 32*D*2-byte run in global memory
-    int16_t* ringC = (int16_t*)(Mb + 2 * (V3_COLS + 2));        // [STAGES][COLS][D]
-    int16_t* ringS = ringC + (size_t)V3_STAGES * V3_COLS * D;   // [STAGES][COLS][D] (ACC only)
+    int16_t* ringC = (int16_t*)(Mb + 2 * (COLS + 2));        // [STAGES][COLS][D]
+    int16_t* ringS = ringC + (size_t)V3_STAGES * COLS * D;   // [STAGES][COLS][D] (ACC only)
     __shared__ __align__(8) uint64_t full[V3_STAGES_MAX];
     const int s = blockIdx.x, nstrips = gridDim.x, f = blockIdx.y, b = b0 + f;
     const int gidx = threadIdx.x / G, lg = threadIdx.x & (G - 1);
-    const int x = s * V3_COLS + gidx;
+    const int x = s * COLS + gidx;
     const bool active = x < g.W1;
     const int xl = min(x, g.W1 - 1);
-    for (int i = threadIdx.x; i < (4 * (V3_COLS + 2) * D) / 2 + 4 * (V3_COLS + 2); i += blockDim.x) ((uint32_t*)v3sm)[i] = 0;
+    for (int i = threadIdx.x; i < (4 * (COLS + 2) * D) / 2 + 4 * (COLS + 2); i += blockDim.x) ((uint32_t*)v3sm)[i] = 0;
     __syncthreads();
     const uint32_t P1x2 = pack16(g.P1, g.P1), P2x2 = pack16(g.P2, g.P2);
     const int pad = 32767 - g.P1;
@@ -570,16 +570,16 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
     };
     int16_t* Sb = S + (size_t)b * g.H * g.W1 * D + (size_t)xl * D + lane_off;
     const size_t rowstride = (size_t)g.W1 * D;
-    const int x0 = s * V3_COLS;
-    const uint32_t tile_bytes = (uint32_t)(min(V3_COLS, g.W1 - x0) * D * 2);
+    const int x0 = s * COLS;
+    const uint32_t tile_bytes = (uint32_t)(min(COLS, g.W1 - x0) * D * 2);
     const int16_t* Ctile = C + (size_t)b * g.crows * g.W1 * D + (size_t)x0 * D;    // + row * rowstride
     const int16_t* Stile = S + (size_t)b * g.H * g.W1 * D + (size_t)x0 * D;
     const int ystart = diry > 0 ? 0 : g.H - 1;
     auto issue = [&](int t, int st) {   // one thread: stage row t of the sweep into ring slot st (= t mod V3_STAGES)
         const int yy = ystart + t * diry;
         mbar_expect_tx(&full[st], ACC ? 2 * tile_bytes : tile_bytes);
-        bulk_g2s(ringC + (size_t)st * V3_COLS * D, Ctile + (size_t)yy * rowstride, tile_bytes, &full[st]);
-        if (ACC) bulk_g2s(ringS + (size_t)st * V3_COLS * D, Stile + (size_t)yy * rowstride, tile_bytes, &full[st]);
+        bulk_g2s(ringC + (size_t)st * COLS * D, Ctile + (size_t)yy * rowstride, tile_bytes, &full[st]);
+        if (ACC) bulk_g2s(ringS + (size_t)st * COLS * D, Stile + (size_t)yy * rowstride, tile_bytes, &full[st]);
     };
     if (threadIdx.x == 0) {
         for (int i = 0; i < V3_STAGES; i++) mbar_init(&full[i], 1);
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
     __syncthreads();
     if (threadIdx.x == 0)
         for (int i = 0; i < V3_STAGES && i < g.H; i++) issue(i, i);
-    const bool left_edge = gidx == 0 && s > 0, right_edge = gidx == V3_COLS - 1 && s + 1 < nstrips;
+    const bool left_edge = gidx == 0 && s > 0, right_edge = gidx == COLS - 1 && s + 1 < nstrips;
     uint32_t Pv[NP], pa[NP], pb[NP], c[NP], so[ACC ? NP : 1], acc[NP];
     uint32_t mv = 0, ma = 0, mb = 0;
     unsigned long long hq[NW];   // prefetched halo of the next row (edge groups only)
@@ -602,24 +602,24 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
     for (int t = 0; t < g.H; t++) {
         const int cur = t & 1, prv = cur ^ 1;
         mbar_wait(&full[stg], ring_phase);
-        load_regs<NP>(ringC + ((size_t)stg * V3_COLS + gidx) * D + lane_off, c);
-        if constexpr (ACC) load_regs<NP>(ringS + ((size_t)stg * V3_COLS + gidx) * D + lane_off, so);
+        load_regs<NP>(ringC + ((size_t)stg * COLS + gidx) * D + lane_off, c);
+        if constexpr (ACC) load_regs<NP>(ringS + ((size_t)stg * COLS + gidx) * D + lane_off, so);
         // previous-row diagonal states: neighbouring column through shared memory, across strips from the prefetched halo
         if (left_edge && t > 0) {
 #pragma unroll
             for (int k = 0; k < NP; k++) pa[k] = (uint32_t)hq[k];
             ma = (uint32_t)hq[NP];
         } else {
-            load_col_sm<NP>(Xa + ((size_t)prv * (V3_COLS + 2) + gidx) * D, lg, pa);
-            ma = Ma[prv * (V3_COLS + 2) + gidx];
+            load_col_sm<NP>(Xa + ((size_t)prv * (COLS + 2) + gidx) * D, lg, pa);
+            ma = Ma[prv * (COLS + 2) + gidx];
         }
         if (right_edge && t > 0) {
 #pragma unroll
             for (int k = 0; k < NP; k++) pb[k] = (uint32_t)hq[k];
             mb = (uint32_t)hq[NP];
         } else {
-            load_col_sm<NP>(Xb + ((size_t)prv * (V3_COLS + 2) + gidx + 2) * D, lg, pb);
-            mb = Mb[prv * (V3_COLS + 2) + gidx + 2];
+            load_col_sm<NP>(Xb + ((size_t)prv * (COLS + 2) + gidx + 2) * D, lg, pb);
+            mb = Mb[prv * (COLS + 2) + gidx + 2];
         }
         __syncwarp();
         sgm_step<NP, G>(pa, ma, c, P1x2, P2x2, PADx2, lg);
@@ -634,8 +634,8 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
             for (int k = 0; k < NP; k++) halo_put(hp + k, pa[k], (uint32_t)(t + 1));
             halo_put(hp + NP, ma, (uint32_t)(t + 1));
         }
-        store_col_sm<NP>(Xa + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D, lg, pa);
-        if (lg == 0) Ma[cur * (V3_COLS + 2) + gidx + 1] = ma;
+        store_col_sm<NP>(Xa + ((size_t)cur * (COLS + 2) + gidx + 1) * D, lg, pa);
+        if (lg == 0) Ma[cur * (COLS + 2) + gidx + 1] = ma;
         sgm_step<NP, G>(pb, mb, c, P1x2, P2x2, PADx2, lg);
         if (!active) {
 #pragma unroll
@@ -648,8 +648,8 @@ __global__ void __launch_bounds__(256, MINB) k_path_v3(Geom g, const int16_t* __
             for (int k = 0; k < NP; k++) halo_put(hp + k, pb[k], (uint32_t)(t + 1));
             halo_put(hp + NP, mb, (uint32_t)(t + 1));
         }
-        store_col_sm<NP>(Xb + ((size_t)cur * (V3_COLS + 2) + gidx + 1) * D, lg, pb);
-        if (lg == 0) Mb[cur * (V3_COLS + 2) + gidx + 1] = mb;
+        store_col_sm<NP>(Xb + ((size_t)cur * (COLS + 2) + gidx + 1) * D, lg, pb);
+        if (lg == 0) Mb[cur * (COLS + 2) + gidx + 1] = mb;
         // request the neighbour's state of THIS row now (it publishes early in its row); it is consumed next row, so the
         // L2 round trip overlaps the vertical path below
         if (t + 1 < g.H) {
@@ -1616,6 +1616,7 @@ struct SgbmTune {
     int h_lanes = 0;        // lanes per row chain in k_path_hh: 8 / 16 / 32, 0 = by the number of rows in flight
     int h_ws = 1;           // few rows in flight: chain warps + tail warps (k_path_hh_ws) instead of k_path_hh with 16 / 32 lanes
     int h_k = 0, h_stages = 0, h_warps = 0, hb_threads = 0, hb_ring = -1, hh_threads = 0;
+    int v3_cols = 0;        // strip width of the sweep kernel k_path_v3: 16 / 32 (0 = by D and the number of strips in flight)
     int v1_cm = 0;          // columns per consumer lane group of the fused cost + vertical path kernel of MODE_SGBM_3WAY: 1 / 2 / 4
 };
 
@@ -1730,20 +1731,20 @@ struct V3Scratch {
 #include "sgbm_wave.inl"
 
 // Returns SDR_OK, an error, or -1 when the cooperative grid cannot be co-resident (caller falls back).
-template <int NP>
-int launch_path_v3(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, const int16_t* C, int16_t* S, int diry, int acc, V3Scratch& sc) {
+template <int NP, int COLS>
+int launch_path_v3c(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, const int16_t* C, int16_t* S, int diry, int acc, V3Scratch& sc) {
     constexpr int MINB = NP <= 8 ? 2 : 1;
-    auto kern = acc ? k_path_v3<NP, MINB, true> : k_path_v3<NP, MINB, false>;
-    const int nstrips = div_up(g.W1, V3_COLS);
+    auto kern = acc ? k_path_v3<NP, MINB, true, COLS> : k_path_v3<NP, MINB, false, COLS>;
+    const int nstrips = div_up(g.W1, COLS);
     const int env_stages = tn.v3_stages;   // tuning knob
     int nst = acc ? 3 : V3_STAGES_DEFAULT;
     if (env_stages >= 2 && env_stages <= V3_STAGES_MAX) nst = acc ? std::min(env_stages, 3) : env_stages;
-    const size_t smem = (size_t)4 * (V3_COLS + 2) * g.D * sizeof(int16_t) + (size_t)4 * (V3_COLS + 2) * sizeof(uint32_t) +
-                        (size_t)(acc ? 2 * nst : nst) * V3_COLS * g.D * sizeof(int16_t);
+    const size_t smem = (size_t)4 * (COLS + 2) * g.D * sizeof(int16_t) + (size_t)4 * (COLS + 2) * sizeof(uint32_t) +
+                        (size_t)(acc ? 2 * nst : nst) * COLS * g.D * sizeof(int16_t);
     if (smem > ctx->smem_optin) return -1;
     SDR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    SDR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    SDR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, COLS * 8, smem));
     const int cap = per_sm * ctx->sm_count;
     if (cap < nstrips) return -1;
     const int fpl = std::min(batch, cap / nstrips);
@@ -1763,11 +1764,27 @@ int launch_path_v3(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, c
         unsigned long long* halo = sc.halo.as<unsigned long long>();
         int* err = sc.err.as<int>();
         void* args[] = {(void*)&gg, (void*)&C, (void*)&S, (void*)&diry, (void*)&b0, (void*)&halo, (void*)&err, (void*)&nst};
-        SDR_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3(nstrips, F, 1), dim3(256, 1, 1), args, smem, ctx->stream));
+        SDR_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3(nstrips, F, 1), dim3(COLS * 8, 1, 1), args, smem, ctx->stream));
         ctx->launches++;
     }
     SDR_CUDA(ctx, cudaMemcpyAsync(sc.host_err.p, sc.err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     return SDR_OK;
+}
+
+// Strip width of the sweep: 32 columns (256 threads) by default, 16 columns when the 32-column strips of the whole submission
+// leave SMs idle (one 1280x720x128 frame, bottom-up sweep of MODE_HH: 1.02 -> 0.89 ms). Measured and not adopted: 16 columns
+// for D = 256, where a 32-column CTA has an SM to itself (1920x1080x256, 2 frames: 2.49 vs 2.55 ms -- the row chain, not
+// occupancy, bounds that sweep).
+template <int NP>
+int launch_path_v3(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, const int16_t* C, int16_t* S, int diry, int acc, V3Scratch& sc) {
+    bool narrow = (long long)div_up(g.W1, 32) * batch * 2 <= ctx->sm_count;
+    if (tn.v3_cols == 16) narrow = true;
+    if (tn.v3_cols == 32) narrow = false;
+    if (narrow) {
+        const int rc = launch_path_v3c<NP, 16>(ctx, tn, g, batch, C, S, diry, acc, sc);
+        if (rc != -1) return rc;
+    }
+    return launch_path_v3c<NP, 32>(ctx, tn, g, batch, C, S, diry, acc, sc);
 }
 
 // Fused cost + top-down sweep. Returns SDR_OK, an error, or -1 when this configuration is not covered (caller runs
@@ -2349,7 +2366,7 @@ extern "C" int sdr_sgbm_set_option(sdr_sgbm* m, const char* name, int value) {
         {"wave", &t.wave}, {"fused_sweep", &t.fused_sweep}, {"cost_fusion", &t.cost_fusion}, {"path_hh", &t.path_hh}, {"shared_device", &t.shared_device},
         {"cf_cols", &t.cf_cols}, {"cf_prod", &t.cf_prod}, {"cf_fpl", &t.cf_fpl}, {"v3_stages", &t.v3_stages}, {"h_legacy", &t.h_legacy}, {"h_lanes", &t.h_lanes}, {"h_ws", &t.h_ws},
         {"h_k", &t.h_k}, {"h_stages", &t.h_stages}, {"h_warps", &t.h_warps}, {"hb_threads", &t.hb_threads}, {"hb_ring", &t.hb_ring},
-        {"hh_threads", &t.hh_threads}, {"v1_cm", &t.v1_cm}};
+        {"hh_threads", &t.hh_threads}, {"v1_cm", &t.v1_cm}, {"v3_cols", &t.v3_cols}};
     for (const auto& e : tab)
         if (!strcmp(e.n, name)) { *e.p = value; return SDR_OK; }
     return SDR_FAIL(m->ctx, SDR_EINVAL, "sdr_sgbm_set_option: unknown option '%s'", name);

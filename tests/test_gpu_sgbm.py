@@ -189,6 +189,24 @@ def test_fused_cost_sweep_kernel(ctx, orc, W, H, D, bs, mode):
         assert np.array_equal(outs[True][1], Sp)
 
 
+@pytest.mark.parametrize("cols", [16, 32])
+@pytest.mark.parametrize("W,H,D,mode", [(210, 40, 80, 0), (331, 35, 256, 1), (180, 21, 64, 1), (150, 2, 48, 0)])
+def test_sweep_kernel_strip_widths(ctx, orc, W, H, D, mode, cols):
+    """k_path_v3 (the sweep without the cost fusion: D other than 64 / 128, and the bottom-up pass of MODE_HH) with 16- and
+    32-column strips, ragged last strips: bit-exact against the oracle."""
+    from stereo_depth_ruler_b200 import capi, synth
+    args = (0, D, 5, 600, 2400, 1, 63, 12, 50, 2, mode)
+    l, r = synth.stereo_pair(W, H, D, 9)
+    m = capi.Sgbm(ctx, capi.make_params(*args))
+    m.set_option("v3_cols", cols)
+    m.set_profiling(True)
+    got = m.compute(l, r)
+    names = [k for k, _ in m.stage_times()]
+    assert any(n.startswith("path_v_fused") for n in names), names
+    assert np.array_equal(got, orc.sgbm_compute(l, r, orc.make_params(*args)))
+    m.close()
+
+
 FUSED_3WAY = [(300, 70, 80, 5, 1), (333, 64, 128, 5, 2), (197, 50, 64, 3, 4), (161, 9, 80, 3, 0), (420, 38, 256, 5, 0), (229, 3, 64, 5, 2),
               (165, 61, 128, 3, 1)]
 
