@@ -1732,11 +1732,12 @@ struct V3Scratch {
 
 // Returns SDR_OK, an error, or -1 when the cooperative grid cannot be co-resident (caller falls back).
 template <int NP, int COLS>
-int launch_path_v3c(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, const int16_t* C, int16_t* S, int diry, int acc, V3Scratch& sc) {
+int launch_path_v3c(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, const int16_t* C, int16_t* S, int diry, int acc, V3Scratch& sc,
+                    int stages = 0, int* fpl_only = nullptr) {
     constexpr int MINB = NP <= 8 ? 2 : 1;
     auto kern = acc ? k_path_v3<NP, MINB, true, COLS> : k_path_v3<NP, MINB, false, COLS>;
     const int nstrips = div_up(g.W1, COLS);
-    const int env_stages = tn.v3_stages;   // tuning knob
+    const int env_stages = tn.v3_stages > 0 ? tn.v3_stages : stages;   // tuning knob, else the caller's choice
     int nst = acc ? 3 : V3_STAGES_DEFAULT;
     if (env_stages >= 2 && env_stages <= V3_STAGES_MAX) nst = acc ? std::min(env_stages, 3) : env_stages;
     const size_t smem = (size_t)4 * (COLS + 2) * g.D * sizeof(int16_t) + (size_t)4 * (COLS + 2) * sizeof(uint32_t) +
@@ -1746,6 +1747,10 @@ int launch_path_v3c(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, 
     int per_sm = 0;
     SDR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, COLS * 8, smem));
     const int cap = per_sm * ctx->sm_count;
+    if (fpl_only) {   // query: frames one cooperative launch of this variant can hold
+        *fpl_only = cap / nstrips;
+        return SDR_OK;
+    }
     if (cap < nstrips) return -1;
     const int fpl = std::min(batch, cap / nstrips);
     int rc;
@@ -1778,10 +1783,21 @@ int launch_path_v3c(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, 
 template <int NP>
 int launch_path_v3(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, const int16_t* C, int16_t* S, int diry, int acc, V3Scratch& sc) {
     bool narrow = (long long)div_up(g.W1, 32) * batch * 2 <= ctx->sm_count;
+    int stages = 0;
+    if constexpr (NP > 8) {
+        // D > 128: a 32-column CTA has an SM to itself (150 registers x 256 threads), so a launch holds sm_count / nstrips
+        // frames. 16-column strips with a two-row ring fit three CTAs per SM: chosen when that saves cooperative launches
+        // (1920x1080x256 MODE_HH, 3 / 4 / 8 frames: 15.9 -> 13.3, 18.0 -> 16.3, 35.6 -> 32.2 ms; with 2 frames, or at
+        // 1280x720x256 x 8, both need the same number of launches and the wide strips are faster)
+        int f32 = 0, f16 = 0, rc;
+        if ((rc = launch_path_v3c<NP, 32>(ctx, tn, g, batch, C, S, diry, acc, sc, 0, &f32)) > 0) return rc;
+        if ((rc = launch_path_v3c<NP, 16>(ctx, tn, g, batch, C, S, diry, acc, sc, 2, &f16)) > 0) return rc;
+        if (f16 > 0 && (f32 == 0 || div_up(batch, f16) < div_up(batch, f32))) { narrow = true; stages = 2; }
+    }
     if (tn.v3_cols == 16) narrow = true;
     if (tn.v3_cols == 32) narrow = false;
     if (narrow) {
-        const int rc = launch_path_v3c<NP, 16>(ctx, tn, g, batch, C, S, diry, acc, sc);
+        const int rc = launch_path_v3c<NP, 16>(ctx, tn, g, batch, C, S, diry, acc, sc, stages);
         if (rc != -1) return rc;
     }
     return launch_path_v3c<NP, 32>(ctx, tn, g, batch, C, S, diry, acc, sc);

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from stereo_depth_ruler_b200 import capi, synth
 ctx = capi.Context(0)
-for (W, H, D, mode, B) in ((1280, 720, 128, 0, 8), (1280, 720, 128, 0, 1), (1280, 720, 80, 2, 8), (1280, 720, 128, 2, 8), (1280, 720, 128, 1, 8), (1920, 1080, 256, 1, 2), (3840, 2160, 256, 2, 1), (640, 360, 80, 2, 16)):
+for (W, H, D, mode, B) in ((1280, 720, 128, 0, 8), (1280, 720, 128, 0, 1), (1280, 720, 80, 2, 8), (1280, 720, 128, 2, 8), (1280, 720, 128, 1, 8), (1920, 1080, 256, 1, 2), (1920, 1080, 256, 1, 4), (3840, 2160, 256, 2, 1), (640, 360, 80, 2, 16)):
     l, r = synth.stereo_pair(W, H, D, 1)
     L = torch.from_numpy(np.stack([l] * B)).cuda(); R = torch.from_numpy(np.stack([r] * B)).cuda()
     O = torch.empty((B, H, W), dtype=torch.int16, device="cuda")
