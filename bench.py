@@ -131,8 +131,11 @@ def parse_ncu_summary(path):
             out.append(cur)
             continue
         m = re.match(r"^(\S+)\s+([-+0-9.eE]+)\s*(\S*)", line)
-        if cur is not None and m:
-            v = float(m.group(2))
+        if cur is not None and m and not line.startswith("#"):
+            try:
+                v = float(m.group(2))
+            except ValueError:
+                continue
             unit = m.group(3)
             scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(unit, 1.0)
             cur[m.group(1)] = v * scale

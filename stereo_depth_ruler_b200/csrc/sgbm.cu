@@ -382,23 +382,23 @@ __device__ __forceinline__ void store_regs(int16_t* p, const uint32_t (&r)[NP]) 
 // Shared-memory copy of one column's D path costs held by G = 8 lanes x NP registers, laid out so that every 128-bit
 // access of a quarter-warp covers 128 contiguous bytes: register quad q of lane lg sits at int16 offset (q*8 + lg)*8.
 // (The natural layout -- lane lg's 2*NP values contiguous -- makes lanes lg and lg+4 hit the same banks when NP = 8.)
-template <int NP>
+template <int NP, int G = 8>
 __device__ __forceinline__ void load_col_sm(const int16_t* col, int lg, uint32_t (&r)[NP]) {
     if constexpr (NP % 4 == 0) {
 #pragma unroll
         for (int q = 0; q < NP / 4; q++) {
-            const uint4 v = *(const uint4*)(col + (q * 8 + lg) * 8);
+            const uint4 v = *(const uint4*)(col + (q * G + lg) * 8);
             r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
         }
     } else {
         load_regs<NP>(col + lg * 2 * NP, r);
     }
 }
-template <int NP>
+template <int NP, int G = 8>
 __device__ __forceinline__ void store_col_sm(int16_t* col, int lg, const uint32_t (&r)[NP]) {
     if constexpr (NP % 4 == 0) {
 #pragma unroll
-        for (int q = 0; q < NP / 4; q++) *(uint4*)(col + (q * 8 + lg) * 8) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        for (int q = 0; q < NP / 4; q++) *(uint4*)(col + (q * G + lg) * 8) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
     } else {
         store_regs<NP>(col + lg * 2 * NP, r);
     }
@@ -537,10 +537,10 @@ __device__ __forceinline__ void halo_complete(const unsigned long long* p, uint3
     }
 }
 
-template <int NP, int MINB, bool ACC, int COLS>
-__global__ void __launch_bounds__(COLS * 8, MINB) k_path_v3(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int diry, int b0,
+template <int NP, int MINB, bool ACC, int COLS, int G>
+__global__ void __launch_bounds__(COLS * G, MINB) k_path_v3(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int diry, int b0,
                                                        unsigned long long* halo, int* err, int V3_STAGES) {
-    constexpr int G = 8, NW = NP + 1;   // halo words per lane: NP state registers + the path minimum
+    constexpr int NW = NP + 1;   // halo words per lane: NP state registers + the path minimum (a column = G lanes x NP registers)
     extern __shared__ __align__(16) int16_t v3sm[];
     const int D = g.D;
     int16_t* Xa = v3sm;                                     // [2][COLS+2][D]  state of the "from (x-1)" diagonal, slot = column+1
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(COLS * 8, MINB) k_path_v3(Geom g, const int16_
             for (int k = 0; k < NP; k++) pa[k] = (uint32_t)hq[k];
             ma = (uint32_t)hq[NP];
         } else {
-            load_col_sm<NP>(Xa + ((size_t)prv * (COLS + 2) + gidx) * D, lg, pa);
+            load_col_sm<NP, G>(Xa + ((size_t)prv * (COLS + 2) + gidx) * D, lg, pa);
             ma = Ma[prv * (COLS + 2) + gidx];
         }
         if (right_edge && t > 0) {
@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(COLS * 8, MINB) k_path_v3(Geom g, const int16_
             for (int k = 0; k < NP; k++) pb[k] = (uint32_t)hq[k];
             mb = (uint32_t)hq[NP];
         } else {
-            load_col_sm<NP>(Xb + ((size_t)prv * (COLS + 2) + gidx + 2) * D, lg, pb);
+            load_col_sm<NP, G>(Xb + ((size_t)prv * (COLS + 2) + gidx + 2) * D, lg, pb);
             mb = Mb[prv * (COLS + 2) + gidx + 2];
         }
         __syncwarp();
@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(COLS * 8, MINB) k_path_v3(Geom g, const int16_
             for (int k = 0; k < NP; k++) halo_put(hp + k, pa[k], (uint32_t)(t + 1));
             halo_put(hp + NP, ma, (uint32_t)(t + 1));
         }
-        store_col_sm<NP>(Xa + ((size_t)cur * (COLS + 2) + gidx + 1) * D, lg, pa);
+        store_col_sm<NP, G>(Xa + ((size_t)cur * (COLS + 2) + gidx + 1) * D, lg, pa);
         if (lg == 0) Ma[cur * (COLS + 2) + gidx + 1] = ma;
         sgm_step<NP, G>(pb, mb, c, P1x2, P2x2, PADx2, lg);
         if (!active) {
@@ -648,7 +648,7 @@ __global__ void __launch_bounds__(COLS * 8, MINB) k_path_v3(Geom g, const int16_
             for (int k = 0; k < NP; k++) halo_put(hp + k, pb[k], (uint32_t)(t + 1));
             halo_put(hp + NP, mb, (uint32_t)(t + 1));
         }
-        store_col_sm<NP>(Xb + ((size_t)cur * (COLS + 2) + gidx + 1) * D, lg, pb);
+        store_col_sm<NP, G>(Xb + ((size_t)cur * (COLS + 2) + gidx + 1) * D, lg, pb);
         if (lg == 0) Mb[cur * (COLS + 2) + gidx + 1] = mb;
         // request the neighbour's state of THIS row now (it publishes early in its row); it is consumed next row, so the
         // L2 round trip overlaps the vertical path below
@@ -1616,6 +1616,7 @@ struct SgbmTune {
     int h_lanes = 0;        // lanes per row chain in k_path_hh: 8 / 16 / 32, 0 = by the number of rows in flight
     int h_ws = 1;           // few rows in flight: chain warps + tail warps (k_path_hh_ws) instead of k_path_hh with 16 / 32 lanes
     int h_k = 0, h_stages = 0, h_warps = 0, hb_threads = 0, hb_ring = -1, hh_threads = 0;
+    int v3_lanes = 0;       // lanes per column of the sweep kernel at D = 256: 8 / 16 (0 = 16)
     int v3_cols = 0;        // strip width of the sweep kernel k_path_v3: 16 / 32 (0 = by D and the number of strips in flight)
     int v1_cm = 0;          // columns per consumer lane group of the fused cost + vertical path kernel of MODE_SGBM_3WAY: 1 / 2 / 4
 };
@@ -1731,11 +1732,11 @@ struct V3Scratch {
 #include "sgbm_wave.inl"
 
 // Returns SDR_OK, an error, or -1 when the cooperative grid cannot be co-resident (caller falls back).
-template <int NP, int COLS>
+template <int NP, int COLS, int G = 8>
 int launch_path_v3c(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, const int16_t* C, int16_t* S, int diry, int acc, V3Scratch& sc,
                     int stages = 0, int* fpl_only = nullptr) {
-    constexpr int MINB = NP <= 8 ? 2 : 1;
-    auto kern = acc ? k_path_v3<NP, MINB, true, COLS> : k_path_v3<NP, MINB, false, COLS>;
+    constexpr int MINB = NP <= 8 && COLS * G <= 256 ? 2 : 1;
+    auto kern = acc ? k_path_v3<NP, MINB, true, COLS, G> : k_path_v3<NP, MINB, false, COLS, G>;
     const int nstrips = div_up(g.W1, COLS);
     const int env_stages = tn.v3_stages > 0 ? tn.v3_stages : stages;   // tuning knob, else the caller's choice
     int nst = acc ? 3 : V3_STAGES_DEFAULT;
@@ -1745,7 +1746,7 @@ int launch_path_v3c(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, 
     if (smem > ctx->smem_optin) return -1;
     SDR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    SDR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, COLS * 8, smem));
+    SDR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, COLS * G, smem));
     const int cap = per_sm * ctx->sm_count;
     if (fpl_only) {   // query: frames one cooperative launch of this variant can hold
         *fpl_only = cap / nstrips;
@@ -1754,7 +1755,7 @@ int launch_path_v3c(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, 
     if (cap < nstrips) return -1;
     const int fpl = std::min(batch, cap / nstrips);
     int rc;
-    const size_t halo_bytes = (size_t)nstrips * 4 * 8 * (NP + 1) * sizeof(unsigned long long);   // per frame
+    const size_t halo_bytes = (size_t)nstrips * 4 * G * (NP + 1) * sizeof(unsigned long long);   // per frame
     if ((rc = sc.halo.reserve(ctx, halo_bytes * fpl))) return rc;
     if (!sc.err.p) {
         if ((rc = sc.err.reserve(ctx, sizeof(int)))) return rc;
@@ -1769,7 +1770,7 @@ int launch_path_v3c(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, 
         unsigned long long* halo = sc.halo.as<unsigned long long>();
         int* err = sc.err.as<int>();
         void* args[] = {(void*)&gg, (void*)&C, (void*)&S, (void*)&diry, (void*)&b0, (void*)&halo, (void*)&err, (void*)&nst};
-        SDR_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3(nstrips, F, 1), dim3(COLS * 8, 1, 1), args, smem, ctx->stream));
+        SDR_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3(nstrips, F, 1), dim3(COLS * G, 1, 1), args, smem, ctx->stream));
         ctx->launches++;
     }
     SDR_CUDA(ctx, cudaMemcpyAsync(sc.host_err.p, sc.err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1785,14 +1786,23 @@ int launch_path_v3(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, c
     bool narrow = (long long)div_up(g.W1, 32) * batch * 2 <= ctx->sm_count;
     int stages = 0;
     if constexpr (NP > 8) {
-        // D > 128: a 32-column CTA has an SM to itself (150 registers x 256 threads), so a launch holds sm_count / nstrips
-        // frames. 16-column strips with a two-row ring fit three CTAs per SM: chosen when that saves cooperative launches
-        // (1920x1080x256 MODE_HH, 3 / 4 / 8 frames: 15.9 -> 13.3, 18.0 -> 16.3, 35.6 -> 32.2 ms; with 2 frames, or at
-        // 1280x720x256 x 8, both need the same number of launches and the wide strips are faster)
+        // D > 128: a 32-column CTA with 8 lanes x NP registers per column has an SM to itself (150 registers x 256 threads), so a
+        // cooperative launch holds sm_count / nstrips frames. Two remedies, measured at 1920x1080x256 MODE_HH:
+        //  (a) a column over 16 lanes x NP/2 registers -- the register shape and step latency of D = 128, 16 warps per CTA:
+        //      2 frames 2.49 -> 2.20 ms top-down, 2.73 -> 2.21 ms bottom-up;
+        //  (b) 16-column strips with a two-row ring, three CTAs per SM, when that saves cooperative launches:
+        //      4 frames top-down 4.97 -> 3.70 ms ((a): 4.40), bottom-up 5.46 -> 5.09 ms ((a): 4.42).
         int f32 = 0, f16 = 0, rc;
         if ((rc = launch_path_v3c<NP, 32>(ctx, tn, g, batch, C, S, diry, acc, sc, 0, &f32)) > 0) return rc;
         if ((rc = launch_path_v3c<NP, 16>(ctx, tn, g, batch, C, S, diry, acc, sc, 2, &f16)) > 0) return rc;
-        if (f16 > 0 && (f32 == 0 || div_up(batch, f16) < div_up(batch, f32))) { narrow = true; stages = 2; }
+        const bool fewer_launches = f16 > 0 && (f32 == 0 || div_up(batch, f16) < div_up(batch, f32));
+        if constexpr (NP % 8 == 0) {
+            if (tn.v3_lanes != 8 && tn.v3_cols == 0 && !(fewer_launches && !acc)) {
+                rc = launch_path_v3c<NP / 2, 32, 16>(ctx, tn, g, batch, C, S, diry, acc, sc);
+                if (rc != -1) return rc;
+            }
+        }
+        if (fewer_launches) { narrow = true; stages = 2; }
     }
     if (tn.v3_cols == 16) narrow = true;
     if (tn.v3_cols == 32) narrow = false;
@@ -2382,7 +2392,7 @@ extern "C" int sdr_sgbm_set_option(sdr_sgbm* m, const char* name, int value) {
         {"wave", &t.wave}, {"fused_sweep", &t.fused_sweep}, {"cost_fusion", &t.cost_fusion}, {"path_hh", &t.path_hh}, {"shared_device", &t.shared_device},
         {"cf_cols", &t.cf_cols}, {"cf_prod", &t.cf_prod}, {"cf_fpl", &t.cf_fpl}, {"v3_stages", &t.v3_stages}, {"h_legacy", &t.h_legacy}, {"h_lanes", &t.h_lanes}, {"h_ws", &t.h_ws},
         {"h_k", &t.h_k}, {"h_stages", &t.h_stages}, {"h_warps", &t.h_warps}, {"hb_threads", &t.hb_threads}, {"hb_ring", &t.hb_ring},
-        {"hh_threads", &t.hh_threads}, {"v1_cm", &t.v1_cm}, {"v3_cols", &t.v3_cols}};
+        {"hh_threads", &t.hh_threads}, {"v1_cm", &t.v1_cm}, {"v3_cols", &t.v3_cols}, {"v3_lanes", &t.v3_lanes}};
     for (const auto& e : tab)
         if (!strcmp(e.n, name)) { *e.p = value; return SDR_OK; }
     return SDR_FAIL(m->ctx, SDR_EINVAL, "sdr_sgbm_set_option: unknown option '%s'", name);

@@ -189,16 +189,17 @@ def test_fused_cost_sweep_kernel(ctx, orc, W, H, D, bs, mode):
         assert np.array_equal(outs[True][1], Sp)
 
 
-@pytest.mark.parametrize("cols", [16, 32])
-@pytest.mark.parametrize("W,H,D,mode", [(210, 40, 80, 0), (331, 35, 256, 1), (180, 21, 64, 1), (150, 2, 48, 0)])
-def test_sweep_kernel_strip_widths(ctx, orc, W, H, D, mode, cols):
+@pytest.mark.parametrize("cols,lanes", [(16, 8), (32, 8), (0, 16)])
+@pytest.mark.parametrize("W,H,D,mode", [(210, 40, 80, 0), (331, 35, 256, 1), (180, 21, 64, 1), (150, 2, 48, 0), (300, 26, 256, 0)])
+def test_sweep_kernel_strip_widths(ctx, orc, W, H, D, mode, cols, lanes):
     """k_path_v3 (the sweep without the cost fusion: D other than 64 / 128, and the bottom-up pass of MODE_HH) with 16- and
-    32-column strips, ragged last strips: bit-exact against the oracle."""
+    32-column strips and, at D = 256, a column's costs over 8 or 16 lanes; ragged last strips: bit-exact against the oracle."""
     from stereo_depth_ruler_b200 import capi, synth
     args = (0, D, 5, 600, 2400, 1, 63, 12, 50, 2, mode)
     l, r = synth.stereo_pair(W, H, D, 9)
     m = capi.Sgbm(ctx, capi.make_params(*args))
     m.set_option("v3_cols", cols)
+    m.set_option("v3_lanes", lanes)
     m.set_profiling(True)
     got = m.compute(l, r)
     names = [k for k, _ in m.stage_times()]
