@@ -866,11 +866,11 @@ template <int CF_PROD, int COLS> struct CfRegs {
     static constexpr int min_blocks = COLS == 16 ? 3 : COLS == 32 ? 2 : 1;   // fixes the launch register count: 80 / 80 or 64 / 80
 };
 
-template <int NP, int SW2, int CF_PROD, int COLS>
-__global__ void __launch_bounds__(CF_PROD + COLS * 8, CfRegs<CF_PROD, COLS>::min_blocks)
+template <int NP, int SW2, int CF_PROD, int COLS, int G>   // a column's D = 2 * G * NP costs: G lanes x NP packed registers
+__global__ void __launch_bounds__(CF_PROD + COLS * G, CfRegs<CF_PROD, COLS * G / 8>::min_blocks)
 k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ PR, int16_t* __restrict__ C, int16_t* __restrict__ S, int b0,
                unsigned long long* halo, int* err) {
-    constexpr int G = 8, NW = NP + 1, D = 16 * NP, DQ = D / 8;
+    constexpr int NW = NP + 1, D = 2 * G * NP, DQ = D / 8;
     constexpr int CF_CONS = COLS * G;           // consumer threads (8 lanes per column)
     constexpr int XG = CF_PROD / DQ;            // producer column groups
     constexpr int CPT = COLS / XG;           // consecutive output columns per producer thread
@@ -906,7 +906,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
         // =============================== producer: cost rows ===============================
         // register split (per thread): 128 producers 64 / consumers 88 (launch 80); 256 producers 48 / consumers 80 (launch 64);
         // 16-column strips: 128 producers 56 / 128 consumers 96 (launch 80)
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(CfRegs<CF_PROD, COLS>::prod));
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(CfRegs<CF_PROD, COLS * G / 8>::prod));
         const int tid = threadIdx.x;
         const int q = tid % DQ, xg = tid / DQ;
         uint8_t* stage = cfsm + lay.off_stage;
@@ -1024,7 +1024,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
     }
 
     // =============================== consumer: the three top-down paths ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(CfRegs<CF_PROD, COLS>::cons));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(CfRegs<CF_PROD, COLS * G / 8>::cons));
     const int ct = threadIdx.x - CF_PROD;
     const int gidx = ct / G, lg = ct & (G - 1);
     const int x = x0 + gidx;
@@ -1062,7 +1062,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             for (int k = 0; k < NP; k++) pa[k] = (uint32_t)hq[k];
             ma = (uint32_t)hq[NP];
         } else {
-            load_col_sm<NP>(Xa + ((size_t)prv * (COLS + 2) + gidx) * D, lg, pa);
+            load_col_sm<NP, G>(Xa + ((size_t)prv * (COLS + 2) + gidx) * D, lg, pa);
             ma = Ma[prv * (COLS + 2) + gidx];
         }
         if (right_edge && t > 0) {
@@ -1070,7 +1070,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             for (int k = 0; k < NP; k++) pb[k] = (uint32_t)hq[k];
             mb = (uint32_t)hq[NP];
         } else {
-            load_col_sm<NP>(Xb + ((size_t)prv * (COLS + 2) + gidx + 2) * D, lg, pb);
+            load_col_sm<NP, G>(Xb + ((size_t)prv * (COLS + 2) + gidx + 2) * D, lg, pb);
             mb = Mb[prv * (COLS + 2) + gidx + 2];
         }
         __syncwarp();
@@ -1086,7 +1086,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             for (int k = 0; k < NP; k++) halo_put(hp + k, pa[k], (uint32_t)(t + 1));
             halo_put(hp + NP, ma, (uint32_t)(t + 1));
         }
-        store_col_sm<NP>(Xa + ((size_t)cur * (COLS + 2) + gidx + 1) * D, lg, pa);
+        store_col_sm<NP, G>(Xa + ((size_t)cur * (COLS + 2) + gidx + 1) * D, lg, pa);
         if (lg == 0) Ma[cur * (COLS + 2) + gidx + 1] = ma;
         sgm_step<NP, G>(pb, mb, c, P1x2, P2x2, PADx2, lg);
         if (!active) {
@@ -1100,7 +1100,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             for (int k = 0; k < NP; k++) halo_put(hp + k, pb[k], (uint32_t)(t + 1));
             halo_put(hp + NP, mb, (uint32_t)(t + 1));
         }
-        store_col_sm<NP>(Xb + ((size_t)cur * (COLS + 2) + gidx + 1) * D, lg, pb);
+        store_col_sm<NP, G>(Xb + ((size_t)cur * (COLS + 2) + gidx + 1) * D, lg, pb);
         if (lg == 0) Mb[cur * (COLS + 2) + gidx + 1] = mb;
         if (t + 1 < g.H) {
             if (left_edge) halo_issue<NW>(Hptr(s, cur, 0), hq);
@@ -1815,10 +1815,10 @@ int launch_path_v3(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, c
 
 // Fused cost + top-down sweep. Returns SDR_OK, an error, or -1 when this configuration is not covered (caller runs
 // k_cost followed by k_path_v3 / k_path_v instead).
-template <int NP, int SW2, int CF_PROD, int COLS>
+template <int NP, int SW2, int CF_PROD, int COLS, int G = 8>
 int launch_cost_path_v3(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, const int4* PL, const uint8_t* PR, int16_t* C, int16_t* S, V3Scratch& sc) {
-    auto kern = k_cost_path_v3<NP, SW2, CF_PROD, COLS>;
-    constexpr int CF_CONS = COLS * 8;
+    auto kern = k_cost_path_v3<NP, SW2, CF_PROD, COLS, G>;
+    constexpr int CF_CONS = COLS * G;
     const int nstrips = div_up(g.W1, COLS);
     const CfLayout lay = cf_layout(g.D, SW2, g.SH2, COLS);
     if (lay.total > ctx->smem_optin) return -1;
@@ -1833,7 +1833,7 @@ int launch_cost_path_v3(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int bat
     int fpl = std::min(batch, cap / nstrips);
     if (env_fpl > 0) fpl = std::min(fpl, env_fpl);
     int rc;
-    const size_t halo_bytes = (size_t)nstrips * 4 * 8 * (NP + 1) * sizeof(unsigned long long);   // per frame
+    const size_t halo_bytes = (size_t)nstrips * 4 * G * (NP + 1) * sizeof(unsigned long long);   // per frame
     if ((rc = sc.halo.reserve(ctx, halo_bytes * fpl))) return rc;
     if (!sc.err.p) {
         if ((rc = sc.err.reserve(ctx, sizeof(int)))) return rc;
@@ -1890,6 +1890,13 @@ int launch_cost_path_fused(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int 
     if (g.nseg != 1 || g.SW2 != g.SH2 || g.seg[0].src_start != 0 || g.crows != g.H) return -1;
     const int np = g.D / 16;
     if (g.D % 16) return -1;
+    if (np == 16 && tn.cf_cols == 0) {
+        // D = 256: 32-column strips, a column over 16 lanes x 8 registers (512 consumer + 256 producer threads, one CTA per SM,
+        // ~200 KB of shared memory): the thread and register shape of the 64-column D = 128 kernel
+        if (g.SW2 == 2) return launch_cost_path_v3<8, 2, 256, 32, 16>(ctx, tn, g, batch, PL, PR, C, S, sc);
+        if (g.SW2 == 1) return launch_cost_path_v3<8, 1, 256, 32, 16>(ctx, tn, g, batch, PL, PR, C, S, sc);
+        return -1;
+    }
     const int env_prod = tn.cf_prod;   // tuning knob: producer threads (128 | 256)
     const int prod = env_prod == 128 || env_prod == 256 ? env_prod : CF_PROD_DEFAULT;
     // D = 128: 64-column strips, one CTA per SM (512 consumer + 256 producer threads): half as many strip borders to hand

@@ -152,12 +152,12 @@ def test_post_filters_standalone(ctx, orc, golden):
 
 
 FUSED = [(300, 70, 128, 5, 0), (290, 45, 128, 3, 0), (333, 40, 128, 5, 1), (197, 50, 64, 3, 0), (161, 37, 64, 5, 1),
-         (161, 2, 128, 5, 0), (164, 9, 64, 5, 0)]
+         (161, 2, 128, 5, 0), (164, 9, 64, 5, 0), (420, 44, 256, 5, 0), (389, 30, 256, 3, 1), (300, 3, 256, 5, 0)]
 
 
 @pytest.mark.parametrize("W,H,D,bs,mode", FUSED)
 def test_fused_cost_sweep_kernel(ctx, orc, W, H, D, bs, mode):
-    """The configurations the fused cost + top-down sweep kernel covers (D = 64 / 128, blockSize 3 / 5, MODE_SGBM and the
+    """The configurations the fused cost + top-down sweep kernel covers (D = 64 / 128 / 256, blockSize 3 / 5, MODE_SGBM and the
     first pass of MODE_HH), ragged strip widths and fewer rows than the box window: bit-exact against the oracle incl.
     the C and S volumes, identical to the two-kernel path, and the stage timer shows which path ran."""
     from stereo_depth_ruler_b200 import capi, synth
@@ -198,6 +198,7 @@ def test_sweep_kernel_strip_widths(ctx, orc, W, H, D, mode, cols, lanes):
     args = (0, D, 5, 600, 2400, 1, 63, 12, 50, 2, mode)
     l, r = synth.stereo_pair(W, H, D, 9)
     m = capi.Sgbm(ctx, capi.make_params(*args))
+    m.set_option("cost_fusion", 0)       # the sweep kernel on its own (D = 256 would otherwise take the fused cost + sweep kernel)
     m.set_option("v3_cols", cols)
     m.set_option("v3_lanes", lanes)
     m.set_profiling(True)
