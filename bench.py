@@ -186,7 +186,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "s16", "data": "synthetic",
         "mpix_disp_per_s": fps * MPIX_DISP_PER_FRAME,
-        "config": base_config("c2"), "run": {"frames_per_step": len(frames)},
+        "config": base_config("c2"), "run": {"frames_per_step_per_gpu": len(frames), "frames_per_submission": 1},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": cpu.kind,
                          "sample": "%d steps x %d frames; %s" % (args.steps, len(frames), cpu.describe())},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
