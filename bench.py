@@ -412,6 +412,8 @@ def run_ours(args):
     if args.value_runner == "native":
         # the library's own worker threads (one per handle) over the device-resident pool: no host language on the path
         rv = capi.Stream([local], NSLOT, calib, params, vox, handle_missing=True, batch=B, download_clouds=False)
+        for k, v in sgbm_opts:
+            rv.set_sgbm_option(k, int(v))
         ms, st_v, t0, t1 = timed_stream(rv, dev_pool, steps * FPS, max(args.warmup * FPS, NSLOT * B))
         launches = int(st_v.kernel_launches)
         rv.close()
@@ -514,6 +516,8 @@ def run_ours(args):
     # (worker threads in the library, one per handle; Python only starts the run) ----
     ESLOT = max(1, args.e2e_slots)      # more handles than the resident leg: the copies of one batch hide behind the kernels of the others
     runner = capi.Stream([local], ESLOT, calib, params, vox, handle_missing=True, batch=B, download_clouds=True)
+    for k, v in sgbm_opts:
+        runner.set_sgbm_option(k, int(v))
     ms_e, st_e, _, _ = timed_stream(runner, host_np, steps * FPS, max(args.warmup * FPS, ESLOT * B))
     runner.close()
     fps_e = sharding.aggregate_throughput(FPS * steps, world, ms_e)

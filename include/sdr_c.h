@@ -342,6 +342,8 @@ SDR_API int sdr_stream_process(sdr_stream* s, int64_t n_frames, sdr_frame_source
 /* sdr_pipeline_set_input_format on every worker's pipeline (call between create and process; sources then return frames in
  * that format and sdr_stream_process_pool reads its pool as such). */
 SDR_API int sdr_stream_set_input_format(sdr_stream* s, int format);
+/* sdr_sgbm_set_option on every worker's matcher (call between create and process; results never depend on it). */
+SDR_API int sdr_stream_set_sgbm_option(sdr_stream* s, const char* name, int value);
 /* process() over a pool of SBS frames at a constant stride, frame i of the stream = pool frame (i mod n_pool), no callback
  * into the host language (BASELINE config 4: 64 unique pairs cycled to 4096); results land in the workers' pinned
  * buffers and are dropped. mem: sdr_mem of the pool. */

@@ -86,7 +86,7 @@ SYMBOLS = [
     "sdr_pipeline_set_profiling",
     "sdr_measure_distance", "sdr_depth_coverage", "sdr_cloud_save_pcd_binary", "sdr_stream_run",
     "sdr_stream_create", "sdr_stream_destroy", "sdr_stream_process", "sdr_stream_process_pool", "sdr_bind_host_to_device",
-    "sdr_ingest_to_bgr", "sdr_pipeline_set_input_format", "sdr_stream_set_input_format",
+    "sdr_ingest_to_bgr", "sdr_pipeline_set_input_format", "sdr_stream_set_input_format", "sdr_stream_set_sgbm_option",
 ]
 
 _lib = None
@@ -716,6 +716,11 @@ class Stream:
                                      int(bool(download_clouds)), C.byref(self._h))
         if rc != SDR_OK:
             raise SdrError(rc, "sdr_stream_create failed")
+
+    def set_sgbm_option(self, name, value):
+        rc = lib().sdr_stream_set_sgbm_option(self._h, name.encode(), int(value))
+        if rc != SDR_OK:
+            raise SdrError(rc, "sdr_stream_set_sgbm_option failed")
 
     def set_input_format(self, fmt):
         rc = lib().sdr_stream_set_input_format(self._h, int(fmt))

@@ -1290,9 +1290,12 @@ __device__ __forceinline__ void wta_pixel(const uint32_t (&Sr)[NP], int lg, cons
 
 // Horizontal chains: one group per output row. dir = +1 (L->R) accumulates into S;
 // dir = -1 (R->L) with WTA = true finishes S in registers and emits the raw disparity.
+// S2 (optional, WTA kernel only): a second volume to add, the L->R path costs when that pass wrote them to a volume of their own
+// instead of read-modify-writing S (one volume pass moved from the HBM-bound L->R kernel to this issue-bound one).
 template <int NP, int G, bool WTA, int THREADS = 128>
 __global__ void __launch_bounds__(THREADS) k_path_h(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int dir,
-                                                    int accumulate, int16_t* __restrict__ dispraw, uint32_t* __restrict__ wta) {
+                                                    int accumulate, int16_t* __restrict__ dispraw, uint32_t* __restrict__ wta,
+                                                    const int16_t* __restrict__ S2 = nullptr) {
     constexpr int CPB = THREADS / G;
     __shared__ __align__(16) int16_t smS[WTA ? CPB * 2 * NP * G : 8];
     const int lane = threadIdx.x & 31, lg = lane & (G - 1);
@@ -1313,23 +1316,39 @@ __global__ void __launch_bounds__(THREADS) k_path_h(Geom g, const int16_t* __res
     const uint32_t P1x2 = pack16(g.P1, g.P1), P2x2 = pack16(g.P2, g.P2);
     const int pad = 32767 - g.P1;
     const uint32_t PADx2 = pack16(pad, pad);
-    uint32_t P[NP], c[NP], s[NP], L[NP], cn[NP], sn[NP], m = 0;
+    uint32_t P[NP], c[NP], s[NP], L[NP], cn[NP], sn[NP], tn[WTA ? NP : 1], m = 0;
 #pragma unroll
     for (int k = 0; k < NP; k++) { P[k] = 0; sn[k] = 0; }
+#pragma unroll
+    for (int k = 0; k < (WTA ? NP : 1); k++) tn[k] = 0;
+    const bool two = WTA && S2 != nullptr;   // (uniform)
+    const int16_t* Tb = two ? S2 + (((size_t)b * g.H + y) * g.W1) * g.D + (size_t)lg * 2 * NP : nullptr;
     const size_t lane_off = (size_t)lg * 2 * NP;
     const int16_t* Cb = C + (((size_t)b * g.crows + sg.crow0 + (y - sg.src_start)) * g.W1) * D + lane_off;
     int16_t* Sb = S + (((size_t)b * g.H + y) * g.W1) * D + lane_off;
     int x = dir > 0 ? 0 : g.W1 - 1;
     load_regs<NP>(Cb + (size_t)x * D, cn);
     if (accumulate) load_regs<NP>(Sb + (size_t)x * D, sn);
+    if constexpr (WTA) {
+        if (two) load_regs<NP>(Tb + (size_t)x * D, tn);
+    }
     int16_t* sm = smS + (threadIdx.x / G) * 2 * NP * G;
     for (int step = 0; step < g.W1; step++) {
 #pragma unroll
         for (int k = 0; k < NP; k++) { c[k] = cn[k]; s[k] = sn[k]; }
+        if constexpr (WTA) {
+            if (two) {
+#pragma unroll
+                for (int k = 0; k < NP; k++) s[k] = __vminu2(__vadd2(s[k], tn[k]), 0x7FFF7FFFu);
+            }
+        }
         const int xn = x + dir;
         if (step + 1 < g.W1) {
             load_regs<NP>(Cb + (size_t)xn * D, cn);
             if (accumulate) load_regs<NP>(Sb + (size_t)xn * D, sn);
+            if constexpr (WTA) {
+                if (two) load_regs<NP>(Tb + (size_t)xn * D, tn);
+            }
         }
         sgm_step<NP, G>(P, m, c, P1x2, P2x2, PADx2, lg);
 #pragma unroll
@@ -1616,6 +1635,8 @@ struct SgbmTune {
     int h_lanes = 0;        // lanes per row chain in k_path_hh: 8 / 16 / 32, 0 = by the number of rows in flight
     int h_ws = 1;           // few rows in flight: chain warps + tail warps (k_path_hh_ws) instead of k_path_hh with 16 / 32 lanes
     int h_k = 0, h_stages = 0, h_warps = 0, hb_threads = 0, hb_ring = -1, hh_threads = 0;
+    int lr_split = -1;      // the L->R pass writes its path costs to a volume of its own (added by the R->L + WTA kernel) instead of
+                            // read-modify-writing S: 1 / 0, -1 = when shared_device is set (the two horizontal passes are separate kernels)
     int v3_lanes = 0;       // lanes per column of the sweep kernel at D = 256: 8 / 16 (0 = 16)
     int v3_cols = 0;        // strip width of the sweep kernel k_path_v3: 16 / 32 (0 = by D and the number of strips in flight)
     int v1_cm = 0;          // columns per consumer lane group of the fused cost + vertical path kernel of MODE_SGBM_3WAY: 1 / 2 / 4
@@ -1639,7 +1660,7 @@ int launch_path_v(sdr_ctx* ctx, const Geom& g, int batch, const int16_t* C, int1
 }
 template <int NP>
 int launch_path_h(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, const int16_t* C, int16_t* S, int dir, int acc, bool wta_on,
-                  int16_t* dispraw, uint32_t* wta) {
+                  int16_t* dispraw, uint32_t* wta, const int16_t* S2 = nullptr) {
     constexpr int G = 8;
     const bool legacy = tn.h_legacy != 0;   // A/B switch: register-prefetch version
     // tuning knobs (defaults chosen on a B200 at 1280x720x128, batch 8)
@@ -1651,7 +1672,7 @@ int launch_path_h(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, co
     const size_t smem = (size_t)nwarp * nst * 2 * 4 * K * g.D * 2;       // [warp][stage][C|S][row][K][D]
     // measured (1280x720x128, batch 8): L->R 1.12 -> 1.01 ms with the ring; the R->L + WTA kernel is bound by its own
     // dependent arithmetic and loses with the extra shared-memory hop (0.94 -> 1.52 ms), so it keeps the register prefetch
-    const bool wta_ring = tn.hb_ring >= 0 ? tn.hb_ring != 0 : HB_RING_DEFAULT;
+    const bool wta_ring = !S2 && (tn.hb_ring >= 0 ? tn.hb_ring != 0 : HB_RING_DEFAULT);   // the ring variant takes one accumulate source
     if (!legacy && (!wta_on || wta_ring) && smem <= ctx->smem_optin) {
         dim3 grid(div_up(g.hrows, 4 * nwarp), 1, batch);
         if (wta_on) {
@@ -1667,9 +1688,9 @@ int launch_path_h(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int batch, co
     const int threads = env_bt == 32 || env_bt == 64 || env_bt == 128 ? env_bt : HB_THREADS_DEFAULT;
     dim3 grid(div_up(g.hrows, threads / G), 1, batch);
     if (wta_on) {
-        if (threads == 32) k_path_h<NP, G, true, 32><<<grid, 32, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
-        else if (threads == 64) k_path_h<NP, G, true, 64><<<grid, 64, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
-        else k_path_h<NP, G, true, 128><<<grid, 128, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
+        if (threads == 32) k_path_h<NP, G, true, 32><<<grid, 32, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta, S2);
+        else if (threads == 64) k_path_h<NP, G, true, 64><<<grid, 64, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta, S2);
+        else k_path_h<NP, G, true, 128><<<grid, 128, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta, S2);
     } else {
         if (threads == 32) k_path_h<NP, G, false, 32><<<grid, 32, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
         else if (threads == 64) k_path_h<NP, G, false, 64><<<grid, 64, 0, ctx->stream>>>(g, C, S, dir, acc, dispraw, wta);
@@ -1958,7 +1979,7 @@ int launch_cost_path_fused(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int 
 struct sdr_sgbm {
     sdr_ctx* ctx = nullptr;
     sdr_sgbm_params p{};
-    DevBuf inL, inR, PL, PR, C, S, dispraw, wta, matched, out;
+    DevBuf inL, inR, PL, PR, C, S, S2, dispraw, wta, matched, out;
     SpeckleScratch speckle;
     V3Scratch v3;
     WaveScratch wave;
@@ -2008,7 +2029,7 @@ extern "C" int sdr_sgbm_create(sdr_ctx* ctx, const sdr_sgbm_params* params, sdr_
 extern "C" void sdr_sgbm_destroy(sdr_sgbm* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
-    for (DevBuf* b : {&m->inL, &m->inR, &m->PL, &m->PR, &m->C, &m->S, &m->dispraw, &m->wta, &m->matched, &m->out,
+    for (DevBuf* b : {&m->inL, &m->inR, &m->PL, &m->PR, &m->C, &m->S, &m->S2, &m->dispraw, &m->wta, &m->matched, &m->out,
                       &m->speckle.parent, &m->speckle.count, &m->v3.halo, &m->v3.err, &m->post_in, &m->wave.haloD, &m->wave.haloH})
         b->release();
     m->v3.host_err.release();
@@ -2216,6 +2237,17 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
             NP_SWITCH(np, rc = launch_path_hh<NPc>(ctx, m->tune, g, batch, C, S, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>()));
             if (rc) return rc;
             m->timer.mark(st, "path_h_both_wta");
+        } else if ((m->tune.lr_split >= 0 ? m->tune.lr_split : m->tune.shared_device) != 0) {
+            // L -> R writes its own volume (C read, L written: 2 volume passes instead of 3 in the HBM-bound kernel); the R -> L +
+            // WTA kernel, bound by instruction issue, reads it besides C and S
+            if ((rc = m->S2.reserve(ctx, (size_t)g.W1 * g.D * sizeof(int16_t) * H * batch))) return rc;
+            int16_t* S2 = m->S2.as<int16_t>();
+            NP_SWITCH(np, rc = launch_path_h<NPc>(ctx, m->tune, g, batch, C, S2, +1, 0, false, nullptr, nullptr));
+            if (rc) return rc;
+            m->timer.mark(st, "path_h_fwd");
+            NP_SWITCH(np, rc = launch_path_h<NPc>(ctx, m->tune, g, batch, C, S, -1, 1, true, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>(), S2));
+            if (rc) return rc;
+            m->timer.mark(st, "path_h_bwd_wta");
         } else {
             NP_SWITCH(np, rc = launch_path_h<NPc>(ctx, m->tune, g, batch, C, S, +1, 1, false, nullptr, nullptr));
             if (rc) return rc;
@@ -2399,7 +2431,7 @@ extern "C" int sdr_sgbm_set_option(sdr_sgbm* m, const char* name, int value) {
         {"wave", &t.wave}, {"fused_sweep", &t.fused_sweep}, {"cost_fusion", &t.cost_fusion}, {"path_hh", &t.path_hh}, {"shared_device", &t.shared_device},
         {"cf_cols", &t.cf_cols}, {"cf_prod", &t.cf_prod}, {"cf_fpl", &t.cf_fpl}, {"v3_stages", &t.v3_stages}, {"h_legacy", &t.h_legacy}, {"h_lanes", &t.h_lanes}, {"h_ws", &t.h_ws},
         {"h_k", &t.h_k}, {"h_stages", &t.h_stages}, {"h_warps", &t.h_warps}, {"hb_threads", &t.hb_threads}, {"hb_ring", &t.hb_ring},
-        {"hh_threads", &t.hh_threads}, {"v1_cm", &t.v1_cm}, {"v3_cols", &t.v3_cols}, {"v3_lanes", &t.v3_lanes}};
+        {"hh_threads", &t.hh_threads}, {"v1_cm", &t.v1_cm}, {"v3_cols", &t.v3_cols}, {"v3_lanes", &t.v3_lanes}, {"lr_split", &t.lr_split}};
     for (const auto& e : tab)
         if (!strcmp(e.n, name)) { *e.p = value; return SDR_OK; }
     return SDR_FAIL(m->ctx, SDR_EINVAL, "sdr_sgbm_set_option: unknown option '%s'", name);

@@ -73,6 +73,7 @@ struct sdr_stream {
     sdr_pipeline_options opt{};
     int download_clouds = 0;
     std::atomic<int> input_format{SDR_PIX_BGR};   // applied by every worker at the start of its next job
+    std::vector<std::pair<std::string, int>> sgbm_options;   // kernel knobs for every worker's matcher (set between jobs)
 
     // one job at a time; workers sleep between jobs
     std::mutex mu;
@@ -136,6 +137,8 @@ void sdr_stream::worker(int di) {
         int jrc = rc;
         const int fmt = input_format.load();
         if (jrc == SDR_OK) jrc = sdr_pipeline_set_input_format(pipe, fmt);
+        for (const auto& kv : sgbm_options)
+            if (jrc == SDR_OK) jrc = sdr_pipeline_set_sgbm_option(pipe, kv.first.c_str(), kv.second);
         int in_rows;
         size_t in_row_bytes;
         sdr_ingest_layout(fmt, 2 * W, H, &in_rows, &in_row_bytes);
@@ -271,6 +274,14 @@ extern "C" int sdr_stream_process(sdr_stream* s, int64_t n_frames, sdr_frame_sou
     }
     if (s->first_error.load() != SDR_OK) fprintf(stderr, "sdr_stream_process: %s\n", s->err_msg.c_str());
     return s->first_error.load();
+}
+
+extern "C" int sdr_stream_set_sgbm_option(sdr_stream* s, const char* name, int value) {
+    if (!s || !name) return SDR_EINVAL;
+    for (auto& kv : s->sgbm_options)
+        if (kv.first == name) { kv.second = value; return SDR_OK; }
+    s->sgbm_options.emplace_back(name, value);   // unknown names surface as SDR_EINVAL from the next process() call
+    return SDR_OK;
 }
 
 extern "C" int sdr_stream_set_input_format(sdr_stream* s, int format) {

@@ -209,6 +209,30 @@ def test_sweep_kernel_strip_widths(ctx, orc, W, H, D, mode, cols, lanes):
     m.close()
 
 
+@pytest.mark.parametrize("W,H,args", [(300, 41, (0, 128, 5, 600, 2400, 1, 63, 12, 50, 2, 0)), (203, 33, (0, 64, 3, 72, 288, 1, 63, 12, 0, 0, 1)),
+                                      (190, 57, (0, 80, 5, 600, 2400, 1, 63, 12, 200, 2, 2)), (140, 9, (3, 48, 3, 72, 288, 2, 31, 5, 20, 1, 0)),
+                                      (333, 27, (0, 256, 5, 600, 2400, 1, 63, 12, 200, 2, 1))])
+def test_forward_pass_with_its_own_volume(ctx, orc, W, H, args):
+    """What several matchers on one device run (option shared_device): the L->R pass writes its path costs to a volume of its
+    own and the R->L + WTA kernel adds C-independent S and that volume (lr_split): bit-exact against the oracle and against the
+    read-modify-write form, batch of 3."""
+    from stereo_depth_ruler_b200 import capi, synth
+    B = 3
+    pairs = [synth.stereo_pair(W, H, args[1], 60 + s) for s in range(B)]
+    refs = [orc.sgbm_compute(l, r, orc.make_params(*args)) for l, r in pairs]
+    for split in (1, 0):
+        m = capi.Sgbm(ctx, capi.make_params(*args))
+        m.set_option("shared_device", 1)
+        m.set_option("lr_split", split)
+        m.set_profiling(True)
+        got = m.compute_batch(np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs]), np.empty((B, H, W), np.int16))
+        names = [k for k, _ in m.stage_times()]
+        assert "path_h_fwd" in names and "path_h_bwd_wta" in names, names
+        for i in range(B):
+            assert np.array_equal(got[i], refs[i]), (split, i)
+        m.close()
+
+
 FUSED_3WAY = [(300, 70, 80, 5, 1), (333, 64, 128, 5, 2), (197, 50, 64, 3, 4), (161, 9, 80, 3, 0), (420, 38, 256, 5, 0), (229, 3, 64, 5, 2),
               (165, 61, 128, 3, 1)]
 
