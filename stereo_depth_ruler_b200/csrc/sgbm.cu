@@ -1635,8 +1635,10 @@ struct SgbmTune {
     int h_lanes = 0;        // lanes per row chain in k_path_hh: 8 / 16 / 32, 0 = by the number of rows in flight
     int h_ws = 1;           // few rows in flight: chain warps + tail warps (k_path_hh_ws) instead of k_path_hh with 16 / 32 lanes
     int h_k = 0, h_stages = 0, h_warps = 0, hb_threads = 0, hb_ring = -1, hh_threads = 0;
-    int lr_split = -1;      // the L->R pass writes its path costs to a volume of its own (added by the R->L + WTA kernel) instead of
-                            // read-modify-writing S: 1 / 0, -1 = when shared_device is set (the two horizontal passes are separate kernels)
+    int lr_split = 0;       // 1: the L->R pass writes its path costs to a volume of its own (added by the R->L + WTA kernel) instead of
+                            // read-modify-writing S. Off: alone the two kernels gain (0.886 + 0.976 -> 0.608 + 1.069 ms per 8 frames),
+                            // but with four handles in flight the benchmark loses 2 % (1775 -> 1740 frames/s, same box): the bytes
+                            // move into the kernel that other handles' HBM-bound work used to overlap with
     int v3_lanes = 0;       // lanes per column of the sweep kernel at D = 256: 8 / 16 (0 = 16)
     int v3_cols = 0;        // strip width of the sweep kernel k_path_v3: 16 / 32 (0 = by D and the number of strips in flight)
     int v1_cm = 0;          // columns per consumer lane group of the fused cost + vertical path kernel of MODE_SGBM_3WAY: 1 / 2 / 4
@@ -2237,7 +2239,7 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
             NP_SWITCH(np, rc = launch_path_hh<NPc>(ctx, m->tune, g, batch, C, S, m->dispraw.as<int16_t>(), m->wta.as<uint32_t>()));
             if (rc) return rc;
             m->timer.mark(st, "path_h_both_wta");
-        } else if ((m->tune.lr_split >= 0 ? m->tune.lr_split : m->tune.shared_device) != 0) {
+        } else if (m->tune.lr_split != 0) {
             // L -> R writes its own volume (C read, L written: 2 volume passes instead of 3 in the HBM-bound kernel); the R -> L +
             // WTA kernel, bound by instruction issue, reads it besides C and S
             if ((rc = m->S2.reserve(ctx, (size_t)g.W1 * g.D * sizeof(int16_t) * H * batch))) return rc;
