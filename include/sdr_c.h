@@ -295,6 +295,10 @@ SDR_API int sdr_pipeline_set_sgbm_option(sdr_pipeline* p, const char* name, int 
 /* Per-stage device times (ms) of the last run (CUDA events on the ctx stream); enable first. */
 SDR_API int sdr_pipeline_set_profiling(sdr_pipeline* p, int enabled);
 SDR_API int sdr_pipeline_stage_times(sdr_pipeline* p, int cap, const char** names, float* ms);
+/* The same marks as absolute times: ms from `base_cuda_event` (a cudaEvent_t recorded earlier on any stream of the device) to
+ * the start of the last run ("begin") and to the end of each stage; which = 0: the pipeline's stages, 1: the matcher's kernels.
+ * Laid side by side for several handles this is the timeline of who ran when (tools/probes/timeline.py). */
+SDR_API int sdr_pipeline_stage_timeline(sdr_pipeline* p, void* base_cuda_event, int which, int cap, const char** names, float* t_ms);
 /* Copy cloud i of the last run to host buffers (any may be NULL); sized by views[i].n. */
 SDR_API int sdr_pipeline_cloud_download(sdr_pipeline* p, int i, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt);
 /* The clouds of frames 0..n-1 of the last run in one go (arrays of n host pointers, any array may be NULL): the copies are

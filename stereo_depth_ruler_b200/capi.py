@@ -86,7 +86,7 @@ SYMBOLS = [
     "sdr_pipeline_set_profiling",
     "sdr_measure_distance", "sdr_depth_coverage", "sdr_cloud_save_pcd_binary", "sdr_stream_run",
     "sdr_stream_create", "sdr_stream_destroy", "sdr_stream_process", "sdr_stream_process_pool", "sdr_bind_host_to_device",
-    "sdr_ingest_to_bgr", "sdr_pipeline_set_input_format", "sdr_stream_set_input_format", "sdr_stream_set_sgbm_option",
+    "sdr_ingest_to_bgr", "sdr_pipeline_set_input_format", "sdr_stream_set_input_format", "sdr_stream_set_sgbm_option", "sdr_pipeline_stage_timeline",
 ]
 
 _lib = None
@@ -673,6 +673,13 @@ class Pipeline:
         total = int(off[n])
         per = (12 if xyz is not None else 0) + (3 if rgb is not None else 0) + (4 if idx is not None else 0) + (4 if cnt is not None else 0)
         return np.array(off[:], np.int64), total * per
+
+    def stage_timeline(self, base_event, which=0):
+        """[(name, ms since base_event)]: "begin" and the end of every stage of the last run (which=1: the matcher's kernels)."""
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        n = lib().sdr_pipeline_stage_timeline(self._h, C.c_void_p(int(base_event)), int(which), 64, names, ms)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
 
     def set_profiling(self, on=True):
         lib().sdr_pipeline_set_profiling(self._h, int(on))

@@ -100,6 +100,20 @@ int StageTimer::collect(int cap, const char** out_names, float* ms) {
     }
     return k;
 }
+// Times of begin() and of every mark since `base` (an event recorded earlier on any stream of the device): a timeline that
+// can be laid beside those of other handles.
+int StageTimer::collect_since(cudaEvent_t base, int cap, const char** out_names, float* ms) {
+    if (!enabled || n < 1) return 0;
+    cudaEventSynchronize(ev[n - 1]);
+    int k = 0;
+    for (size_t i = 0; i < n && k < cap; i++, k++) {
+        float t = 0;
+        cudaEventElapsedTime(&t, base, ev[i]);
+        if (out_names) out_names[k] = i == 0 ? "begin" : names[i - 1];
+        if (ms) ms[k] = t;
+    }
+    return k;
+}
 void StageTimer::release() {
     for (auto& e : ev) cudaEventDestroy(e);
     ev.clear();

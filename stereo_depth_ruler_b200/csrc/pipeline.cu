@@ -206,6 +206,7 @@ extern "C" int sdr_pipeline_set_sgbm_option(sdr_pipeline* p, const char* name, i
 extern "C" int sdr_pipeline_set_profiling(sdr_pipeline* p, int enabled) {
     if (!p) return SDR_EINVAL;
     p->timer.enabled = enabled != 0;
+    sdr_sgbm_timer(p->sgbm)->enabled = enabled != 0;
     return SDR_OK;
 }
 
@@ -213,6 +214,13 @@ extern "C" int sdr_pipeline_stage_times(sdr_pipeline* p, int cap, const char** n
     if (!p) return 0;
     cudaSetDevice(p->ctx->device);
     return p->timer.collect(cap, names, ms);
+}
+
+extern "C" int sdr_pipeline_stage_timeline(sdr_pipeline* p, void* base_cuda_event, int which, int cap, const char** names, float* t_ms) {
+    if (!p || !base_cuda_event) return 0;
+    cudaSetDevice(p->ctx->device);
+    StageTimer* t = which == 0 ? &p->timer : sdr_sgbm_timer(p->sgbm);
+    return t->collect_since((cudaEvent_t)base_cuda_event, cap, names, t_ms);
 }
 
 extern "C" int sdr_pipeline_cloud_download(sdr_pipeline* p, int i, float* xyz, uint8_t* rgb, uint32_t* idx, uint32_t* cnt) {

@@ -95,6 +95,7 @@ struct StageTimer {
     void begin(cudaStream_t s);
     void mark(cudaStream_t s, const char* name);
     int collect(int cap, const char** out_names, float* ms);
+    int collect_since(cudaEvent_t base, int cap, const char** out_names, float* ms);
     void release();
 };
 
