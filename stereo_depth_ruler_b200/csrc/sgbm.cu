@@ -861,9 +861,9 @@ __device__ __forceinline__ void cost_producer(const Geom& g, const int4* __restr
 
 // register split between the roles (setmaxnreg), per strip width: producer / consumer registers per thread
 template <int CF_PROD, int COLS> struct CfRegs {
-    static constexpr int prod = COLS == 16 ? 56 : (2 * CF_PROD == COLS * 8 ? 64 : 48);
-    static constexpr int cons = COLS == 16 ? 96 : (2 * CF_PROD == COLS * 8 ? 88 : 80);
-    static constexpr int min_blocks = COLS == 16 ? 3 : COLS == 32 ? 2 : 1;   // fixes the launch register count: 80 / 80 or 64 / 80
+    static constexpr int prod = COLS <= 16 ? 56 : (2 * CF_PROD == COLS * 8 ? 64 : 48);
+    static constexpr int cons = COLS <= 16 ? 96 : (2 * CF_PROD == COLS * 8 ? 88 : 80);
+    static constexpr int min_blocks = COLS == 8 ? 4 : COLS == 16 ? 3 : COLS == 32 ? 2 : 1;   // fixes the launch register count: 80 / 80 or 64 / 80
 };
 
 template <int NP, int SW2, int CF_PROD, int COLS, int G>   // a column's D = 2 * G * NP costs: G lanes x NP packed registers
@@ -1935,6 +1935,16 @@ int launch_cost_path_fused(sdr_ctx* ctx, const SgbmTune& tn, const Geom& g, int 
     }
     // Few frames in flight (the reference's usage: one frame at a time): 16-column strips put twice as many CTAs on the machine
     // (one 1280x720 frame: 72 instead of 36), each with half the work per row.
+    // 8-column strips (one 1280x720 frame = 144 CTAs of 128 producer + 64 consumer threads): option only -- measured slower at
+    // 1280x720x128 (1.03 -> 1.49 ms: the producers' halo columns double) and equal at 640x360x64 (profiles/experiments/README.md)
+    if (env_cols == 8) {
+        int rc8 = -1;
+        if (np == 8 && g.SW2 == 2) rc8 = launch_cost_path_v3<8, 2, 128, 8>(ctx, tn, g, batch, PL, PR, C, S, sc);
+        else if (np == 8 && g.SW2 == 1) rc8 = launch_cost_path_v3<8, 1, 128, 8>(ctx, tn, g, batch, PL, PR, C, S, sc);
+        else if (np == 4 && g.SW2 == 2) rc8 = launch_cost_path_v3<4, 2, 64, 8>(ctx, tn, g, batch, PL, PR, C, S, sc);
+        else if (np == 4 && g.SW2 == 1) rc8 = launch_cost_path_v3<4, 1, 64, 8>(ctx, tn, g, batch, PL, PR, C, S, sc);
+        if (rc8 != -1) return rc8;
+    }
     if (env_cols == 16 || (env_cols == 0 && (long long)div_up(g.W1, 32) * batch * 2 <= ctx->sm_count)) {
         int rc16 = -1;
         if (np == 8 && g.SW2 == 2) rc16 = launch_cost_path_v3<8, 2, 128, 16>(ctx, tn, g, batch, PL, PR, C, S, sc);

@@ -365,7 +365,7 @@ def test_per_direction_fallback_kernels(ctx, orc, mode):
     m.close()
 
 
-@pytest.mark.parametrize("cols,D", [(64, 128), (16, 128), (16, 64), (32, 128)])
+@pytest.mark.parametrize("cols,D", [(64, 128), (16, 128), (16, 64), (32, 128), (8, 128), (8, 64)])
 @pytest.mark.parametrize("W,H,bs", [(300, 40, 5), (333, 23, 3), (257, 31, 5)])
 def test_fused_kernel_strip_widths_small(ctx, orc, W, H, bs, cols, D):
     """Option cf_cols: the fused kernel with 64-column strips (one CTA per SM; what a batch of 8 at 1280 wide runs), 32-column
