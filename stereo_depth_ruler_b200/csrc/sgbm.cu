@@ -436,6 +436,58 @@ __device__ __forceinline__ void sgm_step(uint32_t (&P)[NP], uint32_t& m, const u
     for (int o = G / 2; o >= 1; o >>= 1) mm = __vmins2(mm, __shfl_xor_sync(0xffffffffu, mm, o, G));
     m = mm;
 }
+// N independent path steps (the sweep's two diagonals) advanced together: the same arithmetic as N sgm_step calls, written
+// so that the shuffles of the chains are issued back to back and their arithmetic interleaves. Pays only when few warps
+// share a scheduler (narrow strips, one frame at a time: fused kernel 1.018 -> 0.984 ms); with 64-column strips at batch 8
+// it is slower (1.99 -> 2.06 ms for two chains, 2.17 for three): profiles/experiments/README.md.
+template <int NP, int G, int N>
+__device__ __forceinline__ void sgm_step_n(uint32_t* const (&P)[N], uint32_t (&m)[N], const uint32_t (&c)[NP], uint32_t P1x2, uint32_t P2x2,
+                                           uint32_t PADx2, int lg) {
+    uint32_t up[N], dn[N], negm[N], mm[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        up[j] = __shfl_up_sync(0xffffffffu, P[j][NP - 1], 1, G);
+        dn[j] = __shfl_down_sync(0xffffffffu, P[j][0], 1, G);
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        if (lg == 0) up[j] = PADx2;
+        if (lg == G - 1) dn[j] = PADx2;
+        negm[j] = __vadd2(~m[j], 0x00010001u);
+        mm[j] = 0x7FFF7FFFu;
+    }
+    uint32_t lo[N];   // prmt(P[k-1], P[k]) of the register being updated (old values)
+#pragma unroll
+    for (int j = 0; j < N; j++) lo[j] = prmt(up[j], P[j][0], 0x5432);
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            const uint32_t hi = prmt(P[j][k], k + 1 < NP ? P[j][k + 1] : dn[j], 0x5432);
+            uint32_t t = __vmins2(lo[j], hi);
+            t = __viaddmin_s16x2(t, P1x2, P[j][k]);
+            t = __viaddmin_s16x2(t, negm[j], P2x2);
+            P[j][k] = __vadd2(c[k], t);
+            lo[j] = hi;
+            if (k & 1) mm[j] = __vimin3_s16x2(mm[j], P[j][k - 1], P[j][k]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        if (NP & 1) mm[j] = __vmins2(mm[j], P[j][NP - 1]);
+        mm[j] = __vmins2(mm[j], prmt(mm[j], mm[j], 0x1032));
+    }
+#pragma unroll
+    for (int o = G / 2; o >= 1; o >>= 1) {
+        uint32_t t[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) t[j] = __shfl_xor_sync(0xffffffffu, mm[j], o, G);
+#pragma unroll
+        for (int j = 0; j < N; j++) mm[j] = __vmins2(mm[j], t[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) m[j] = mm[j];
+}
 template <int NP, int G>
 __global__ void __launch_bounds__(128) k_path_v(Geom g, const int16_t* __restrict__ C, int16_t* __restrict__ S, int dirx,
                                                 int diry, int accumulate) {
@@ -1073,6 +1125,45 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
             load_col_sm<NP, G>(Xb + ((size_t)prv * (COLS + 2) + gidx + 2) * D, lg, pb);
             mb = Mb[prv * (COLS + 2) + gidx + 2];
         }
+        if constexpr (COLS <= 16) {   // few warps per scheduler: the two diagonal steps interleaved
+            __syncwarp();
+            {
+                uint32_t* const PP[2] = {pa, pb};
+                uint32_t mmm[2] = {ma, mb};
+                sgm_step_n<NP, G, 2>(PP, mmm, c, P1x2, P2x2, PADx2, lg);
+                ma = mmm[0]; mb = mmm[1];
+            }
+            if (!active) {
+#pragma unroll
+                for (int k = 0; k < NP; k++) { pa[k] = 0; pb[k] = 0; }
+                ma = 0; mb = 0;
+            }
+            if (right_edge) {
+                unsigned long long* hp = Hptr(s + 1, cur, 0);
+#pragma unroll
+                for (int k = 0; k < NP; k++) halo_put(hp + k, pa[k], (uint32_t)(t + 1));
+                halo_put(hp + NP, ma, (uint32_t)(t + 1));
+            }
+            if (left_edge) {
+                unsigned long long* hp = Hptr(s - 1, cur, 1);
+#pragma unroll
+                for (int k = 0; k < NP; k++) halo_put(hp + k, pb[k], (uint32_t)(t + 1));
+                halo_put(hp + NP, mb, (uint32_t)(t + 1));
+            }
+            store_col_sm<NP, G>(Xa + ((size_t)cur * (COLS + 2) + gidx + 1) * D, lg, pa);
+            store_col_sm<NP, G>(Xb + ((size_t)cur * (COLS + 2) + gidx + 1) * D, lg, pb);
+            if (lg == 0) { Ma[cur * (COLS + 2) + gidx + 1] = ma; Mb[cur * (COLS + 2) + gidx + 1] = mb; }
+            if (t + 1 < g.H) {
+                if (left_edge) halo_issue<NW>(Hptr(s, cur, 0), hq);
+                if (right_edge) halo_issue<NW>(Hptr(s, cur, 1), hq);
+            }
+            sgm_step<NP, G>(Pv, mv, c, P1x2, P2x2, PADx2, lg);
+#pragma unroll
+            for (int k = 0; k < NP; k++) {
+                acc[k] = __vminu2(__vadd2(pa[k], pb[k]), 0x7FFF7FFFu);
+                acc[k] = __vminu2(__vadd2(acc[k], Pv[k]), 0x7FFF7FFFu);
+            }
+        } else {
         __syncwarp();
         sgm_step<NP, G>(pa, ma, c, P1x2, P2x2, PADx2, lg);
         if (!active) {
@@ -1112,6 +1203,7 @@ k_cost_path_v3(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ 
         sgm_step<NP, G>(Pv, mv, c, P1x2, P2x2, PADx2, lg);
 #pragma unroll
         for (int k = 0; k < NP; k++) acc[k] = __vminu2(__vadd2(acc[k], Pv[k]), 0x7FFF7FFFu);
+        }
         if (active) store_regs<NP>(Sb + (size_t)t * rowstride, acc);
         if (t + 1 < g.H) {
             if (left_edge) halo_complete<NW>(Hptr(s, cur, 0), (uint32_t)(t + 1), err, hq);
