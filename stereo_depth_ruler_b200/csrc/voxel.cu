@@ -26,6 +26,7 @@ struct VoxParams {  // lives on the device; written by k_vox_params
     int bbox_key[6];  // min xyz, max xyz as ordered-int keys
     unsigned nvox;
     int min_disp_key;
+    unsigned nsort;   // points that enter the sort: nvalid, or 0 when the index guard trips (passthrough)
 };
 
 struct Source {  // where a pixel's 3-D point comes from
@@ -83,6 +84,7 @@ __global__ void k_vox_reset(VoxParams* vp0) {
     vp->bbox_key[3] = vp->bbox_key[4] = vp->bbox_key[5] = (int)0x80000000;
     vp->nvalid = 0;
     vp->nvox = 0;
+    vp->nsort = 0;
     vp->overflow = 0;
     vp->min_disp_key = 0x7FFFFFFF;
 }
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(256) k_vox_mindisp(Source s, VoxParams* vp0) {
     }
 }
 
-__global__ void __launch_bounds__(256) k_vox_bbox(Source s, VoxParams* vp0) {
+__global__ void __launch_bounds__(256) k_vox_bbox(Source s, VoxParams* vp0, uint32_t* __restrict__ blk_cnt) {
     const int fr = blockIdx.y;
     VoxParams* vp = vp0 + fr;
     int mn[3] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF}, mx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(256) k_vox_bbox(Source s, VoxParams* vp0) {
             for (int c = 0; c < 3; c++) { mn[c] = min(mn[c], smn[w][c]); mx[c] = max(mx[c], smx[w][c]); }
             ok += sok[w];
         }
+        blk_cnt[(size_t)fr * gridDim.x + blockIdx.x] = ok;   // points of this block's 2048 pixels that enter the grid (k_vox_keys compacts with it)
         if (ok) {
 #pragma unroll
             for (int c = 0; c < 3; c++) {
@@ -189,42 +192,80 @@ __global__ void k_vox_params(VoxParams* vp0, float lx, float ly, float lz) {
     // PCL multiplies in int64; for absurd boxes the product wraps (two's complement, as on x86)
     const long long prod = (long long)((unsigned long long)d[0] * (unsigned long long)d[1] * (unsigned long long)d[2]);
     vp->overflow = prod > 2147483647LL ? 1 : 0;
+    vp->nsort = vp->overflow ? 0u : vp->nvalid;
     vp->mul[0] = 1;
     vp->mul[1] = vp->divb[0];
     vp->mul[2] = (int)((unsigned)vp->divb[0] * (unsigned)vp->divb[1]);
 }
 
-__global__ void __launch_bounds__(256) k_vox_keys(Source s, const VoxParams* vp0, uint32_t* keys, uint32_t* vals, int npad) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, fr = blockIdx.y;
-    if (i >= npad) return;
+// Keys (voxel index) and values (pixel index) of the points that enter the grid, compacted in ascending pixel order: block
+// (bx, fr) owns the same 2048 pixels as in k_vox_bbox, whose per-block counts (scanned) say where its points go. Pixels that
+// do not enter the grid (62 % of a typical frame do) are never sorted.
+__global__ void __launch_bounds__(256) k_vox_keys(Source s, const VoxParams* vp0, const uint32_t* __restrict__ blk_off, uint32_t* keys,
+                                                  uint32_t* vals, int npad) {
+    const int fr = blockIdx.y;
     const VoxParams* vp = vp0 + fr;
+    if (vp->nsort == 0) return;
     keys += (size_t)fr * npad;
     vals += (size_t)fr * npad;
-    uint32_t key = 0xFFFFFFFFu;
-    if (i < s.W * s.H && !vp->overflow) {
-        float p[3];
-        if (fetch_point(s, vp, fr, i, p[0], p[1], p[2])) {
-            const int i0 = (int)__fsub_rn(floorf(__fmul_rn(p[0], vp->inv[0])), (float)vp->minb[0]);
-            const int i1 = (int)__fsub_rn(floorf(__fmul_rn(p[1], vp->inv[1])), (float)vp->minb[1]);
-            const int i2 = (int)__fsub_rn(floorf(__fmul_rn(p[2], vp->inv[2])), (float)vp->minb[2]);
-            key = (uint32_t)i0 * (uint32_t)vp->mul[0] + (uint32_t)i1 * (uint32_t)vp->mul[1] + (uint32_t)i2 * (uint32_t)vp->mul[2];
+    __shared__ uint32_t cnt[VOX_PPT * 8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t key[VOX_PPT];
+    unsigned okmask = 0;
+    uint32_t rank[VOX_PPT];
+#pragma unroll
+    for (int k = 0; k < VOX_PPT; k++) {
+        const int i = (blockIdx.x * VOX_PPT + k) * blockDim.x + threadIdx.x;
+        bool ok = false;
+        key[k] = 0;
+        if (i < s.W * s.H) {
+            float p[3];
+            if (fetch_point(s, vp, fr, i, p[0], p[1], p[2])) {
+                const int i0 = (int)__fsub_rn(floorf(__fmul_rn(p[0], vp->inv[0])), (float)vp->minb[0]);
+                const int i1 = (int)__fsub_rn(floorf(__fmul_rn(p[1], vp->inv[1])), (float)vp->minb[1]);
+                const int i2 = (int)__fsub_rn(floorf(__fmul_rn(p[2], vp->inv[2])), (float)vp->minb[2]);
+                key[k] = (uint32_t)i0 * (uint32_t)vp->mul[0] + (uint32_t)i1 * (uint32_t)vp->mul[1] + (uint32_t)i2 * (uint32_t)vp->mul[2];
+                ok = true;
+            }
         }
+        const unsigned b = __ballot_sync(0xffffffffu, ok);
+        rank[k] = __popc(b & ((1u << lane) - 1));
+        if (ok) okmask |= 1u << k;
+        if (lane == 0) cnt[k * 8 + warp] = __popc(b);
     }
-    keys[i] = key;
-    vals[i] = (uint32_t)i;
+    __syncthreads();
+    uint32_t mine = 0;   // exclusive prefix over the (k, warp) cells = ascending pixel order
+    if (threadIdx.x < VOX_PPT * 8)
+        for (int j = 0; j < (int)threadIdx.x; j++) mine += cnt[j];
+    __syncthreads();
+    if (threadIdx.x < VOX_PPT * 8) cnt[threadIdx.x] = mine;
+    __syncthreads();
+    const uint32_t base = blk_off[(size_t)fr * gridDim.x + blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < VOX_PPT; k++)
+        if (okmask >> k & 1) {
+            const uint32_t pos = base + cnt[k * 8 + warp] + rank[k];
+            keys[pos] = key[k];
+            vals[pos] = (uint32_t)((blockIdx.x * VOX_PPT + k) * blockDim.x + threadIdx.x);
+        }
 }
 
 // ---- stable LSD radix sort, 8-bit digits ---------------------------------------------------
 constexpr int RS_THREADS = 256, RS_ITEMS = 8, RS_TILE = RS_THREADS * RS_ITEMS;
 
-__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint32_t* __restrict__ keys, int n, int shift, uint32_t* __restrict__ hist,
-                                                        int nblocks) {
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint32_t* __restrict__ keys, const VoxParams* __restrict__ vp0, int npad, int shift,
+                                                        uint32_t* __restrict__ hist, int nblocks) {
     __shared__ uint32_t h[256];
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    keys += (size_t)blockIdx.y * n;
+    const int n = (int)vp0[blockIdx.y].nsort;   // the frame's compacted points; tiles beyond them only report zeros
+    keys += (size_t)blockIdx.y * npad;
     hist += (size_t)blockIdx.y * 256 * nblocks;
     const int base = blockIdx.x * RS_TILE;
+    if (base >= n) {
+        hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = 0;
+        return;
+    }
+    h[threadIdx.x] = 0;
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < RS_ITEMS; k++) {
         const int i = base + k * RS_THREADS + threadIdx.x;
@@ -334,13 +375,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_apply(uint32_t* __re
     }
 }
 
-__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n,
-                                                           int shift, const uint32_t* __restrict__ hist, int nblocks,
-                                                           uint32_t* __restrict__ okeys, uint32_t* __restrict__ ovals) {
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                           const VoxParams* __restrict__ vp0, int npad, int shift,
+                                                           const uint32_t* __restrict__ hist, int nblocks, uint32_t* __restrict__ okeys,
+                                                           uint32_t* __restrict__ ovals) {
     constexpr int NW = RS_THREADS / 32;
     __shared__ uint32_t wcount[NW][256];
-    keys += (size_t)blockIdx.y * n; vals += (size_t)blockIdx.y * n;
-    okeys += (size_t)blockIdx.y * n; ovals += (size_t)blockIdx.y * n;
+    const int n = (int)vp0[blockIdx.y].nsort;
+    if (blockIdx.x * RS_TILE >= n) return;
+    keys += (size_t)blockIdx.y * npad; vals += (size_t)blockIdx.y * npad;
+    okeys += (size_t)blockIdx.y * npad; ovals += (size_t)blockIdx.y * npad;
     hist += (size_t)blockIdx.y * 256 * nblocks;
     for (int i = threadIdx.x; i < NW * 256; i += RS_THREADS) (&wcount[0][0])[i] = 0;
     __syncthreads();
@@ -399,22 +443,30 @@ __device__ __forceinline__ size_t cloud_base(const VoxParams* vp0, int fr, size_
     return base;
 }
 
-__global__ void __launch_bounds__(256) k_vox_heads(const uint32_t* __restrict__ keys, int n, uint32_t* __restrict__ flags) {
+__global__ void __launch_bounds__(256) k_vox_heads(const uint32_t* __restrict__ keys, const VoxParams* __restrict__ vp0, int npad,
+                                                   uint32_t* __restrict__ flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    keys += (size_t)blockIdx.y * n;
-    flags += (size_t)blockIdx.y * n;
+    if (i >= npad) return;
+    const int n = (int)vp0[blockIdx.y].nsort;
+    keys += (size_t)blockIdx.y * npad;
+    flags += (size_t)blockIdx.y * npad;
+    if (i >= n) {
+        flags[i] = 0;
+        return;
+    }
     const uint32_t k = keys[i];
-    flags[i] = (k != 0xFFFFFFFFu && (i == 0 || keys[i - 1] != k)) ? 1u : 0u;
+    flags[i] = (i == 0 || keys[i - 1] != k) ? 1u : 0u;
 }
 
 __global__ void __launch_bounds__(256) k_vox_reduce(Source s, VoxParams* vp0, const uint32_t* __restrict__ keys,
-                                                    const uint32_t* __restrict__ vals, const uint32_t* __restrict__ slot, int n,
+                                                    const uint32_t* __restrict__ vals, const uint32_t* __restrict__ slot, int npad,
                                                     float* __restrict__ oxyz, uint8_t* __restrict__ orgb, uint32_t* __restrict__ oidx,
                                                     uint32_t* __restrict__ ocnt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, fr = blockIdx.y;
     VoxParams* vp = vp0 + fr;
-    keys += (size_t)fr * n; vals += (size_t)fr * n; slot += (size_t)fr * n;
+    const int n = (int)vp->nsort;
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    keys += (size_t)fr * npad; vals += (size_t)fr * npad; slot += (size_t)fr * npad;
     {   // the clouds of a batch are packed back to back (frame fr starts where frame fr-1 ends): one copy brings them all home
         const size_t base = cloud_base(vp0, fr, (size_t)s.W * s.H);
         oxyz += base * 3; orgb += base * 3; oidx += base; ocnt += base;
@@ -509,7 +561,7 @@ __global__ void __launch_bounds__(256) k_vox_passthrough(Source s, const VoxPara
 struct sdr_cloud {
     sdr_ctx* ctx = nullptr;
     DevBuf in_points, in_bgr, in_disp;
-    DevBuf keys[2], vals[2], hist, flags, params, scan_sums;
+    DevBuf keys[2], vals[2], hist, flags, params, scan_sums, blk_cnt;
     DevBuf oxyz, orgb, oidx, ocnt;
     PinnedBuf host_params;
     cudaEvent_t done = nullptr;
@@ -531,7 +583,7 @@ extern "C" void sdr_cloud_destroy(sdr_cloud* c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
     for (DevBuf* b : {&c->in_points, &c->in_bgr, &c->in_disp, &c->keys[0], &c->keys[1], &c->vals[0], &c->vals[1], &c->hist, &c->flags,
-                      &c->params, &c->scan_sums, &c->oxyz, &c->orgb, &c->oidx, &c->ocnt})
+                      &c->params, &c->scan_sums, &c->blk_cnt, &c->oxyz, &c->orgb, &c->oidx, &c->ocnt})
         b->release();
     c->host_params.release();
     if (c->done) cudaEventDestroy(c->done);
@@ -571,6 +623,7 @@ int sdr_cloud_enqueue(sdr_cloud* c, int frames, const uint8_t* points, size_t ps
     if ((rc = c->hist.reserve(ctx, F * 256 * nblocks * 4))) return rc;
     if ((rc = c->flags.reserve(ctx, F * n * 4))) return rc;
     if ((rc = c->params.reserve(ctx, F * sizeof(VoxParams)))) return rc;
+    if ((rc = c->blk_cnt.reserve(ctx, F * div_up(n, 256 * VOX_PPT) * 4))) return rc;
     if ((rc = c->oxyz.reserve(ctx, F * n * 12))) return rc;
     if ((rc = c->orgb.reserve(ctx, F * n * 3))) return rc;
     if ((rc = c->oidx.reserve(ctx, F * n * 4))) return rc;
@@ -595,25 +648,27 @@ int sdr_cloud_enqueue(sdr_cloud* c, int frames, const uint8_t* points, size_t ps
         k_vox_mindisp<<<gppt, 256, 0, st>>>(s, vp);
         SDR_LAUNCHED(ctx);
     }
-    k_vox_bbox<<<gppt, 256, 0, st>>>(s, vp);
+    k_vox_bbox<<<gppt, 256, 0, st>>>(s, vp, c->blk_cnt.as<uint32_t>());
     SDR_LAUNCHED(ctx);
     k_vox_params<<<frames, 1, 0, st>>>(vp, opt->leaf[0], opt->leaf[1], opt->leaf[2]);
     SDR_LAUNCHED(ctx);
-    k_vox_keys<<<g256, 256, 0, st>>>(s, vp, c->keys[0].as<uint32_t>(), c->vals[0].as<uint32_t>(), n);
+    k_scan_block<<<frames, 1024, 0, st>>>(c->blk_cnt.as<uint32_t>(), (int)gppt.x, nullptr, 0);   // where each block's points go
+    SDR_LAUNCHED(ctx);
+    k_vox_keys<<<gppt, 256, 0, st>>>(s, vp, c->blk_cnt.as<uint32_t>(), c->keys[0].as<uint32_t>(), c->vals[0].as<uint32_t>(), n);
     SDR_LAUNCHED(ctx);
     int cur = 0;
     for (int pass = 0; pass < 4; pass++) {
         const int shift = pass * 8;
-        k_rs_hist<<<dim3(nblocks, frames), RS_THREADS, 0, st>>>(c->keys[cur].as<uint32_t>(), n, shift, c->hist.as<uint32_t>(), nblocks);
+        k_rs_hist<<<dim3(nblocks, frames), RS_THREADS, 0, st>>>(c->keys[cur].as<uint32_t>(), vp, n, shift, c->hist.as<uint32_t>(), nblocks);
         SDR_LAUNCHED(ctx);
         if ((rc = scan_u32(c, frames, c->hist.as<uint32_t>(), 256 * nblocks, nullptr, 0))) return rc;
-        k_rs_scatter<<<dim3(nblocks, frames), RS_THREADS, 0, st>>>(c->keys[cur].as<uint32_t>(), c->vals[cur].as<uint32_t>(), n, shift,
+        k_rs_scatter<<<dim3(nblocks, frames), RS_THREADS, 0, st>>>(c->keys[cur].as<uint32_t>(), c->vals[cur].as<uint32_t>(), vp, n, shift,
                                                                    c->hist.as<uint32_t>(), nblocks, c->keys[cur ^ 1].as<uint32_t>(),
                                                                    c->vals[cur ^ 1].as<uint32_t>());
         SDR_LAUNCHED(ctx);
         cur ^= 1;
     }
-    k_vox_heads<<<g256, 256, 0, st>>>(c->keys[cur].as<uint32_t>(), n, c->flags.as<uint32_t>());
+    k_vox_heads<<<g256, 256, 0, st>>>(c->keys[cur].as<uint32_t>(), vp, n, c->flags.as<uint32_t>());
     SDR_LAUNCHED(ctx);
     if ((rc = scan_u32(c, frames, c->flags.as<uint32_t>(), n, &vp->nvox, sizeof(VoxParams)))) return rc;
     k_vox_reduce<<<g256, 256, 0, st>>>(s, vp, c->keys[cur].as<uint32_t>(), c->vals[cur].as<uint32_t>(), c->flags.as<uint32_t>(), n,
