@@ -223,13 +223,13 @@ constexpr int COST_STAGES = 2;
 // thread-private shared-memory ring (no synchronisation needed for it). The prefiltered image rows are staged in
 // shared memory by TMA bulk copies (two per row: the left constants and the right byte planes of the tile), two rows
 // ahead, completion signalled on an mbarrier.
-template <int ITEMS>
+template <int ITEMS, int TXH>   // TXH: columns per CTA including the 2*SW2 halo (64; 32 when the 64-column tile does not fit shared memory)
 __global__ void __launch_bounds__(256) k_cost(Geom g, const int4* __restrict__ PL, const uint8_t* __restrict__ PR,
                                               int16_t* __restrict__ C) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full[COST_STAGES];
     const int D = g.D, DQ = D >> 3;
-    const int n = 2 * g.SH2 + 1, TX = COST_TXH - 2 * g.SW2;
+    const int n = 2 * g.SH2 + 1, TX = TXH - 2 * g.SW2;
     const int b = blockIdx.z;
     int band = blockIdx.y, si = 0;
     for (; si < g.nseg; si++) {
@@ -243,14 +243,14 @@ __global__ void __launch_bounds__(256) k_cost(Geom g, const int4* __restrict__ P
     const int ymin = sg.src_start, ymax = g.H - 1;
     const int x0 = blockIdx.x * TX;
     // tile geometry (uniform): cost-space columns [lo, hi), staged right-image chunks [cs, cs + nchunks)
-    const int lo = max(x0 - g.SW2, 0), hi = min(x0 - g.SW2 + COST_TXH, g.W1);
+    const int lo = max(x0 - g.SW2, 0), hi = min(x0 - g.SW2 + TXH, g.W1);
     const int j0_min = (g.W - 1 - (hi - 1 + g.minX1)) + g.minD, j0_max = (g.W - 1 - (lo + g.minX1)) + g.minD + 8 * (DQ - 1);
     const int cs = max(j0_min - 3, 0) >> 4, nchunks = ((j0_max + 7) >> 4) - cs + 1;
     const uint32_t pl_bytes = (uint32_t)(hi - lo) * 16, pr_bytes = (uint32_t)nchunks * PR_CHUNK;
-    const size_t stage_bytes = (size_t)COST_TXH * 16 + (size_t)((COST_TXH + D + 32) / 16 + 1) * PR_CHUNK;   // as sized by the host
+    const size_t stage_bytes = (size_t)TXH * 16 + (size_t)((TXH + D + 32) / 16 + 1) * PR_CHUNK;   // as sized by the host
     uint8_t* stage = smem;                                                      // [STAGES][PL 64 x 16 B | PR chunks]
     uint8_t* ring = smem + COST_STAGES * stage_bytes;                           // [n][64][D] u8
-    uint16_t* Vs = (uint16_t*)(ring + (size_t)n * COST_TXH * D);                // [64][D] u16
+    uint16_t* Vs = (uint16_t*)(ring + (size_t)n * TXH * D);                // [64][D] u16
     const int q = threadIdx.x % DQ, xg = threadIdx.x / DQ, XG = blockDim.x / DQ;
     int ix[ITEMS], o0[ITEMS], o1[ITEMS];
     uint32_t V[ITEMS][4];
@@ -258,14 +258,14 @@ __global__ void __launch_bounds__(256) k_cost(Geom g, const int4* __restrict__ P
     for (int k = 0; k < ITEMS; k++) {
         const int xh = xg + k * XG;
         const int xc = min(max(x0 - g.SW2 + xh, 0), g.W1 - 1);
-        ix[k] = min(max(xc - lo, 0), COST_TXH - 1);
+        ix[k] = min(max(xc - lo, 0), TXH - 1);
         const int j0 = (g.W - 1 - (xc + g.minX1)) + g.minD + 8 * q;
         const int a = j0 & 3, p0 = j0 - a, p1 = p0 + 4;
         o0[k] = ((p0 >> 4) - cs) * PR_CHUNK + (p0 & 15) + a * 16;
         o1[k] = ((p1 >> 4) - cs) * PR_CHUNK + (p1 & 15) + a * 16;
         V[k][0] = V[k][1] = V[k][2] = V[k][3] = 0;
-        if (xh < COST_TXH)
-            for (int s = 0; s < n; s++) *(uint2*)(ring + ((size_t)s * COST_TXH + xh) * D + 8 * q) = make_uint2(0, 0);
+        if (xh < TXH)
+            for (int s = 0; s < n; s++) *(uint2*)(ring + ((size_t)s * TXH + xh) * D + 8 * q) = make_uint2(0, 0);
     }
     const int kv0 = ya - g.SH2, NV = (yb - 1 + g.SH2) - kv0 + 1;
     auto issue = [&](int i) {   // one thread: stage virtual row i
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(256) k_cost(Geom g, const int4* __restrict__ P
         uint64_t* bar = &full[i % COST_STAGES];
         mbar_expect_tx(bar, pl_bytes + pr_bytes);
         bulk_g2s(st, PL + ((size_t)b * g.H + rc) * g.W + lo + g.minX1, pl_bytes, bar);
-        bulk_g2s(st + COST_TXH * 16, PR + (((size_t)b * g.H + rc) * (g.Wp >> 4) + cs) * PR_CHUNK, pr_bytes, bar);
+        bulk_g2s(st + TXH * 16, PR + (((size_t)b * g.H + rc) * (g.Wp >> 4) + cs) * PR_CHUNK, pr_bytes, bar);
     };
     if (threadIdx.x == 0) {
         for (int s = 0; s < COST_STAGES; s++) mbar_init(&full[s], 1);
@@ -289,14 +289,14 @@ __global__ void __launch_bounds__(256) k_cost(Geom g, const int4* __restrict__ P
         const uint8_t* st = stage + (size_t)(i % COST_STAGES) * stage_bytes;
         mbar_wait(&full[i % COST_STAGES], (uint32_t)((i / COST_STAGES) & 1));
         const int4* pls = (const int4*)st;
-        const uint8_t* prs = st + COST_TXH * 16;
+        const uint8_t* prs = st + TXH * 16;
 #pragma unroll
         for (int k = 0; k < ITEMS; k++) {
             const int xh = xg + k * XG;
-            if (xh < COST_TXH) {
+            if (xh < TXH) {
                 uint32_t n0, n1;
                 bt_item(pls[ix[k]], prs, o0[k], o1[k], n0, n1);
-                uint2* rp = (uint2*)(ring + ((size_t)slot * COST_TXH + xh) * D + 8 * q);
+                uint2* rp = (uint2*)(ring + ((size_t)slot * TXH + xh) * D + 8 * q);
                 const uint2 old = *rp;
                 *rp = make_uint2(n0, n1);
                 const uint32_t c0 = ~old.x, c1 = ~old.y;   // 255 - old per byte
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(256) k_cost(Geom g, const int4* __restrict__ P
 #pragma unroll
             for (int k = 0; k < ITEMS; k++) {
                 const int xh = xg + k * XG;
-                if (xh < COST_TXH) *(uint4*)(Vs + (size_t)xh * D + 8 * q) = make_uint4(V[k][0], V[k][1], V[k][2], V[k][3]);
+                if (xh < TXH) *(uint4*)(Vs + (size_t)xh * D + 8 * q) = make_uint4(V[k][0], V[k][1], V[k][2], V[k][3]);
             }
         }
         __syncthreads();   // every thread is done with this stage (and Vs is complete)
@@ -1356,7 +1356,9 @@ __device__ __forceinline__ void wta_pixel(const uint32_t (&Sr)[NP], int lg, cons
     const int Sm = best > 0 ? sm[best - 1] : 0, Sp = best < g.D - 1 ? sm[best + 1] : 0;
     __syncwarp();
     int nexcl = (minS < thr) + (best > 0 && Sm < thr) + (best < g.D - 1 && Sp < thr);
-    if (nlt > nexcl) {
+    // A pixel whose costs are ALL saturated (minS == SHRT_MAX: large windows and penalties, eight paths of MODE_HH) keeps cv2's
+    // initial bestDisp = -1 in computeDisparitySGBM (no cost is < MAX_COST), which comes out as the invalid value
+    if (nlt > nexcl || (!g.three_way && minS >= 32767)) {
         disp_out = (g.minD - 1) * 16;
         wta_out = 0xFFFFFFFFu;
         return;
@@ -1678,7 +1680,8 @@ __global__ void __launch_bounds__(256) k_lrcheck(Geom g, const int16_t* __restri
         if (w != 0xFFFFFFFFu) {
             const int best = (int)(w & 0xFFFFu), minS = (int)(w >> 16);
             const int x2 = x + g.minX1 - best - g.minD;
-            if (x2 >= 0 && x2 < g.W) atomicMin(&keys[x2], ((uint32_t)minS << 16) | (uint32_t)(0xFFFF - x));
+            // cv2 updates disp2 only when the cost is below its initial MAX_COST = SHRT_MAX: a saturated minimum never enters
+            if (minS < 32767 && x2 >= 0 && x2 < g.W) atomicMin(&keys[x2], ((uint32_t)minS << 16) | (uint32_t)(0xFFFF - x));
         }
     }
     __syncthreads();
@@ -2288,17 +2291,29 @@ static int sgbm_run(sdr_sgbm* m, int batch, const uint8_t* L, size_t lpitch, siz
         if (!cost_done) {
             const int n = 2 * g.SH2 + 1, DQ = g.D / 8;
             const int nthr = (256 / DQ) * DQ, XG = nthr / DQ;
-            const int items = div_up(COST_TXH, XG);
-            const size_t stage_bytes = (size_t)COST_TXH * 16 + (size_t)((COST_TXH + g.D + 32) / 16 + 1) * PR_CHUNK;
-            const size_t smem = COST_STAGES * stage_bytes + (size_t)n * COST_TXH * g.D + (size_t)COST_TXH * g.D * 2;
-            if (smem > ctx->smem_optin) return SDR_FAIL(ctx, SDR_EINVAL, "cost kernel needs %zu B shared memory", smem);
+            // 64-column tiles; 32-column tiles when the pixel-cost ring of a large window x disparity range does not fit shared
+            // memory (D = 256 with blockSize 11: 233 KB -> 123 KB)
+            int txh = COST_TXH;
+            size_t smem = 0;
+            for (;; txh /= 2) {
+                const size_t stage_bytes = (size_t)txh * 16 + (size_t)((txh + g.D + 32) / 16 + 1) * PR_CHUNK;
+                smem = COST_STAGES * stage_bytes + (size_t)n * txh * g.D + (size_t)txh * g.D * 2;
+                if (smem <= ctx->smem_optin || txh == 32) break;
+            }
+            if (smem > ctx->smem_optin || txh <= 2 * g.SW2) return SDR_FAIL(ctx, SDR_EINVAL, "cost kernel needs %zu B shared memory", smem);
+            const int items = div_up(txh, XG);
             int bands = 0;
             for (int i = 0; i < g.nseg; i++) bands += div_up(g.seg[i].src_end - g.seg[i].src_start, COST_RB);
-            const dim3 grid(div_up(g.W1, COST_TXH - 2 * g.SW2), bands, batch);
-#define COST_LAUNCH(IT)                                                                                               \
-    case IT:                                                                                                          \
-        SDR_CUDA(ctx, cudaFuncSetAttribute(k_cost<IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        k_cost<IT><<<grid, nthr, smem, st>>>(g, m->PL.as<int4>(), m->PR.as<uint8_t>(), m->C.as<int16_t>());          \
+            const dim3 grid(div_up(g.W1, txh - 2 * g.SW2), bands, batch);
+#define COST_LAUNCH(IT)                                                                                                      \
+    case IT:                                                                                                                 \
+        if (txh == 64) {                                                                                                     \
+            SDR_CUDA(ctx, cudaFuncSetAttribute(k_cost<IT, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+            k_cost<IT, 64><<<grid, nthr, smem, st>>>(g, m->PL.as<int4>(), m->PR.as<uint8_t>(), m->C.as<int16_t>());         \
+        } else {                                                                                                             \
+            SDR_CUDA(ctx, cudaFuncSetAttribute(k_cost<IT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+            k_cost<IT, 32><<<grid, nthr, smem, st>>>(g, m->PL.as<int4>(), m->PR.as<uint8_t>(), m->C.as<int16_t>());         \
+        }                                                                                                                    \
         break;
             switch (items) {
                 COST_LAUNCH(1) COST_LAUNCH(2) COST_LAUNCH(3) COST_LAUNCH(4) COST_LAUNCH(5) COST_LAUNCH(6) COST_LAUNCH(7) COST_LAUNCH(8)

@@ -53,13 +53,19 @@ template <int N>
 __device__ __forceinline__ void ld_chain(const int16_t* p, uint32_t (&r)[N]) {
     if constexpr (N == 4) { const uint4 v = *(const uint4*)p; r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w; }
     else if constexpr (N == 2) { const uint2 v = *(const uint2*)p; r[0] = v.x; r[1] = v.y; }
-    else { r[0] = *(const uint32_t*)p; }
+    else {   // N = 1, 3 (D = 64, 192): a lane's 4*N bytes are only 4-byte aligned
+#pragma unroll
+        for (int i = 0; i < N; i++) r[i] = ((const uint32_t*)p)[i];
+    }
 }
 template <int N>
 __device__ __forceinline__ void st_chain(int16_t* p, const uint32_t (&r)[N]) {
     if constexpr (N == 4) *(uint4*)p = make_uint4(r[0], r[1], r[2], r[3]);
     else if constexpr (N == 2) *(uint2*)p = make_uint2(r[0], r[1]);
-    else *(uint32_t*)p = r[0];
+    else {
+#pragma unroll
+        for (int i = 0; i < N; i++) ((uint32_t*)p)[i] = r[i];
+    }
 }
 
 // Winner-take-all / uniqueness / sub-pixel for one pixel whose final S is spread over the 32 lanes of a warp (lane l: disparities
@@ -101,7 +107,9 @@ __device__ __forceinline__ void wta_pixel32(const uint32_t (&Sr)[NPc], int lane,
     }
     const int Sm = best > 0 ? sm[best - 1] : 0, Sp = best < g.D - 1 ? sm[best + 1] : 0;
     const int nexcl = (minS < thr) + (best > 0 && Sm < thr) + (best < g.D - 1 && Sp < thr);
-    if (nlt > nexcl) {
+    // A pixel whose costs are ALL saturated (minS == SHRT_MAX: large windows and penalties, eight paths of MODE_HH) keeps cv2's
+    // initial bestDisp = -1 in computeDisparitySGBM (no cost is < MAX_COST), which comes out as the invalid value
+    if (nlt > nexcl || (!g.three_way && minS >= 32767)) {
         disp_out = (g.minD - 1) * 16;
         wta_out = 0xFFFFFFFFu;
         return;
