@@ -49,6 +49,9 @@ __device__ __forceinline__ int fkey(float f) {
     return i >= 0 ? i : i ^ 0x7FFFFFFF;
 }
 __device__ __forceinline__ float kfloat(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
+// static_cast<int>(float) as the x86 build of PCL performs it (cvttss2si): a value outside the int range gives INT_MIN, where
+// the GPU's conversion saturates. Only reached with absurd leaf sizes whose int64 index guard wraps around and passes.
+__device__ __forceinline__ int f2i_x86(float v) { return (v >= 2147483648.f || v < -2147483648.f || v != v) ? (int)0x80000000 : (int)v; }
 
 // xyz of pixel i; returns false when the point does not enter the voxel grid.
 __device__ __forceinline__ bool fetch_point(const Source& s, const VoxParams* vp, int fr, int i, float& X, float& Y, float& Z) {
@@ -185,9 +188,9 @@ __global__ void k_vox_params(VoxParams* vp0, float lx, float ly, float lz) {
         const float mn = kfloat(vp->bbox_key[c]), mx = kfloat(vp->bbox_key[3 + c]);
         vp->inv[c] = inv;
         d[c] = (long long)__fmul_rn(__fsub_rn(mx, mn), inv) + 1;
-        vp->minb[c] = (int)floorf(__fmul_rn(mn, inv));
-        const int maxb = (int)floorf(__fmul_rn(mx, inv));
-        vp->divb[c] = maxb - vp->minb[c] + 1;
+        vp->minb[c] = f2i_x86(floorf(__fmul_rn(mn, inv)));
+        const int maxb = f2i_x86(floorf(__fmul_rn(mx, inv)));
+        vp->divb[c] = (int)((unsigned)maxb - (unsigned)vp->minb[c] + 1u);
     }
     // PCL multiplies in int64; for absurd boxes the product wraps (two's complement, as on x86)
     const long long prod = (long long)((unsigned long long)d[0] * (unsigned long long)d[1] * (unsigned long long)d[2]);
@@ -221,9 +224,9 @@ __global__ void __launch_bounds__(256) k_vox_keys(Source s, const VoxParams* vp0
         if (i < s.W * s.H) {
             float p[3];
             if (fetch_point(s, vp, fr, i, p[0], p[1], p[2])) {
-                const int i0 = (int)__fsub_rn(floorf(__fmul_rn(p[0], vp->inv[0])), (float)vp->minb[0]);
-                const int i1 = (int)__fsub_rn(floorf(__fmul_rn(p[1], vp->inv[1])), (float)vp->minb[1]);
-                const int i2 = (int)__fsub_rn(floorf(__fmul_rn(p[2], vp->inv[2])), (float)vp->minb[2]);
+                const int i0 = f2i_x86(__fsub_rn(floorf(__fmul_rn(p[0], vp->inv[0])), (float)vp->minb[0]));
+                const int i1 = f2i_x86(__fsub_rn(floorf(__fmul_rn(p[1], vp->inv[1])), (float)vp->minb[1]));
+                const int i2 = f2i_x86(__fsub_rn(floorf(__fmul_rn(p[2], vp->inv[2])), (float)vp->minb[2]));
                 key[k] = (uint32_t)i0 * (uint32_t)vp->mul[0] + (uint32_t)i1 * (uint32_t)vp->mul[1] + (uint32_t)i2 * (uint32_t)vp->mul[2];
                 ok = true;
             }
@@ -476,10 +479,11 @@ __global__ void __launch_bounds__(256) k_vox_reduce(Source s, VoxParams* vp0, co
     __shared__ float pxyz[256][3];
     __shared__ float prgb[256][3];
     __shared__ uint32_t pkey[256];
-    const uint32_t key = i < n ? keys[i] : 0xFFFFFFFFu;
+    const bool valid = i < n;          // (every compacted key is a real voxel index, 0xFFFFFFFF included when an absurd grid wraps)
+    const uint32_t key = valid ? keys[i] : 0u;
     {
         float X = 0.f, Y = 0.f, Z = 0.f, R = 0.f, G = 0.f, B = 0.f;
-        if (key != 0xFFFFFFFFu) {
+        if (valid) {
             const int pt = (int)vals[i];
             fetch_point(s, vp, fr, pt, X, Y, Z);
             if (s.bgr) {
@@ -493,7 +497,7 @@ __global__ void __launch_bounds__(256) k_vox_reduce(Source s, VoxParams* vp0, co
         pkey[threadIdx.x] = key;
     }
     __syncthreads();
-    if (key == 0xFFFFFFFFu || (i > 0 && keys[i - 1] == key)) return;
+    if (!valid || (i > 0 && keys[i - 1] == key)) return;
     float sx = 0.f, sy = 0.f, sz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
     int cnt = 0;
     int j = i;

@@ -232,3 +232,38 @@ def test_pcd_binary_writer(ctx, orc, golden, tmp_path):
     with pytest.raises(capi.SdrError):
         empty.save_pcd_binary(tmp_path / "none.pcd")
     cloud.close(); empty.close()
+
+
+def test_voxelgrid_absurd_leaves_random(ctx, orc):
+    """Leaf sizes so small that PCL's int64 index guard wraps around and passes (the reference's literal leaf 0.005 on a millimetre
+    cloud is of this kind), or trips: the GPU must take the same branch as the restatement and, when the guard passes, produce the same
+    wrapped int32 indices -- including coordinates whose float -> int conversion leaves the int range (x86: INT_MIN). Found by
+    tools/fuzz_stages.py."""
+    from stereo_depth_ruler_b200 import capi
+    rng = np.random.default_rng(11)
+    passed = tripped = 0
+    for case in range(45):
+        n = int(rng.integers(50, 3000))
+        kind = case % 3
+        if kind == 0:
+            pts = rng.uniform(-5000, 5000, size=(n, 3))
+        elif kind == 1:
+            pts = np.stack([rng.uniform(-3000, 3000, n), rng.uniform(-2000, 2000, n), rng.choice([10000.0, 500.0, 2500.0], n) + rng.uniform(0, 50, n)], -1)
+        else:
+            pts = rng.uniform(-3e5, 3e5, size=(n, 3))            # coordinate / leaf beyond the int range
+        pts = pts.astype(np.float32).reshape(1, n, 3)
+        leaf = float(rng.choice([1e-5, 1e-3, 3e-4]))
+        with np.errstate(all="ignore"):
+            ref = orc.voxelgrid(pts, None, leaf)
+        cl = capi.Cloud(ctx)
+        got = cl.voxelgrid(pts, None, capi.voxel_options(leaf))
+        cl.close()
+        if ref is None:
+            tripped += 1
+            assert got["passthrough"], (case, kind, leaf)
+            continue
+        passed += 1
+        assert not got["passthrough"], (case, kind, leaf)
+        assert np.array_equal(got["idx"], ref["idx"]) and np.array_equal(got["cnt"], ref["cnt"]), (case, kind, leaf)
+        assert np.array_equal(got["xyz"].view(np.uint32), ref["xyz"].view(np.uint32)), (case, kind, leaf)
+    assert passed >= 10 and tripped >= 10, (passed, tripped)
