@@ -1,5 +1,5 @@
 """Randomised differential test of the CUDA matcher against the C oracle: random shapes, StereoSGBM tuples, modes, batch sizes and
-kernel-selection knobs (results must never depend on the knobs). usage: python tools/fuzz_sgbm.py [cases] [seed]
+kernel-selection knobs (results must never depend on the knobs). usage: python tools/fuzz_sgbm.py [cases] [seed] [max rows, default 70] [max extra width, default 260]
 Prints one line per failure and a summary; exit status 1 on any mismatch. Test infrastructure (uses oracle/)."""
 import os
 import sys
@@ -12,6 +12,8 @@ from stereo_depth_ruler_b200 import capi, synth
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+HMAX = int(sys.argv[3]) if len(sys.argv) > 3 else 70
+WEXTRA = int(sys.argv[4]) if len(sys.argv) > 4 else 260
 rng = np.random.default_rng(seed)
 ctx = capi.Context(0)
 KNOBS = [{}, {"cf_cols": 64}, {"cf_cols": 32}, {"cf_cols": 16}, {"cf_cols": 8}, {"path_hh": 1}, {"path_hh": 0}, {"lr_split": 1}, {"fused_sweep": 0},
@@ -24,8 +26,8 @@ for case in range(N):
     D = 16 * int(rng.choice([1, 2, 3, 4, 5, 6, 8, 8, 8, 10, 12, 16]))
     bs = int(rng.choice([1, 3, 5, 5, 5, 7, 9, 11]))
     minD = int(rng.choice([0, 0, 0, 4, -8, -16, 16]))
-    W = int(rng.integers(D + max(minD, 0) + 2 * bs + 3, D + max(minD, 0) + 2 * bs + 260))
-    H = int(rng.integers(1, 70))
+    W = int(rng.integers(D + max(minD, 0) + 2 * bs + 3, D + max(minD, 0) + 2 * bs + WEXTRA))
+    H = int(rng.integers(1, HMAX))
     cap = int(rng.choice([15, 31, 45, 63, 63, 63]))
     ft = max(cap, 15) | 1
     P1 = int(rng.choice([0, 8 * bs * bs, 8 * 3 * bs * bs, int(rng.integers(1, 400))]))
