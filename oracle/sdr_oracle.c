@@ -255,7 +255,7 @@ static void wta_row(const int16_t* S, int W, int W1, int D, int minD, int minX1,
         for (int d = 0; d < D; d++)
             if (Sp[d] < minS) { minS = Sp[d]; best = d; }
         if (three_way) {
-            /* QUIRK (pinned against cv2 4.13.0, tools/probes/diag3.py: 24 image/parameter cases, 0 differing pixels):
+            /* QUIRK (pinned against cv2 4.13.0, tests/probes/diag3.py: 24 image/parameter cases, 0 differing pixels):
              * computeDisparity3WaySGBM searches the minimum with 8-lane int16 vectors (128-bit universal intrinsics in the
              * pip build). Lane r sees d = r, r+8, ...; an equal value REPLACES the lane's best position (last occurrence
              * per lane), then min_pos() takes the smallest position among the lanes that hold the global minimum.

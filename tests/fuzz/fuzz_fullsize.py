@@ -1,11 +1,11 @@
 """Full-size randomised test of the matcher against cv2.StereoSGBM itself: the launch shapes only big frames reach (all SMs in
 one cooperative launch, many strips, several bands and waves), random tuples / modes / batch sizes at 640x360 ... 1920x1080.
-usage: python tools/fuzz_fullsize.py [cases] [seed]. Test infrastructure (needs cv2)."""
+usage: python tests/fuzz/fuzz_fullsize.py [cases] [seed]. Test infrastructure (needs cv2)."""
 import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import cv2
 import numpy as np
 import torch

@@ -1,12 +1,12 @@
 """Randomised differential test of the whole path per frame (sdr_pipeline_run: SBS frame -> rectify -> matcher -> reproject ->
 VoxelGrid) against the oracle chain, on calibrations scaled down from the ZED 2 one (random sizes), random matcher tuples, batch
-sizes, BGR / NV12 / YUYV input and leaf sizes. usage: python tools/fuzz_pipeline.py [cases] [seed]. Test infrastructure."""
+sizes, BGR / NV12 / YUYV input and leaf sizes. usage: python tests/fuzz/fuzz_pipeline.py [cases] [seed]. Test infrastructure."""
 import copy
 import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import orc
 from stereo_depth_ruler_b200 import capi
@@ -15,7 +15,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 rng = np.random.default_rng(seed)
 ctx = capi.Context(0)
-CAL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "zed2_calibration.yaml")
+CAL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "golden", "zed2_calibration.yaml")
 fails = 0
 t0 = time.time()
 

@@ -1,11 +1,11 @@
 """Randomised differential test of the CUDA matcher against the C oracle: random shapes, StereoSGBM tuples, modes, batch sizes and
-kernel-selection knobs (results must never depend on the knobs). usage: python tools/fuzz_sgbm.py [cases] [seed] [max rows, default 70] [max extra width, default 260]
+kernel-selection knobs (results must never depend on the knobs). usage: python tests/fuzz/fuzz_sgbm.py [cases] [seed] [max rows, default 70] [max extra width, default 260]
 Prints one line per failure and a summary; exit status 1 on any mismatch. Test infrastructure (uses oracle/)."""
 import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import orc
 from stereo_depth_ruler_b200 import capi, synth

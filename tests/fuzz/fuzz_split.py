@@ -1,12 +1,12 @@
 """Randomised differential test of the stripe split of MODE_SGBM_3WAY (BASELINE config 5) against the oracle: random shapes and
 tuples; (a) sdr_sgbm_match_stripes over a random partition of the four stripes + one sdr_sgbm_postfilter, host and device-resident
 buffers; (b) the native split sdr_sgbm_split_* with a random number of parts (all on device 0 when the box has one GPU, spread over
-the GPUs otherwise). usage: python tools/fuzz_split.py [cases] [seed]. Test infrastructure."""
+the GPUs otherwise). usage: python tests/fuzz/fuzz_split.py [cases] [seed]. Test infrastructure."""
 import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from oracle import orc

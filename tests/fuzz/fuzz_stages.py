@@ -1,12 +1,12 @@
 """Randomised differential test of the stages around the matcher against the C oracle: remap (random CV_16SC2 maps incl. far
 out-of-range), BGR2GRAY, half-size INTER_AREA (vs cv2 when importable), median 3x3, filterSpeckles, reprojectImageTo3D (random Q,
 both handleMissingValues), VoxelGrid (random clouds: NaN / inf, duplicates, negative coordinates, points on voxel faces, leaf sizes
-down to the int32-guard passthrough), NV12 / YUYV ingest. usage: python tools/fuzz_stages.py [cases] [seed]. Test infrastructure."""
+down to the int32-guard passthrough), NV12 / YUYV ingest. usage: python tests/fuzz/fuzz_stages.py [cases] [seed]. Test infrastructure."""
 import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import orc
 from stereo_depth_ruler_b200 import capi

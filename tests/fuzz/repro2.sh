@@ -1,4 +1,4 @@
-r() { echo -n "$* => "; timeout 120 python tools/probes/repro_case.py "$@" 2>&1 | tail -1; }
+r() { echo -n "$* => "; timeout 120 python tests/fuzz/repro_case.py "$@" 2>&1 | tail -1; }
 for D in 96 144 160 176 192 208 224 240; do
 for mode in 0 1 2; do
 r 400 32 2 tex 0,$D,5,200,800,1,63,12,0,0,$mode

@@ -1,5 +1,5 @@
 """One matcher call against the oracle, everything from the command line (fuzz-failure triage; a crashed CUDA context is sticky, so
-one process per case): python tools/probes/repro_case.py W H B kind "minD,D,bs,P1,P2,d12,cap,uq,sw,sr,mode" [knob=value ...]"""
+one process per case): python tests/fuzz/repro_case.py W H B kind "minD,D,bs,P1,P2,d12,cap,uq,sw,sr,mode" [knob=value ...]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np

@@ -1,11 +1,11 @@
 import sys
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tools/probes")
+sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests/probes")
 import numpy as np, cv2
 from stereo_depth_ruler_b200 import synth
 from oracle import orc
 import importlib.util
-spec = importlib.util.spec_from_file_location("d3", "/root/repo/tools/probes/diag3.py")
-src = open("/root/repo/tools/probes/diag3.py").read().split("tot = {}")[0]
+spec = importlib.util.spec_from_file_location("d3", "/root/repo/tests/probes/diag3.py")
+src = open("/root/repo/tests/probes/diag3.py").read().split("tot = {}")[0]
 exec(src)
 tot = {}
 for seed in range(1, 7):

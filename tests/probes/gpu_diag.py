@@ -1,7 +1,7 @@
 """GPU-side stage-by-stage comparison of the CUDA SGBM path against the C oracle.
-Debug tool (not a test): python tools/gpu_diag.py  -> gpurun_out/diag.txt"""
+Debug tool (not a test): python tests/probes/gpu_diag.py  -> gpurun_out/diag.txt"""
 import os, sys, time, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import orc
 from stereo_depth_ruler_b200 import capi, synth

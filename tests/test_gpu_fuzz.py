@@ -1,4 +1,4 @@
-"""GPU: short runs of the randomised differential fuzzers (tools/fuzz_*.py) -- each in its own process, because a kernel fault
+"""GPU: short runs of the randomised differential fuzzers (tests/fuzz/fuzz_*.py) -- each in its own process, because a kernel fault
 would poison the CUDA context of the test session. The long runs of the same tools are recorded under profiles/fuzz/."""
 import os
 import subprocess
@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
                                        ("fuzz_stages.py", ["40", "103"]), ("fuzz_pipeline.py", ["16", "104"]),
                                        ("fuzz_split.py", ["16", "105"])])
 def test_fuzzer_finds_nothing(tool, args):
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool)] + args, capture_output=True, text=True, timeout=900)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fuzz", tool)] + args, capture_output=True, text=True, timeout=900)
     tail = "\n".join((r.stdout + r.stderr).strip().splitlines()[-12:])
     assert r.returncode == 0, tail
     assert "0 failures" in r.stdout or "failures none" in r.stdout, tail

@@ -238,7 +238,7 @@ def test_voxelgrid_absurd_leaves_random(ctx, orc):
     """Leaf sizes so small that PCL's int64 index guard wraps around and passes (the reference's literal leaf 0.005 on a millimetre
     cloud is of this kind), or trips: the GPU must take the same branch as the restatement and, when the guard passes, produce the same
     wrapped int32 indices -- including coordinates whose float -> int conversion leaves the int range (x86: INT_MIN). Found by
-    tools/fuzz_stages.py."""
+    tests/fuzz/fuzz_stages.py."""
     from stereo_depth_ruler_b200 import capi
     rng = np.random.default_rng(11)
     passed = tripped = 0

@@ -36,14 +36,14 @@ for mode in (0, 1, 2):
         (131, 3, (0, 16, 5, 600, 2400, 1, 63, 12, 0, 0, mode), "noise"),   # fewer rows than the window
         (50, 1, (0, 16, 3, 216, 864, 1, 63, 0, 0, 0, mode), "noise"),      # single row
         # every D / 64 of the latency-mode chain kernel (k_path_hh_ws: D / 32 values per lane; D = 192 is the odd register count
-        # that tools/fuzz_sgbm.py found broken) and D that are no multiple of 32 or 64
+        # that tests/fuzz/fuzz_sgbm.py found broken) and D that are no multiple of 32 or 64
         (400, 32, (0, 192, 5, 200, 800, 1, 63, 12, 0, 0, mode), "tex"),
         (289, 32, (-16, 192, 5, 200, 800, 5, 63, 0, 0, 0, mode), "tex"),
         (300, 21, (0, 96, 5, 600, 2400, 1, 63, 12, 50, 2, mode), "tex"),
         (330, 18, (0, 160, 3, 72, 288, 1, 63, 10, 0, 0, mode), "tex"),
         (380, 12, (0, 240, 5, 600, 2400, 1, 63, 12, 0, 0, mode), "noise"),
         # saturated cost sums (large window and P2): a pixel whose S is SHRT_MAX at every disparity keeps cv2's bestDisp = -1
-        # (MODE_SGBM / MODE_HH: invalid) and never enters disp2 (found by tools/fuzz_sgbm.py)
+        # (MODE_SGBM / MODE_HH: invalid) and never enters disp2 (found by tests/fuzz/fuzz_sgbm.py)
         (196, 16, (16, 128, 9, 0, 7776, 1, 63, 0, 100, 4, mode), "tex"),
         (196, 16, (0, 128, 9, 0, 7776, 1, 63, 0, 0, 0, mode), "noise"),
         # the 64-column cost tile does not fit shared memory (233 KB): 32-column tiles
