@@ -420,6 +420,8 @@ class Rectifier:
 
 def remap_with_maps(ctx, src, map1, map2):
     H, W = map2.shape
+    if tuple(map1.shape) != (H, W, 2):      # the ABI takes bare pointers sized by the destination: check here
+        raise SdrError(SDR_ESIZE, "remap: map1 must be [H][W][2] and map2 [H][W] of the same H x W")
     ch = 1 if src.ndim == 2 else src.shape[2]
     dst = np.empty((H, W) if ch == 1 else (H, W, ch), np.uint8)
     si, _ = as_image(src); di, _ = as_image(dst)
