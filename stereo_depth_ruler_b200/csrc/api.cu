@@ -128,6 +128,33 @@ int sdr_check_image(sdr_ctx* ctx, const sdr_image* im, int channels, int elem_si
     if (im->step_bytes < (size_t)im->cols * channels * elem_size) return SDR_FAIL(ctx, SDR_ESIZE, "%s: step too small", what);
     if (im->mem != SDR_MEM_HOST && im->mem != SDR_MEM_PINNED && im->mem != SDR_MEM_DEVICE)
         return SDR_FAIL(ctx, SDR_EINVAL, "%s: bad mem kind %d", what, im->mem);
+    if (im->mem == SDR_MEM_DEVICE) {
+        // Device images are used in place by the kernels of ctx->device: the pointer must be device memory, and when it lives on
+        // another GPU (a frame pool on GPU 0 read by the workers of a multi-GPU stream) that GPU must be a peer -- enabled here on
+        // first use (NVLink / PCIe P2P) or refused, never a fault inside a kernel.
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, im->data) != cudaSuccess) {
+            cudaGetLastError();
+            return SDR_FAIL(ctx, SDR_EINVAL, "%s: not a CUDA pointer", what);
+        }
+        if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)
+            return SDR_FAIL(ctx, SDR_EINVAL, "%s: mem says device memory, the pointer is not", what);
+        if (at.type == cudaMemoryTypeDevice && at.device != ctx->device && at.device >= 0 && at.device < 64 &&
+            !(ctx->peer_ok >> at.device & 1ull)) {
+            int can = 0;
+            cudaSetDevice(ctx->device);
+            if (cudaDeviceCanAccessPeer(&can, ctx->device, at.device) != cudaSuccess || !can) {
+                cudaGetLastError();
+                return SDR_FAIL(ctx, SDR_EINVAL, "%s: the image lives on GPU %d, which GPU %d cannot access (no peer access)", what, at.device,
+                                ctx->device);
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+            cudaGetLastError();
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return SDR_FAIL(ctx, SDR_ECUDA, "%s: cudaDeviceEnablePeerAccess(%d) failed: %s", what, at.device, cudaGetErrorString(e));
+            ctx->peer_ok |= 1ull << at.device;
+        }
+    }
     return SDR_OK;
 }
 

@@ -19,6 +19,7 @@ struct sdr_ctx {
     int sm_count = 148;
     size_t smem_optin = 0;
     cudaEvent_t wait_ev = nullptr;   // cudaEventBlockingSync: host waits sleep instead of spinning
+    unsigned long long peer_ok = 0;  // bit d: peer access from this device to device d is enabled (images that live on another GPU)
 };
 
 // Host wait for everything queued on the ctx stream. Sleeps on a blocking-sync event: with several handles per GPU and

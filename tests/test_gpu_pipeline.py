@@ -131,3 +131,30 @@ def test_stream_runner_shards_frames_over_devices(ctx, orc, calib_path):
     assert sum(st.per_device[:len(devices)]) == n_frames and st.frames_per_s > 0
     if len(devices) > 1:
         assert len({v[0][0] for v in seen.values()}) > 1                   # more than one GPU took frames
+
+
+def test_device_image_on_another_gpu_is_a_peer_access_or_an_error(ctx, calib_path):
+    """A device-resident frame pool that lives on GPU 0 read by a worker on GPU 1 (found by tests/fuzz/fuzz_stream.py on a 2-GPU
+    box: the kernels used the pointer in place and faulted): peer access is enabled on first use, or the call is refused."""
+    import torch
+    from stereo_depth_ruler_b200 import capi
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    calib = capi.load_calibration(calib_path)
+    args = (0, 64, 5, 600, 2400, 1, 63, 12, 100, 2, 0)
+    vox = capi.voxel_options(5.0, drop_invalid=True, z_max=Z_MAX)
+    frames = np.stack([_raw_sbs(51), _raw_sbs(53)])
+    pool0 = torch.from_numpy(frames).to("cuda:0")
+    torch.cuda.synchronize()
+    s = capi.Stream([0, 1], 1, calib, capi.make_params(*args), vox, handle_missing=True, batch=1, download_clouds=False)
+    st = s.process_pool(8, pool0)
+    assert st.frames == 8 and st.per_device[0] + st.per_device[1] == 8
+    s.close()
+    # one handle on GPU 1 reading GPU 0's memory directly: same map as from host memory
+    c1 = capi.Context(1)
+    p = capi.Pipeline(c1, calib, capi.make_params(*args), vox, handle_missing=True, batch=1)
+    d_host, d_peer = [np.empty((720, 1280), np.int16)], [np.empty((720, 1280), np.int16)]
+    p.run([frames[0]], disp=d_host)
+    p.run([pool0[0]], disp=d_peer)
+    assert np.array_equal(d_host[0], d_peer[0])
+    p.close(); c1.close()
