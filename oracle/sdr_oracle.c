@@ -113,10 +113,12 @@ ORC_API int orc_init_rectify_map(const double* K, const double* dist, const doub
             double yd = y * kr + p1 * (r2 + 2 * y2) + p2 * _2xy;
             double u = fx * xd + cx;
             double v = fy * yd + cy;
-            int iu = (int)lrint(u * 32.0); /* round-half-even, as cvRound */
-            int iv = (int)lrint(v * 32.0);
-            map1[((size_t)i * W + j) * 2 + 0] = (int16_t)(iu >> 5);
-            map1[((size_t)i * W + j) * 2 + 1] = (int16_t)(iv >> 5);
+            /* saturate_cast<int>(double) = cvRound: round-half-even (cvtsd2si), INT_MIN when the value leaves the int range;
+             * the integer part is then saturate_cast<short> (pinned by tests/fuzz/fuzz_oracle_vs_cv2.py on absurd calibrations) */
+            int iu = fabs(u * 32.0) < 2147483648.0 ? (int)lrint(u * 32.0) : INT32_MIN;
+            int iv = fabs(v * 32.0) < 2147483648.0 ? (int)lrint(v * 32.0) : INT32_MIN;
+            map1[((size_t)i * W + j) * 2 + 0] = sat16(iu >> 5);
+            map1[((size_t)i * W + j) * 2 + 1] = sat16(iv >> 5);
             map2[(size_t)i * W + j] = (uint16_t)((iv & 31) * 32 + (iu & 31));
         }
     }

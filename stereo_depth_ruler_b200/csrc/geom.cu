@@ -35,8 +35,10 @@ __device__ __forceinline__ void eval_map(const MapParams& m, int j, int i, int& 
                                 __dmul_rn(m.p2, _2xy));
     const double u = __dadd_rn(__dmul_rn(m.fx, xd), m.cx);
     const double v = __dadd_rn(__dmul_rn(m.fy, yd), m.cy);
-    const int iu = __double2int_rn(__dmul_rn(u, 32.0));  // round-half-even == cvRound
-    const int iv = __double2int_rn(__dmul_rn(v, 32.0));
+    // round-half-even == cvRound; a value beyond the int range is INT_MIN there (cvtsd2si), where the GPU's conversion saturates
+    const double u32 = __dmul_rn(u, 32.0), v32 = __dmul_rn(v, 32.0);
+    const int iu = fabs(u32) < 2147483648.0 ? __double2int_rn(u32) : (int)0x80000000;
+    const int iv = fabs(v32) < 2147483648.0 ? __double2int_rn(v32) : (int)0x80000000;
     // CV_16SC2 storage wraps to int16 (saturate_cast in OpenCV; identical while |coord| < 32768)
     sx = max(min(iu >> 5, 32767), -32768);
     sy = max(min(iv >> 5, 32767), -32768);

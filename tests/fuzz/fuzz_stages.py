@@ -110,5 +110,30 @@ for case in range(N):
     check("nv12", np.array_equal(capi.ingest_to_bgr(ctx, capi.PIX_NV12, nv12), orc.ingest_to_bgr(1, nv12)), "case %d" % case)
     yuyv = rng.integers(0, 256, size=(He, We, 2)).astype(np.uint8)
     check("yuyv", np.array_equal(capi.ingest_to_bgr(ctx, capi.PIX_YUYV, yuyv), orc.ingest_to_bgr(2, yuyv)), "case %d" % case)
+    # ---- rectification maps of a random (sometimes extreme) calibration ----
+    if case % 3 == 0:
+        Wc, Hc = int(rng.integers(40, 300)), int(rng.integers(30, 200))
+        c = capi.Calibration()
+        c.image_width, c.image_height = Wc, Hc
+        sc = float(rng.choice([1.0, 1.0, 3.0]))
+        mats = {}
+        for side, (Kn, dn, Rn, Pn) in enumerate((("K_left", "dist_left", "R1", "P1"), ("K_right", "dist_right", "R2", "P2"))):
+            K = np.array([[rng.uniform(0.5, 1.5) * Wc, 0, Wc / 2 + rng.uniform(-10, 10)], [0, rng.uniform(0.5, 1.5) * Wc, Hc / 2 + rng.uniform(-10, 10)], [0, 0, 1]])
+            dist = np.array([rng.normal(0, 0.1) * sc, rng.normal(0, 0.05) * sc, rng.normal(0, 0.001), rng.normal(0, 0.001), rng.normal(0, 0.01) * sc])
+            rv = rng.normal(0, 0.02, size=3)
+            th = np.linalg.norm(rv); kx = rv / th
+            Kx = np.array([[0, -kx[2], kx[1]], [kx[2], 0, -kx[0]], [-kx[1], kx[0], 0]])
+            R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+            P = np.hstack([K * rng.uniform(0.9, 1.1), np.array([[rng.uniform(-100, 0)], [0], [0]])]); P[2, 2] = 1.0
+            for name, m in ((Kn, K), (dn, dist), (Rn, R), (Pn, P)):
+                getattr(c, name)[:] = list(np.asarray(m, np.float64).ravel())
+            mats[side] = (K, dist.reshape(1, 5), R, P)
+        c.present = 0xFFFFFFFF
+        rect = capi.Rectifier(ctx, c)
+        for eye in (0, 1):
+            g1, g2 = rect.maps(eye)
+            o1, o2 = orc.init_rectify_map(*mats[eye], (Wc, Hc))
+            check("rectify_map", np.array_equal(g1, o1) and np.array_equal(g2, o2), "case %d eye %d %dx%d sc %g" % (case, eye, Wc, Hc, sc))
+        rect.close()
 print("fuzz_stages: %d cases, seed %d, %.0f s; runs %s; failures %s" % (N, seed, time.time() - t0, runs, fails or "none"))
 sys.exit(1 if fails else 0)
