@@ -41,6 +41,9 @@ typedef enum sdr_status {
     SDR_EVOXEL_OVERFLOW = 6  /* non-fatal: PCL's int32 voxel-index guard tripped, cloud passed through */
 } sdr_status;
 
+/* SDR_MEM_DEVICE images are used in place by the kernels of the handle's device. They may live on another GPU of the box when
+ * that GPU is a peer (NVLink / PCIe P2P): peer access is enabled on first use; otherwise, or when the pointer is not device
+ * memory at all, the call returns SDR_EINVAL (never a fault inside a kernel). */
 typedef enum sdr_mem { SDR_MEM_HOST = 0, SDR_MEM_PINNED = 1, SDR_MEM_DEVICE = 2 } sdr_mem;
 
 /* Layout-compatible with the fields of cv::Mat the reference relies on
