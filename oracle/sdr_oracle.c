@@ -500,10 +500,16 @@ static int sgbm_3way(const uint8_t* left, size_t lstep, const uint8_t* right, si
                     Sp[d] = sat16(leftb[(size_t)x * D + d] + rc[d] + top[(size_t)x * D + d]);
                 int16_t* t = rp; rp = rc; rc = t;
             }
-            if (y >= dst_off) {
-                if (Svol_out) memcpy(Svol_out + row * y, S, row * sizeof(int16_t));
-                wta_row(S, W, W1, D, minD, minX1, maxX1, uq, d12, 1, disp + (size_t)y * dstep_elems, &rs);
-            }
+            /* QUIRK of tiny frames (pinned against cv2 4.13.0 over every height 1 ... 39 and window 1 ... 11,
+             * tests/fuzz/fuzz_oracle_vs_cv2.py): when s * stripe_sz - overlap is negative OpenCV clamps the first SOURCE row of the
+             * stripe to 0 but keeps counting OUTPUT rows from the unclamped start, so source row y lands in row y - shift and the
+             * last `shift` rows of the stripe's range are never written (they keep the invalid value). */
+            const int ustart = s * stripe_sz - overlap;
+            const int shift = (s > 0 && ustart < 0) ? -ustart : 0;
+            const int out_row = y - shift;
+            if (Svol_out && y >= dst_off) memcpy(Svol_out + row * y, S, row * sizeof(int16_t));   /* (indexed by source row) */
+            if (out_row >= dst_off)
+                wta_row(S, W, W1, D, minD, minX1, maxX1, uq, d12, 1, disp + (size_t)out_row * dstep_elems, &rs);
         }
     }
     free(hs); free(pix); free(C); free(top); free(topMin); free(leftb); free(S); free(rbuf); free(zero);

@@ -22,6 +22,7 @@ namespace {
 
 struct Seg {
     int src_start, src_end, dst_start, crow0;
+    int shift;   // MODE_SGBM_3WAY on tiny frames: source row y of this stripe lands in output row y - shift (see make_geom)
 };
 
 struct Geom {
@@ -1672,9 +1673,21 @@ __global__ void __launch_bounds__(256) k_lrcheck(Geom g, const int16_t* __restri
     extern __shared__ uint32_t keys[];
     const int y = y0 + blockIdx.x, b = blockIdx.z;
     const int INV = (g.minD - 1) * 16;
+    int16_t* orow = (int16_t*)((uint8_t*)out + (size_t)b * oframe + (size_t)y * opitch);
+    // output row y holds the matcher's row ys (ys != y only for the shifted stripes of tiny MODE_SGBM_3WAY frames, Seg::shift)
+    int ys = y;
+    for (int i = 0; i < g.nseg; i++)
+        if (g.seg[i].shift > 0 && y >= g.seg[i].dst_start && y < g.seg[i].src_end) {
+            ys = y + g.seg[i].shift;
+            if (ys >= g.seg[i].src_end) ys = -1;   // never written by OpenCV: stays invalid
+        }
+    if (ys < 0) {   // (uniform over the block)
+        for (int x = threadIdx.x; x < g.W; x += blockDim.x) orow[x] = (int16_t)INV;
+        return;
+    }
     for (int x = threadIdx.x; x < g.W; x += blockDim.x) keys[x] = 0xFFFFFFFFu;
     __syncthreads();
-    const uint32_t* wr = wta + ((size_t)b * g.H + y) * g.W1;
+    const uint32_t* wr = wta + ((size_t)b * g.H + ys) * g.W1;
     for (int x = threadIdx.x; x < g.W1; x += blockDim.x) {
         const uint32_t w = wr[x];
         if (w != 0xFFFFFFFFu) {
@@ -1685,8 +1698,7 @@ __global__ void __launch_bounds__(256) k_lrcheck(Geom g, const int16_t* __restri
         }
     }
     __syncthreads();
-    const int16_t* dr = dispraw + ((size_t)b * g.H + y) * g.W;
-    int16_t* orow = (int16_t*)((uint8_t*)out + (size_t)b * oframe + (size_t)y * opitch);
+    const int16_t* dr = dispraw + ((size_t)b * g.H + ys) * g.W;
     for (int x = threadIdx.x; x < g.W; x += blockDim.x) {
         int d1 = INV;
         if (x >= g.minX1 && x < g.maxX1) {
@@ -2170,6 +2182,11 @@ static void make_geom(const sdr_sgbm_params& p, int W, int H, Geom& g) {
         for (int s = 0; s < nstripes; s++) {
             Seg sg;
             sg.src_start = s == 0 ? 0 : std::max(std::min(s * stripe_sz - overlap, H), 0);
+            // cv2 quirk (pinned by tests/fuzz/fuzz_oracle_vs_cv2.py over every height 1 ... 39 and window 1 ... 11): when a stripe's
+            // warm-up start s * stripe_sz - overlap is negative (frames of <= 4 * (blockSize / 2 + 1) rows) OpenCV clamps the first
+            // SOURCE row to 0 but keeps counting OUTPUT rows from the unclamped start: source row y is written to row y - shift, and
+            // the last `shift` rows of the stripe's range are never written (they stay invalid). k_lrcheck applies the mapping.
+            sg.shift = (s > 0 && s * stripe_sz - overlap < 0) ? -(s * stripe_sz - overlap) : 0;
             sg.dst_start = s * stripe_sz;
             sg.src_end = std::min((s + 1) * stripe_sz, H);
             if (sg.dst_start >= sg.src_end) continue;  // empty stripe (tiny images)
@@ -2181,7 +2198,7 @@ static void make_geom(const sdr_sgbm_params& p, int W, int H, Geom& g) {
     } else {
         g.SW2 = g.SH2 = (p.blockSize > 0 ? p.blockSize : 5) / 2;
         g.nseg = 1;
-        g.seg[0] = Seg{0, H, 0, 0};
+        g.seg[0] = Seg{0, H, 0, 0, 0};
         g.crows = H;
     }
 }
