@@ -15,3 +15,11 @@ def test_oracle_equals_cv2_on_random_inputs():
                        timeout=600)
     tail = "\\n".join((r.stdout + r.stderr).strip().splitlines()[-10:])
     assert r.returncode == 0 and "failures none" in r.stdout, tail
+
+
+def test_voxelgrid_restatements_agree_on_random_clouds():
+    """The C and the numpy restatement of pcl::VoxelGrid (written independently) on random clouds, absurd leaves included."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fuzz", "fuzz_voxel_c_vs_numpy.py"), "150", "202"], capture_output=True, text=True,
+                       timeout=600)
+    tail = "\n".join((r.stdout + r.stderr).strip().splitlines()[-10:])
+    assert r.returncode == 0 and " 0 failures" in r.stdout, tail
